@@ -1,0 +1,180 @@
+/* vecvad.h -- C ABI of libvecvad.so, the B200 (sm_100a) implementation of the VEC_VAD hot path.
+ *
+ * Plain C: raw device pointers, explicit sizes, a cudaStream_t passed as void*, int status.
+ * The library never allocates device memory behind the caller's back: every buffer
+ * (parameters, gradients, workspace, outputs) is owned by the caller (PyTorch in this repo,
+ * see vec_vad_b200/_lib.py) and handed in as a pointer.  Every entry point returns 0 on
+ * success and a negative code on failure; vecvad_last_error() gives the message (the reference
+ * FFI printed and aborted instead: correlation_cuda_kernel.cu:362-368, correlation_cuda.c:87-89).
+ *
+ * Two groups of entry points:
+ *   (1) the FlowNet2 ops, replacing the reference's cffi symbols one for one
+ *         Correlation_forward_cuda / _backward_cuda   (ops/correlation/src/correlation_cuda.h:1-17)
+ *         Resample2d_cuda_forward / _backward         (ops/resample2d/src/Resample2d_cuda.h:1-3)
+ *         ChannelNorm_cuda_forward / _backward        (ops/channelnorm/src/ChannelNorm_cuda.h:1-3)
+ *   (2) the completion-UNet set (model/unet.py:73-652) + train-step body (train.py:383-402),
+ *       which in the reference is PyTorch/cuDNN called from Python: the binding surface is the
+ *       nn.Module API (vec_vad_b200/unet.py); these are the native calls underneath it.
+ */
+#ifndef VECVAD_H_
+#define VECVAD_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VECVAD_ABI_VERSION 1
+#define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
+#define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
+#define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
+
+typedef void *vecvad_stream;  /* cudaStream_t */
+
+int vecvad_abi_version(void);
+const char *vecvad_last_error(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (1) FlowNet2 ops.  All tensors are contiguous NCHW fp32 on the current device (the reference
+ * asserts contiguity: functions/correlation.py:17-18, functions/resample2d.py:9-10).
+ * Unlike the reference (which resizes + zero-fills tensors it is handed, correlation_cuda.c:36-42)
+ * the caller allocates the output; vecvad_correlation_out_shape() gives its size
+ * (shape rule: correlation_cuda.c:25-34).  No padded NHWC scratch copies (rInput1/rInput2) exist.
+ * ------------------------------------------------------------------------------------------ */
+int vecvad_correlation_out_shape(int in_h, int in_w, int pad_size, int kernel_size, int max_displacement,
+                                 int stride1, int stride2, int *out_c, int *out_h, int *out_w);
+
+/* replaces Correlation_forward_cuda (correlation_cuda.c:11-93; kernels correlation_cuda_kernel.cu:10-106).
+ * out[n,tc,y,x] = 1/(k*k*C) * sum_{j,i,c} in1[n,c,y1+j,x1+i] * in2[n,c,y1+tj*s2+j,x1+ti*s2+i] (zero padded). */
+int vecvad_correlation_forward(const float *in1, const float *in2, float *out, int batch, int channels, int in_h, int in_w,
+                               int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
+                               int corr_type_multiply, vecvad_stream stream);
+
+/* replaces Correlation_backward_cuda (correlation_cuda.c:95-180; kernels :108-290). grad_in1/2 are fully written. */
+int vecvad_correlation_backward(const float *in1, const float *in2, const float *grad_out, float *grad_in1, float *grad_in2,
+                                int batch, int channels, int in_h, int in_w, int pad_size, int kernel_size,
+                                int max_displacement, int stride1, int stride2, int corr_type_multiply, vecvad_stream stream);
+
+/* replaces Resample2d_cuda_forward (Resample2d_kernel.cu:20-66,188-206): border-clamped bilinear warp.
+ * img [B,C,H,W], flow [B,2,Ho,Wo] -> out [B,C,Ho,Wo] (reference allocates out with the flow's H,W:
+ * functions/resample2d.py:16-19). */
+int vecvad_resample2d_forward(const float *img, const float *flow, float *out, int batch, int channels, int img_h, int img_w,
+                              int out_h, int out_w, int kernel_size, vecvad_stream stream);
+
+/* replaces Resample2d_cuda_backward (Resample2d_kernel.cu:69-186,208-238). grad_img is zeroed then scatter-added. */
+int vecvad_resample2d_backward(const float *img, const float *flow, const float *grad_out, float *grad_img, float *grad_flow,
+                               int batch, int channels, int img_h, int img_w, int out_h, int out_w, int kernel_size,
+                               vecvad_stream stream);
+
+/* replaces ChannelNorm_cuda_forward (ChannelNorm_kernel.cu:19-51): out[b,0,y,x] = sqrt(sum_c in^2). */
+int vecvad_channelnorm_forward(const float *in, float *out, int batch, int channels, int h, int w, int norm_deg,
+                               vecvad_stream stream);
+
+/* replaces ChannelNorm_cuda_backward (ChannelNorm_kernel.cu:54-81): g*x/(out+1e-9). */
+int vecvad_channelnorm_backward(const float *in, const float *out, const float *grad_out, float *grad_in, int batch,
+                                int channels, int h, int w, int norm_deg, vecvad_stream stream);
+
+/* fused img0 - warp(img1, flow) and its channel norm (FlowNet2 call sites flownet2.py:79-81,93-95,108-115):
+ * warped [B,C,H,W], diff [B,C,H,W] (may be NULL), norm [B,1,H,W] (may be NULL). */
+int vecvad_warp_diff_norm(const float *img0, const float *img1, const float *flow, float *warped, float *diff, float *norm,
+                          int batch, int channels, int h, int w, vecvad_stream stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (2) Completion-UNet set.
+ *
+ * A "net" is G independent UNets that read the same 5-frame cube batch x[B, 3*tot_raw, S, S]
+ * (NCHW fp32, channel = 3*t+c; vad_datasets.py:159-160).  UNet g sees the cube with frame
+ * erase_frame[g] dropped (padding=0, model/unet.py:183) or zeroed (padding=1, :180-181) and
+ * regresses either that raw frame (3 channels) or a flow frame of x_of (2 channels).
+ *
+ * Parameters live in ONE flat fp32 buffer owned by the caller, laid out per UNet "slot" with a
+ * uniform stride; inside a slot every tensor keeps PyTorch's own layout (Conv2d [Cout,Cin,3,3],
+ * ConvTranspose2d [Cin,Cout,3,3]) at the offsets given below, so nn.Parameter views alias it.
+ * Gradients use a second buffer with the identical layout; BatchNorm running statistics a third.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct vecvad_net_config {
+    int n_unets;                              /* G: UNets executed per forward (<= VECVAD_MAX_UNETS)            */
+    int features_root;                        /* nf (config.cfg:62); multiple of 16                              */
+    int tot_raw_num;                          /* frames per cube (5)                                             */
+    int patch;                                /* S: patch size (32); multiple of 8                               */
+    int padding;                              /* 0: erased frame dropped, 1: erased frame zeroed                 */
+    int param_slot[VECVAD_MAX_UNETS];         /* which slot of the flat buffers UNet g uses                      */
+    int erase_frame[VECVAD_MAX_UNETS];        /* frame removed from UNet g's input                               */
+    int out_channels[VECVAD_MAX_UNETS];       /* 3 (raw) or 2 (flow)                                             */
+    int target_is_flow[VECVAD_MAX_UNETS];     /* 0: target = x[:, 3*target_index ...]; 1: x_of[:, 2*target_index]*/
+    int target_index[VECVAD_MAX_UNETS];
+    int out_slot[VECVAD_MAX_UNETS];           /* position inside raw_out (3 ch each) or of_out (2 ch each)       */
+    int64_t slot_param_stride;                /* floats between consecutive slots in params / grads              */
+    int64_t slot_stat_stride;                 /* floats between consecutive slots in the running-stat buffer     */
+    /* offsets (floats) inside one slot */
+    int64_t conv_w[VECVAD_N_UNITS], conv_b[VECVAD_N_UNITS], bn_w[VECVAD_N_UNITS], bn_b[VECVAD_N_UNITS];
+    int64_t up_w[VECVAD_N_UPS], up_b[VECVAD_N_UPS];
+    int64_t out_w, out_b;
+    int64_t run_mean[VECVAD_N_UNITS], run_var[VECVAD_N_UNITS];
+    int use_tensor_cores;                     /* 1: tcgen05 kind::tf32 implicit-GEMM tiles; 0: fp32 SIMT tiles   */
+} vecvad_net_config;
+
+typedef struct vecvad_net vecvad_net;
+
+int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out);
+void vecvad_net_destroy(vecvad_net *net);
+
+/* bytes of device workspace needed for a batch of `batch` cubes (activations saved for backward,
+ * gradient scratch, re-laid-out weights). */
+int vecvad_net_workspace_bytes(const vecvad_net *net, int batch, int64_t *bytes);
+
+/* bind caller-owned device buffers. running_stats may be NULL only if the net is never run in
+ * training mode and never in eval mode (i.e. never). workspace must be 256-byte aligned. */
+int vecvad_net_bind(vecvad_net *net, float *params, float *grads, float *running_stats, void *workspace,
+                    int64_t workspace_bytes, int max_batch);
+
+/* forward.  x [B,3*tot_raw,S,S], x_of [B,2*T_of,S,S] (may be NULL when no UNet targets flow).
+ * raw_out [B,3*n_raw_out,S,S] / of_out [B,2*n_of_out,S,S]: UNet g writes its channels at out_slot[g].
+ * training=1: batch statistics, running stats updated (momentum 0.1, unbiased var; nn.BatchNorm2d defaults),
+ *             activations kept for vecvad_net_backward.   training=0: running statistics.
+ * If sse (device, [G][B] floats) is non-NULL the per-cube sum of squared error against the targets is written
+ * (train.py:414-427 scoring), and -- when training -- d(loss)/d(out) is staged for vecvad_net_backward with
+ *   loss = lambda_raw * mean((raw_tgt-raw_out)^2) + lambda_of * mean((of_tgt-of_out)^2)      (train.py:385-392). */
+int vecvad_net_forward(vecvad_net *net, const float *x, const float *x_of, int x_of_channels, int batch, int training,
+                       float *raw_out, int raw_out_channels, float *of_out, int of_out_channels, float *sse,
+                       float lambda_raw, float lambda_of, vecvad_stream stream);
+
+/* backward of the last training forward.  grad_raw_out/grad_of_out: NCHW gradients wrt the outputs, or both
+ * NULL to use the fused MSE gradient staged by vecvad_net_forward(..., sse != NULL).
+ * Writes (overwrites) every gradient of the executed UNets into the bound `grads` buffer. */
+int vecvad_net_backward(vecvad_net *net, const float *grad_raw_out, const float *grad_of_out, vecvad_stream stream);
+
+/* losses[0] = mean raw MSE, losses[1] = mean flow MSE (0 if no flow UNet) from the sse buffer of the last forward. */
+int vecvad_net_losses(vecvad_net *net, const float *sse, int batch, float *losses, vecvad_stream stream);
+
+/* torch.optim.Adam semantics (train.py:376: lr 1e-3, betas (0.9,0.999), eps 1e-7, weight_decay 0) on flat buffers.
+ * `step` is the 1-based step count used for bias correction.  grad_scale multiplies g first (1/world_size after a
+ * summing all-reduce). */
+int vecvad_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                     float beta2, float eps, float weight_decay, int step, float grad_scale, vecvad_stream stream);
+
+/* debug / test facility: copy an internal workspace buffer (device to device) into dst.  kind: 0 X0, 1 Z[u], 2 A[u] (even u),
+ * 3 CAT[k], 4 PL[k], 5 X4, 6 UU[k], 7 dCAT[k], 8 GA, 9 GB, 10 DOUT, 11 Wf[u], 12 dWf[u], 13 tWf[k], 14 tdW[k].
+ * Buffers are grouped NHWC [G][B*H*W][C] of the last forward; *n_floats receives the element count copied. */
+int vecvad_net_debug_read(vecvad_net *net, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
+                          vecvad_stream stream);
+
+/* ---- single ops on NHWC tensors, exported for unit tests and for profiling one kernel at a time ---- */
+
+/* 3x3 pad-1 convolution as implicit GEMM.  in [B,H,W,cin] (row stride ld_in), w [cout,cin,3,3] PyTorch layout,
+ * out [B,H,W,cout] raw (pre-BN) values; stats[2*cout] (double) receives per-channel sum and sum of squares
+ * (may be NULL).  scratch: >= 9*cout*cin floats. use_tc selects the tcgen05 path. */
+int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
+                           float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream);
+
+/* cube staging: uint8 cubes [N,T,S,S,3] (+ float flow [N,T_of,S,S,2]) -> x [N,3T,S,S] float /255, x_of [N,2*T_of,S,S]
+ * == cube_to_train_dataset + ToTensor + collate (vad_datasets.py:130-168). */
+int vecvad_cubes_to_tensors(const uint8_t *raw, const float *flow, float *x, float *x_of, int n, int t_raw, int t_of, int patch,
+                            vecvad_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECVAD_H_ */

@@ -1,0 +1,70 @@
+// Shared declarations for libvecvad.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "vecvad.h"
+
+int vv_set_err(int code, const char *fmt, ...);
+
+#define VV_CK(call)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t e_ = (call);                                                                           \
+        if (e_ != cudaSuccess)                                                                             \
+            return vv_set_err(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
+    } while (0)
+#define VV_CKL() VV_CK(cudaGetLastError())
+#define VV_REQUIRE(cond, ...)                          \
+    do {                                               \
+        if (!(cond)) return vv_set_err(-1, __VA_ARGS__); \
+    } while (0)
+
+static inline int vv_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// Implicit-GEMM problem descriptions shared by the SIMT (fp32) and tcgen05 (tf32) tile kernels.
+// Activations are NHWC fp32, "grouped": [G][B*H*W][ld] with a uniform group stride, so the G
+// independent UNets of a net run in one launch (blockIdx.z = g).
+// ---------------------------------------------------------------------------------------------
+struct VvTaps {
+    int n;
+    int dy[9];
+    int dx[9];
+};
+
+// out[m, n] = bias[n] + sum_t sum_k A[shift(m, t), k] * Wt[t][n][k]
+struct VvIGemm {
+    const float *A;     long long a_gs;  int lda, a_coff, a_s2d;   // a_s2d: A is the space-to-depth view of a [B,2H,2W,Kt/4] tensor
+    int Kt;                                                        // K per tap (multiple of 16)
+    int B, H, W;                                                   // logical pixel grid
+    const float *Wt;    long long w_gs;                            // [ntaps][N][Kt]
+    VvTaps taps;
+    int N;                                                         // multiple of 16
+    float *O;           long long o_gs;  int ldo, o_coff, o_d2s;   // o_d2s: N = 4*Co, pixel-shuffled into a [B,2H,2W,*] tensor
+    const float *bias;  long long bias_gs;                         // nullable; indexed by n (or co when o_d2s)
+    double *stats;      long long stats_gs;                        // nullable; [2][N] column sum / sum of squares
+    int G;
+};
+
+// dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]
+struct VvWGrad {
+    const float *A;     long long a_gs;  int lda, a_coff;
+    int Kt;
+    int B, H, W;
+    const float *Gd;    long long g_gs;  int ldg, g_coff, g_s2d;   // g_s2d: Gd is the space-to-depth view of a [B,2H,2W,N/4] tensor
+    int N;
+    VvTaps taps;
+    float *dW;          long long dw_gs;                           // [ntaps][N][Kt], pre-zeroed, atomically accumulated
+    int G;
+};
+
+int vv_launch_igemm_simt(const VvIGemm &p, cudaStream_t st);
+int vv_launch_wgrad_simt(const VvWGrad &p, cudaStream_t st);
+// tcgen05 (kind::tf32) tiles; return -3 if the shape is not supported by the tensor-core path.
+int vv_launch_igemm_tc(const VvIGemm &p, cudaStream_t st);
+int vv_launch_wgrad_tc(const VvWGrad &p, cudaStream_t st);
+bool vv_igemm_tc_supported(const VvIGemm &p);
+bool vv_wgrad_tc_supported(const VvWGrad &p);

@@ -1,0 +1,560 @@
+// The completion-UNet set engine: plans the workspace, sequences the kernels of one forward /
+// backward over G independent UNets (grouped launches), behind the C ABI of include/vecvad.h.
+//
+// Reference data flow restated: model/unet.py:172-267 (SelfCompleteNet4.forward), :410-556
+// (SelfCompleteNetFull.forward), :619-652 (SelfCompleteNet1raw1of.forward); one UNet = inc -> down x3
+// -> up x3 -> outc (model/unet.py:187-196); loss + backward = train.py:385-402.
+#include <new>
+
+#include "unet_kernels.h"
+
+static thread_local char g_err[768] = "";
+
+int vv_set_err(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+extern "C" const char *vecvad_last_error(void) { return g_err; }
+extern "C" int vecvad_abi_version(void) { return VECVAD_ABI_VERSION; }
+
+namespace {
+
+struct View {           // grouped NHWC view: element (g, m, c) at p + g*gs + m*ld + coff + c
+    float *p;
+    long long gs;
+    int ld, coff, C, H;
+};
+
+constexpr int NU = VECVAD_N_UNITS;
+constexpr int NT = VECVAD_N_UPS;
+
+}  // namespace
+
+struct vecvad_net {
+    vecvad_net_config cfg;
+    int G, F, S, T, cin_real, cinp;
+    VvIntG slot, erase, outc, isflow, tidx, oslot;
+    int n_raw_out, n_of_out;
+    // unit geometry: conv unit u maps C -> N at resolution H
+    int uC[NU], uCp[NU], uN[NU], uH[NU];
+    int tCi[NT], tCo[NT], tH[NT];          // transposed convs: Ci -> Co, input resolution tH
+    // bound buffers
+    float *params, *grads, *running;
+    char *ws;
+    int64_t ws_bytes;
+    int maxB;
+    // workspace sub-buffers (float offsets resolved to pointers at bind time)
+    float *X0, *Z[NU], *A[NU], *CAT[3], *PL[3], *X4, *UU[3], *dCAT[3], *GA, *GB, *DOUT;
+    float *Wf[NU], *Wd[NU], *vec[NU], *save[NU], *tWf[NT], *tWd[NT], *tvec[NT];
+    float *dWf[NU], *tdW[NT];
+    double *stats[NU], *bsums[NU];
+    char *zero_fwd;  size_t zero_fwd_bytes;   // BN statistics accumulators
+    char *zero_bwd;  size_t zero_bwd_bytes;   // weight-gradient accumulators + BN backward sums
+    // state of the last forward
+    int lastB, last_training, have_dout;
+};
+
+namespace {
+
+inline long long align_up(long long v, long long a) { return (v + a - 1) / a * a; }
+
+// Walks the workspace layout; with base == nullptr it only measures.
+long long layout(vecvad_net *n, int B, char *base) {
+    long long off = 0;
+    auto take = [&](long long bytes) -> char * {
+        char *p = base ? base + off : nullptr;
+        off = align_up(off + bytes, 256);
+        return p;
+    };
+    const int G = n->G, F = n->F, S = n->S;
+    auto M = [&](int H) { return (long long)B * H * H; };
+    auto fl = [&](long long count) { return (float *)take(count * (long long)sizeof(float)); };
+    n->X0 = fl(G * M(S) * n->cinp);
+    for (int u = 0; u < NU; u++) n->Z[u] = fl(G * M(n->uH[u]) * n->uN[u]);
+    for (int u = 0; u < NU; u += 2) n->A[u] = fl(G * M(n->uH[u]) * n->uN[u]);
+    // CAT[k]: concat input of up-block k+1:  k=0 @S/4 (8F), k=1 @S/2 (4F), k=2 @S (2F)
+    for (int k = 0; k < 3; k++) {
+        int H = S >> (2 - k), C = F << (3 - k);
+        n->CAT[k] = fl(G * M(H) * C);
+        n->dCAT[k] = fl(G * M(H) * C);
+    }
+    // PL[k]: pooled input of down-block k+1: k=0 @S/2 (F), k=1 @S/4 (2F), k=2 @S/8 (4F)
+    for (int k = 0; k < 3; k++) n->PL[k] = fl(G * M(S >> (k + 1)) * (F << k));
+    n->X4 = fl(G * M(S >> 3) * 8 * F);
+    for (int k = 0; k < 3; k++) n->UU[k] = fl(G * M(S >> (2 - k)) * (F << (2 - k)));   // U1 @S/4 4F, U2 @S/2 2F, U3 @S F
+    n->GA = fl(G * M(S) * F);
+    n->GB = fl(G * M(S) * F);
+    n->DOUT = fl(G * M(S) * 4);
+    for (int u = 0; u < NU; u++) {
+        n->Wf[u] = fl((long long)G * 9 * n->uN[u] * n->uCp[u]);
+        n->Wd[u] = fl((long long)G * 9 * n->uN[u] * n->uCp[u]);
+        n->vec[u] = fl((long long)G * 3 * n->uN[u]);
+        n->save[u] = fl((long long)G * 4 * n->uN[u]);
+    }
+    for (int k = 0; k < NT; k++) {
+        n->tWf[k] = fl((long long)G * 16 * n->tCo[k] * n->tCi[k]);
+        n->tWd[k] = fl((long long)G * 16 * n->tCo[k] * n->tCi[k]);
+        n->tvec[k] = fl((long long)G * n->tCo[k]);
+    }
+    long long z0 = off;
+    for (int u = 0; u < NU; u++) n->stats[u] = (double *)take((long long)G * 2 * n->uN[u] * sizeof(double));
+    n->zero_fwd = base ? base + z0 : nullptr;
+    n->zero_fwd_bytes = (size_t)(off - z0);
+    long long z1 = off;
+    for (int u = 0; u < NU; u++) {
+        n->dWf[u] = fl((long long)G * 9 * n->uN[u] * n->uCp[u]);
+        n->bsums[u] = (double *)take((long long)G * 2 * n->uN[u] * sizeof(double));
+    }
+    for (int k = 0; k < NT; k++) n->tdW[k] = fl((long long)G * 16 * n->tCo[k] * n->tCi[k]);
+    n->zero_bwd = base ? base + z1 : nullptr;
+    n->zero_bwd_bytes = (size_t)(off - z1);
+    return off;
+}
+
+VvTaps taps3x3(int sign) {
+    VvTaps t;
+    t.n = 9;
+    for (int k = 0; k < 9; k++) { t.dy[k] = sign * (k / 3 - 1); t.dx[k] = sign * (k % 3 - 1); }
+    return t;
+}
+VvTaps taps2x2(int sign) {
+    VvTaps t;
+    t.n = 4;
+    for (int k = 0; k < 4; k++) { t.dy[k] = sign * (k >> 1); t.dx[k] = sign * (k & 1); }
+    for (int k = 4; k < 9; k++) { t.dy[k] = 0; t.dx[k] = 0; }
+    return t;
+}
+
+int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st) {
+    if (n->cfg.use_tensor_cores && vv_igemm_tc_supported(p)) return vv_launch_igemm_tc(p, st);
+    return vv_launch_igemm_simt(p, st);
+}
+int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st) {
+    if (n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p)) return vv_launch_wgrad_tc(p, st);
+    return vv_launch_wgrad_simt(p, st);
+}
+
+struct Flow {   // buffer wiring of one forward for batch B
+    View in[NU], y[NU];
+    int pool[NU];      // index into PL or -1
+    View tin[NT], tout[NT];
+};
+
+View mk(float *p, int B, int H, int ld, int coff, int C) {
+    View v;
+    v.p = p; v.gs = (long long)B * H * H * ld; v.ld = ld; v.coff = coff; v.C = C; v.H = H;
+    return v;
+}
+
+void wire(const vecvad_net *n, int B, Flow &f) {
+    const int F = n->F, S = n->S;
+    for (int u = 0; u < NU; u++) f.pool[u] = -1;
+    // encoder
+    f.in[0] = mk(n->X0, B, S, n->cinp, 0, n->cinp);
+    f.y[0] = mk(n->A[0], B, S, F, 0, F);
+    f.in[1] = f.y[0];
+    f.y[1] = mk(n->CAT[2], B, S, 2 * F, 0, F);            f.pool[1] = 0;
+    f.in[2] = mk(n->PL[0], B, S / 2, F, 0, F);
+    f.y[2] = mk(n->A[2], B, S / 2, 2 * F, 0, 2 * F);
+    f.in[3] = f.y[2];
+    f.y[3] = mk(n->CAT[1], B, S / 2, 4 * F, 0, 2 * F);    f.pool[3] = 1;
+    f.in[4] = mk(n->PL[1], B, S / 4, 2 * F, 0, 2 * F);
+    f.y[4] = mk(n->A[4], B, S / 4, 4 * F, 0, 4 * F);
+    f.in[5] = f.y[4];
+    f.y[5] = mk(n->CAT[0], B, S / 4, 8 * F, 0, 4 * F);    f.pool[5] = 2;
+    f.in[6] = mk(n->PL[2], B, S / 8, 4 * F, 0, 4 * F);
+    f.y[6] = mk(n->A[6], B, S / 8, 8 * F, 0, 8 * F);
+    f.in[7] = f.y[6];
+    f.y[7] = mk(n->X4, B, S / 8, 8 * F, 0, 8 * F);
+    // decoder: up-block k (0..2): convT(tin -> second half of CAT[k]) ; conv units 8+2k, 9+2k
+    for (int k = 0; k < 3; k++) {
+        int H = S >> (2 - k), C = F << (3 - k);           // concat resolution / channels
+        f.tin[k] = (k == 0) ? f.y[7] : f.y[7 + 2 * k];    // X4, U1, U2
+        f.tout[k] = mk(n->CAT[k], B, H, C, C / 2, C / 2);
+        int u = 8 + 2 * k;
+        f.in[u] = mk(n->CAT[k], B, H, C, 0, C);
+        f.y[u] = mk(n->A[u], B, H, C / 2, 0, C / 2);
+        f.in[u + 1] = f.y[u];
+        f.y[u + 1] = mk(n->UU[k], B, H, C / 2, 0, C / 2);
+    }
+}
+
+}  // namespace
+
+extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out) {
+    VV_REQUIRE(cfg && out, "net_create: null argument");
+    VV_REQUIRE(cfg->n_unets >= 1 && cfg->n_unets <= VECVAD_MAX_UNETS, "net_create: n_unets=%d out of range", cfg->n_unets);
+    VV_REQUIRE(cfg->features_root >= 16 && cfg->features_root % 16 == 0, "net_create: features_root=%d must be a multiple of 16",
+               cfg->features_root);
+    VV_REQUIRE(cfg->patch >= 16 && cfg->patch % 16 == 0, "net_create: patch=%d must be a multiple of 16", cfg->patch);
+    VV_REQUIRE(cfg->tot_raw_num >= 2 && cfg->tot_raw_num <= 10, "net_create: tot_raw_num=%d unsupported", cfg->tot_raw_num);
+    vecvad_net *n = new (std::nothrow) vecvad_net();
+    VV_REQUIRE(n, "net_create: out of host memory");
+    memset(n, 0, sizeof(*n));
+    n->cfg = *cfg;
+    n->G = cfg->n_unets; n->F = cfg->features_root; n->S = cfg->patch; n->T = cfg->tot_raw_num;
+    n->cin_real = 3 * (cfg->padding ? n->T : n->T - 1);
+    n->cinp = (n->cin_real + 15) / 16 * 16;
+    if (cfg->use_tensor_cores) n->cinp = (n->cin_real + 31) / 32 * 32;   // tcgen05 tiles use 128-byte (32 x tf32) K slabs
+    int max_raw = -1, max_of = -1;
+    for (int g = 0; g < n->G; g++) {
+        n->slot.v[g] = cfg->param_slot[g]; n->erase.v[g] = cfg->erase_frame[g]; n->outc.v[g] = cfg->out_channels[g];
+        n->isflow.v[g] = cfg->target_is_flow[g]; n->tidx.v[g] = cfg->target_index[g]; n->oslot.v[g] = cfg->out_slot[g];
+        if (!(cfg->erase_frame[g] >= 0 && cfg->erase_frame[g] < n->T) || !(cfg->out_channels[g] == (cfg->target_is_flow[g] ? 2 : 3)) ||
+            cfg->param_slot[g] < 0 || cfg->out_slot[g] < 0 || cfg->target_index[g] < 0) {
+            delete n;
+            return vv_set_err(-1, "net_create: bad per-UNet configuration at g=%d", g);
+        }
+        if (cfg->target_is_flow[g]) max_of = cfg->out_slot[g] > max_of ? cfg->out_slot[g] : max_of;
+        else max_raw = cfg->out_slot[g] > max_raw ? cfg->out_slot[g] : max_raw;
+    }
+    n->n_raw_out = max_raw + 1; n->n_of_out = max_of + 1;
+    const int F = n->F, S = n->S;
+    // conv units: (C -> N @H)
+    int C[NU] = {n->cin_real, F, F, 2 * F, 2 * F, 4 * F, 4 * F, 8 * F, 8 * F, 4 * F, 4 * F, 2 * F, 2 * F, F};
+    int N[NU] = {F, F, 2 * F, 2 * F, 4 * F, 4 * F, 8 * F, 8 * F, 4 * F, 4 * F, 2 * F, 2 * F, F, F};
+    int H[NU] = {S, S, S / 2, S / 2, S / 4, S / 4, S / 8, S / 8, S / 4, S / 4, S / 2, S / 2, S, S};
+    for (int u = 0; u < NU; u++) { n->uC[u] = C[u]; n->uCp[u] = (u == 0) ? n->cinp : C[u]; n->uN[u] = N[u]; n->uH[u] = H[u]; }
+    for (int k = 0; k < NT; k++) { n->tCi[k] = F << (3 - k); n->tCo[k] = F << (2 - k); n->tH[k] = S >> (3 - k); }
+    *out = n;
+    return 0;
+}
+
+extern "C" void vecvad_net_destroy(vecvad_net *net) { delete net; }
+
+extern "C" int vecvad_net_workspace_bytes(const vecvad_net *net, int batch, int64_t *bytes) {
+    VV_REQUIRE(net && bytes && batch >= 1, "workspace_bytes: bad arguments");
+    vecvad_net tmp = *net;
+    *bytes = layout(&tmp, batch, nullptr);
+    return 0;
+}
+
+extern "C" int vecvad_net_bind(vecvad_net *net, float *params, float *grads, float *running_stats, void *workspace,
+                               int64_t workspace_bytes, int max_batch) {
+    VV_REQUIRE(net && params && workspace && max_batch >= 1, "net_bind: bad arguments");
+    VV_REQUIRE(((uintptr_t)workspace) % 256 == 0, "net_bind: workspace must be 256-byte aligned");
+    VV_REQUIRE(((uintptr_t)params) % 16 == 0 && ((uintptr_t)grads) % 16 == 0, "net_bind: params/grads must be 16-byte aligned");
+    long long need = layout(net, max_batch, (char *)workspace);
+    VV_REQUIRE(need <= workspace_bytes, "net_bind: workspace too small (%lld needed, %lld given)", need, (long long)workspace_bytes);
+    net->params = params; net->grads = grads; net->running = running_stats;
+    net->ws = (char *)workspace; net->ws_bytes = workspace_bytes; net->maxB = max_batch;
+    net->lastB = 0; net->last_training = 0; net->have_dout = 0;
+    return 0;
+}
+
+extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_of, int x_of_channels, int batch, int training,
+                                  float *raw_out, int raw_out_channels, float *of_out, int of_out_channels, float *sse, float lambda_raw,
+                                  float lambda_of, vecvad_stream stream) {
+    VV_REQUIRE(n && n->ws, "net_forward: net not bound");
+    VV_REQUIRE(x && batch >= 1 && batch <= n->maxB, "net_forward: batch=%d outside 1..%d", batch, n->maxB);
+    VV_REQUIRE(n->running, "net_forward: running-statistics buffer not bound");
+    VV_REQUIRE(!training || batch * (n->S / 8) * (n->S / 8) > 1, "net_forward: BatchNorm needs more than one value per channel in training");
+    if (raw_out) VV_REQUIRE(raw_out_channels >= 3 * n->n_raw_out, "net_forward: raw_out has %d channels, need %d", raw_out_channels, 3 * n->n_raw_out);
+    if (n->n_of_out > 0) {
+        if (of_out) VV_REQUIRE(of_out_channels >= 2 * n->n_of_out, "net_forward: of_out has %d channels, need %d", of_out_channels, 2 * n->n_of_out);
+        if (sse) VV_REQUIRE(x_of != nullptr, "net_forward: x_of required for flow targets");
+    }
+    for (int g = 0; g < n->G; g++) {
+        if (sse && n->isflow.v[g]) VV_REQUIRE(2 * n->tidx.v[g] + 2 <= x_of_channels, "net_forward: flow target %d outside x_of (%d channels)", n->tidx.v[g], x_of_channels);
+        if (sse && !n->isflow.v[g]) VV_REQUIRE(n->tidx.v[g] < n->T, "net_forward: raw target %d outside the cube", n->tidx.v[g]);
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = n->G, B = batch, F = n->F, S = n->S;
+    const vecvad_net_config &c = n->cfg;
+    Flow f;
+    wire(n, B, f);
+    // 1. weights into GEMM layouts (they change every optimiser step)
+    for (int u = 0; u < NU; u++) {
+        int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
+                               n->uCp[u], n->Wf[u], 9LL * n->uN[u] * n->uCp[u], (training && u > 0) ? n->Wd[u] : nullptr,
+                               9LL * n->uN[u] * n->uCp[u], n->vec[u], 3LL * n->uN[u], G, st);
+        if (r) return r;
+    }
+    for (int k = 0; k < NT; k++) {
+        int r = vv_prep_ct_w(n->params, n->slot, c.slot_param_stride, c.up_w[k], c.up_b[k], n->tCi[k], n->tCo[k], n->tWf[k],
+                             16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->tvec[k], n->tCo[k], G, st);
+        if (r) return r;
+    }
+    if (training) VV_CK(cudaMemsetAsync(n->zero_fwd, 0, n->zero_fwd_bytes, st));
+    // 2. the erased-frame inputs of every UNet
+    {
+        int r = vv_prep_input(x, n->X0, G, B, n->T, S, n->cinp, c.padding, n->erase, st);
+        if (r) return r;
+    }
+    const VvTaps t3 = taps3x3(+1), t2 = taps2x2(+1);
+    auto conv_unit = [&](int u) -> int {
+        const View &in = f.in[u];
+        const View &y = f.y[u];
+        const int H = n->uH[u], N = n->uN[u];
+        VvIGemm p;
+        memset(&p, 0, sizeof(p));
+        p.A = in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->uCp[u];
+        p.B = B; p.H = H; p.W = H;
+        p.Wt = n->Wf[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3; p.N = N;
+        p.O = n->Z[u]; p.o_gs = (long long)B * H * H * N; p.ldo = N; p.o_coff = 0; p.o_d2s = 0;
+        p.bias = n->vec[u]; p.bias_gs = 3LL * N;
+        p.stats = training ? n->stats[u] : nullptr; p.stats_gs = 2LL * N;
+        p.G = G;
+        int r = run_igemm(n, p, st);
+        if (r) return r;
+        VvBnApply q;
+        memset(&q, 0, sizeof(q));
+        q.Z = n->Z[u]; q.z_gs = p.o_gs;
+        q.Y = y.p; q.y_gs = y.gs; q.ldy = y.ld; q.y_coff = y.coff;
+        q.pool = f.pool[u] >= 0;
+        if (q.pool) { q.P = n->PL[f.pool[u]]; q.p_gs = (long long)B * (H / 2) * (H / 2) * N; }
+        q.M = B * H * H; q.H = H; q.W = H; q.C = N; q.training = training;
+        q.stats = n->stats[u]; q.stats_gs = 2LL * N;
+        q.vec = n->vec[u]; q.vec_gs = 3LL * N;
+        q.running = n->running; q.slot = n->slot; q.slot_stat_stride = c.slot_stat_stride; q.rm_off = c.run_mean[u]; q.rv_off = c.run_var[u];
+        q.save = training ? n->save[u] : nullptr; q.save_gs = 4LL * N;
+        return vv_bn_apply(q, G, st);
+    };
+    auto convT = [&](int k) -> int {
+        const View &in = f.tin[k];
+        const View &o = f.tout[k];
+        VvIGemm p;
+        memset(&p, 0, sizeof(p));
+        p.A = in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->tCi[k];
+        p.B = B; p.H = n->tH[k]; p.W = n->tH[k];
+        p.Wt = n->tWf[k]; p.w_gs = 16LL * n->tCo[k] * n->tCi[k]; p.taps = t2; p.N = 4 * n->tCo[k];
+        p.O = o.p; p.o_gs = o.gs; p.ldo = o.ld; p.o_coff = o.coff; p.o_d2s = 1;
+        p.bias = n->tvec[k]; p.bias_gs = n->tCo[k];
+        p.stats = nullptr; p.G = G;
+        return run_igemm(n, p, st);
+    };
+    int r;
+    for (int u = 0; u < 8; u++) if ((r = conv_unit(u))) return r;
+    for (int k = 0; k < 3; k++) {
+        if ((r = convT(k))) return r;
+        if ((r = conv_unit(8 + 2 * k))) return r;
+        if ((r = conv_unit(9 + 2 * k))) return r;
+    }
+    // 3. 1x1 output conv (+ squared error / MSE gradient)
+    VvOutFwd q;
+    memset(&q, 0, sizeof(q));
+    q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F;
+    q.params = n->params; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.w_off = c.out_w; q.b_off = c.out_b;
+    q.out_channels = n->outc; q.target_is_flow = n->isflow; q.target_index = n->tidx; q.out_slot = n->oslot;
+    q.B = B; q.S = S; q.F = F;
+    q.raw_out = raw_out; q.raw_out_channels = raw_out_channels; q.of_out = of_out; q.of_out_channels = of_out_channels;
+    q.x = x; q.x_channels = 3 * n->T; q.x_of = x_of; q.x_of_channels = x_of_channels;
+    q.sse = sse;
+    q.dout = (sse && training) ? n->DOUT : nullptr;
+    // loss = lambda_raw * mean_{B,3*n_raw,S,S} + lambda_of * mean_{B,2*n_of,S,S}   (train.py:385-392)
+    q.coef_raw = n->n_raw_out ? 2.f * lambda_raw / ((float)B * 3.f * n->n_raw_out * S * S) : 0.f;
+    q.coef_of = n->n_of_out ? 2.f * lambda_of / ((float)B * 2.f * n->n_of_out * S * S) : 0.f;
+    if ((r = vv_outconv_fwd(q, G, st))) return r;
+    n->lastB = B; n->last_training = training; n->have_dout = (sse && training) ? 1 : 0;
+    return 0;
+}
+
+extern "C" int vecvad_net_losses(vecvad_net *n, const float *sse, int batch, float *losses, vecvad_stream stream) {
+    VV_REQUIRE(n && sse && losses && batch >= 1, "net_losses: bad arguments");
+    float inv_raw = n->n_raw_out ? 1.f / ((float)batch * 3.f * n->n_raw_out * n->S * n->S) : 0.f;
+    float inv_of = n->n_of_out ? 1.f / ((float)batch * 2.f * n->n_of_out * n->S * n->S) : 0.f;
+    return vv_losses(sse, n->G, batch, n->isflow, inv_raw, inv_of, losses, (cudaStream_t)stream);
+}
+
+extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, const float *grad_of_out, vecvad_stream stream) {
+    VV_REQUIRE(n && n->ws && n->grads, "net_backward: net not bound (or no gradient buffer)");
+    VV_REQUIRE(n->lastB > 0 && n->last_training, "net_backward: no training-mode forward to differentiate");
+    const bool ext = grad_raw_out || grad_of_out;
+    VV_REQUIRE(ext || n->have_dout, "net_backward: no output gradient (pass grad_*_out or run forward with sse)");
+    if (ext) {
+        VV_REQUIRE(n->n_raw_out == 0 || grad_raw_out, "net_backward: grad_raw_out missing");
+        VV_REQUIRE(n->n_of_out == 0 || grad_of_out, "net_backward: grad_of_out missing");
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int G = n->G, B = n->lastB, F = n->F, S = n->S;
+    const vecvad_net_config &c = n->cfg;
+    Flow f;
+    wire(n, B, f);
+    int r;
+    // every gradient of every slot is (re)written: zero first, then kernels accumulate / overwrite
+    long long max_slot = 0;
+    for (int g = 0; g < G; g++) max_slot = n->slot.v[g] > max_slot ? n->slot.v[g] : max_slot;
+    (void)max_slot;
+    VV_CK(cudaMemsetAsync(n->zero_bwd, 0, n->zero_bwd_bytes, st));
+    for (int g = 0; g < G; g++)
+        VV_CK(cudaMemsetAsync(n->grads + n->slot.v[g] * c.slot_param_stride, 0, c.slot_param_stride * sizeof(float), st));
+
+    // ---- output conv
+    {
+        VvOutBwd q;
+        memset(&q, 0, sizeof(q));
+        q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F;
+        q.dU = n->GA; q.du_gs = q.u_gs;
+        q.params = n->params; q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.w_off = c.out_w; q.b_off = c.out_b;
+        q.out_channels = n->outc; q.target_is_flow = n->isflow; q.out_slot = n->oslot;
+        q.M = B * S * S; q.S = S; q.F = F;
+        q.dout = n->DOUT;
+        q.grad_raw_out = grad_raw_out; q.raw_out_channels = 3 * n->n_raw_out;
+        q.grad_of_out = grad_of_out; q.of_out_channels = 2 * n->n_of_out;
+        if ((r = vv_outconv_bwd(q, G, st))) return r;
+    }
+    const VvTaps t3f = taps3x3(+1), t3b = taps3x3(-1), t2f = taps2x2(+1), t2b = taps2x2(-1);
+
+    // gradient of the post-ReLU output of unit u lives in dyv; produces d(input of unit u) into `din` (if u > 0)
+    auto unit_bwd = [&](int u, const View &dyv, float *dz_buf, const View *din) -> int {
+        const int H = n->uH[u], N = n->uN[u], M = B * H * H;
+        VvBnBwd q;
+        memset(&q, 0, sizeof(q));
+        q.Z = n->Z[u]; q.z_gs = (long long)M * N;
+        q.dY = dyv.p; q.dy_gs = dyv.gs; q.ldy = dyv.ld; q.dy_coff = dyv.coff;
+        q.dZ = dz_buf; q.dz_gs = (long long)M * N;
+        q.M = M; q.C = N;
+        q.save = n->save[u]; q.save_gs = 4LL * N;
+        q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
+        q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.gamma_off = c.bn_w[u]; q.beta_off = c.bn_b[u];
+        int rr = vv_bn_bwd(q, G, st);
+        if (rr) return rr;
+        // weight gradient
+        const View &in = f.in[u];
+        VvWGrad w;
+        memset(&w, 0, sizeof(w));
+        w.A = in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = n->uCp[u];
+        w.B = B; w.H = H; w.W = H;
+        w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
+        w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
+        if ((rr = run_wgrad(n, w, st))) return rr;
+        if ((rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, st)))
+            return rr;
+        // (pre-BN conv bias: its gradient is exactly zero in training mode -- left at the memset value; the reference
+        //  produces round-off noise there)
+        if (din) {
+            VvIGemm p;
+            memset(&p, 0, sizeof(p));
+            p.A = dz_buf; p.a_gs = (long long)M * N; p.lda = N; p.a_coff = 0; p.a_s2d = 0; p.Kt = N;
+            p.B = B; p.H = H; p.W = H;
+            p.Wt = n->Wd[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3b; p.N = n->uC[u];
+            p.O = din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
+            p.bias = nullptr; p.stats = nullptr; p.G = G;
+            if ((rr = run_igemm(n, p, st))) return rr;
+        }
+        return 0;
+    };
+    // transposed conv k: gradient arrives in the second half of dCAT[k]
+    auto convT_bwd = [&](int k, const View &ddeep) -> int {
+        const int Hi = n->tH[k], Ci = n->tCi[k], Co = n->tCo[k];
+        const int Hc = 2 * Hi, Cc = 2 * Co;                   // concat buffer geometry
+        View dhalf = mk(n->dCAT[k], B, Hc, Cc, Co, Co);
+        int rr = vv_colsum(dhalf.p, dhalf.gs, dhalf.ld, dhalf.coff, B * Hc * Hc, Co, n->grads, n->slot, c.slot_param_stride, c.up_b[k], G, st);
+        if (rr) return rr;
+        const View &in = f.tin[k];
+        VvWGrad w;
+        memset(&w, 0, sizeof(w));
+        w.A = in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = Ci;
+        w.B = B; w.H = Hi; w.W = Hi;
+        w.Gd = dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
+        w.taps = t2f; w.dW = n->tdW[k]; w.dw_gs = 16LL * Co * Ci; w.G = G;
+        if ((rr = run_wgrad(n, w, st))) return rr;
+        if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, st))) return rr;
+        VvIGemm p;
+        memset(&p, 0, sizeof(p));
+        p.A = dhalf.p; p.a_gs = dhalf.gs; p.lda = dhalf.ld; p.a_coff = dhalf.coff; p.a_s2d = 1; p.Kt = 4 * Co;
+        p.B = B; p.H = Hi; p.W = Hi;
+        p.Wt = n->tWd[k]; p.w_gs = 16LL * Co * Ci; p.taps = t2b; p.N = Ci;
+        p.O = ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
+        p.bias = nullptr; p.stats = nullptr; p.G = G;
+        return run_igemm(n, p, st);
+    };
+
+    // ---- decoder, deepest last.  GA holds dU3 now.
+    float *ga = n->GA, *gb = n->GB;
+    for (int k = 2; k >= 0; k--) {
+        const int H = S >> (2 - k), C = F << (3 - k);          // concat geometry of up-block k
+        const int u2 = 9 + 2 * k, u1 = 8 + 2 * k;
+        View dy2 = mk(ga, B, H, C / 2, 0, C / 2);               // d(output of second conv)
+        View dmid = mk(gb, B, H, C / 2, 0, C / 2);
+        if ((r = unit_bwd(u2, dy2, ga, &dmid))) return r;        // dz in place in ga, d(mid) -> gb
+        View dcat = mk(n->dCAT[k], B, H, C, 0, C);
+        if ((r = unit_bwd(u1, dmid, gb, &dcat))) return r;       // dz in place in gb, d(concat) -> dCAT[k]
+        View ddeep = mk(ga, B, H / 2, C, 0, C);                  // d(X4 / U1 / U2): [B,(H/2)^2, C]
+        if ((r = convT_bwd(k, ddeep))) return r;
+    }
+    // ---- encoder.  ga holds dX4.
+    for (int k = 3; k >= 0; k--) {
+        const int u2 = 2 * k + 1, u1 = 2 * k;
+        const int H = n->uH[u1], N = n->uN[u2];
+        View dy2;
+        if (k == 3) dy2 = mk(ga, B, H, N, 0, N);
+        else dy2 = mk(n->dCAT[2 - k], B, H, 2 * N, 0, N);       // first half of the concat gradient (+ pooled path, added below)
+        float *dz2 = (k == 3) ? ga : gb;
+        float *other = (dz2 == ga) ? gb : ga;
+        View dmid = mk(other, B, H, N, 0, N);
+        if ((r = unit_bwd(u2, dy2, dz2, &dmid))) return r;
+        if (k == 0) {
+            if ((r = unit_bwd(u1, dmid, other, nullptr))) return r;   // first conv: its input needs no gradient
+        } else {
+            // d(pooled input) -> the remaining scratch buffer, then routed through the max-pool into dCAT[3-k]
+            View dpool = mk(dz2, B, H, n->uC[u1], 0, n->uC[u1]);
+            if ((r = unit_bwd(u1, dmid, other, &dpool))) return r;
+            const int Hs = 2 * H, Cs = n->uC[u1];                 // skip tensor geometry (x_k) : [B,Hs,Hs,Cs] inside CAT[3-k]
+            View ysk = mk(n->CAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
+            View dsk = mk(n->dCAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
+            if ((r = vv_maxpool_bwd(ysk.p, ysk.gs, ysk.ld, ysk.coff, dpool.p, dpool.gs, dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B, Hs, Hs, Cs, st)))
+                return r;
+        }
+    }
+    return 0;
+}
+
+// ---- single-op export: 3x3 pad-1 convolution on one NHWC tensor (unit tests, single-kernel profiling)
+extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
+                                      float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(in && w && out && scratch, "conv3x3_forward: null argument");
+    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && ld_in >= cin && ld_in % 4 == 0, "conv3x3_forward: cin/cout must be multiples of 16");
+    cudaStream_t st = (cudaStream_t)stream;
+    VvIntG slot;
+    memset(&slot, 0, sizeof(slot));
+    int r = vv_prep_conv_w(w, slot, 0, 0, 0, 0, 0, cout, cin, cin, scratch, 0, nullptr, 0, nullptr, 0, 1, st);
+    if (r) return r;
+    if (stats) VV_CK(cudaMemsetAsync(stats, 0, 2 * cout * sizeof(double), st));
+    VvIGemm p;
+    memset(&p, 0, sizeof(p));
+    p.A = in; p.a_gs = 0; p.lda = ld_in; p.Kt = cin; p.B = batch; p.H = h; p.W = wd;
+    p.Wt = scratch; p.taps = taps3x3(+1); p.N = cout;
+    p.O = out; p.ldo = cout; p.bias = bias; p.stats = stats; p.G = 1;
+    if (use_tc) {
+        VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_forward: shape not supported by the tcgen05 path");
+        return vv_launch_igemm_tc(p, st);
+    }
+    return vv_launch_igemm_simt(p, st);
+}
+
+extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
+                                     vecvad_stream stream) {
+    VV_REQUIRE(n && n->ws && dst && n_floats && n->lastB > 0, "debug_read: net not bound / no forward yet");
+    const long long G = n->G, B = n->lastB, F = n->F, S = n->S;
+    auto M = [&](long long H) { return B * H * H; };
+    const float *src = nullptr;
+    long long cnt = 0;
+    const int u = index, k = index;
+    switch (kind) {
+        case 0: src = n->X0; cnt = G * M(S) * n->cinp; break;
+        case 1: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Z[u]; cnt = G * M(n->uH[u]) * n->uN[u]; break;
+        case 2: VV_REQUIRE(u >= 0 && u < NU && u % 2 == 0, "debug_read: unit"); src = n->A[u]; cnt = G * M(n->uH[u]) * n->uN[u]; break;
+        case 3: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->CAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); break;
+        case 4: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->PL[k]; cnt = G * M(S >> (k + 1)) * (F << k); break;
+        case 5: src = n->X4; cnt = G * M(S >> 3) * 8 * F; break;
+        case 6: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->UU[k]; cnt = G * M(S >> (2 - k)) * (F << (2 - k)); break;
+        case 7: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->dCAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); break;
+        case 8: src = n->GA; cnt = G * M(S) * F; break;
+        case 9: src = n->GB; cnt = G * M(S) * F; break;
+        case 10: src = n->DOUT; cnt = G * M(S) * 4; break;
+        case 11: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Wf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; break;
+        case 12: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->dWf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; break;
+        case 13: VV_REQUIRE(k >= 0 && k < NT, "debug_read: k"); src = n->tWf[k]; cnt = G * 16 * n->tCo[k] * n->tCi[k]; break;
+        case 14: VV_REQUIRE(k >= 0 && k < NT, "debug_read: k"); src = n->tdW[k]; cnt = G * 16 * n->tCo[k] * n->tCi[k]; break;
+        default: return vv_set_err(-1, "debug_read: unknown kind %d", kind);
+    }
+    VV_REQUIRE(cnt <= max_floats, "debug_read: destination too small (%lld > %lld)", cnt, (long long)max_floats);
+    VV_CK(cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    *n_floats = cnt;
+    return 0;
+}
