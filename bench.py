@@ -1,0 +1,237 @@
+#!/usr/bin/env python
+"""bench.py -- STCs/sec of one train step of the completion-UNet set (BASELINE.json metric) on N B200s.
+
+    python bench.py --gpus 1 --steps 30 --warmup 5            (ours; N>1 is launched by torch.distributed.run)
+    python bench.py --impl reference --steps 3 --warmup 1     (the reference algorithm on the host cores)
+
+A step = cube staging (uint8 cubes -> float tensors) + forward of every UNet + MSE losses + backward +
+(N>1: one NCCL all-reduce of the flat gradient buffer) + Adam, for one batch of 128 synthetic 5x32x32x3 cubes
+per GPU (BASELINE.json configs[1]: UCSDped2 5raw1of dual-UNet set, batch 128).
+  value : device-timed (CUDA events on the launch stream), cubes already resident in HBM as uint8.
+  e2e   : the same step through the public module API with HOST (pinned) cube buffers: H2D of the cubes and
+          D2H of the two losses inside the timed region, every step.
+Prints exactly one JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+# algorithmic FLOPs of one train step per STC (fwd + dgrad + wgrad of every conv; SURVEY.md section 8a / BASELINE.md section 2)
+FLOPS_PER_STC = {'net4': 5.524e9, 'full': 9.206e9, 'noflow': 4.604e9}
+NET_KW = {
+    'net4': ('net4', dict(features_root=32, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False), 1),
+    'full': ('full', dict(features_root=32, tot_raw_num=5, tot_of_num=5, border_mode='predict', rawRange=None, useFlow=True, padding=False), 5),
+    'noflow': ('net4', dict(features_root=32, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=False, padding=False), 1),
+}
+WORKLOAD = {'net4': 'UCSDped2 raw+flow dual-UNet set (5raw1of, SelfCompleteNet4), synthetic 5x32x32x3 cubes',
+            'full': 'avenue 5raw5of (SelfCompleteNetFull, context_of_num=4), synthetic 5x32x32x3 cubes',
+            'noflow': 'UCSDped2 appearance-only UNet set (useFlow=False), synthetic 5x32x32x3 cubes'}
+
+
+def peaks():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, 'measured'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback'
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        self.thr.join(timeout=2)
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 2 + i and r[2 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def cpu_reference_steps(net, batch, steps, warmup, threads):
+    """The reference algorithm (oracle port of model/unet.py + train.py:383-402) on the host cores. -> (STC/s, s/step)"""
+    import torch
+    from oracle import unet_oracle as orc
+    kind, kw, t_of = NET_KW[net]
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    m = orc.CompletionNetOracle(kind, **kw).train()
+    opt = orc.make_adam(m)
+    raw_u8, flow = orc.synthetic_cubes(batch, t_of=t_of, seed=1234)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    for _ in range(warmup):
+        orc.train_step(m, opt, x, x_of)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        orc.train_step(m, opt, x, x_of)
+    dt = (time.perf_counter() - t0) / steps
+    return batch / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = args.batch
+    v, dt = cpu_reference_steps(args.net, batch, args.steps, args.warmup, threads)
+    line = {'impl': 'reference', 'metric': 'STCs/sec (train step)', 'value': v, 'unit': 'STC/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_step': batch},
+            'cpu_baseline': {'value': v, 'unit': 'STC/s', 'cores': threads, 'kind': 'port',
+                             'sample': '%d train steps of batch %d (oracle port of model/unet.py + train.py:383-402, torch CPU fp32)' % (args.steps, batch)},
+            'e2e': {'value': v, 'unit': 'STC/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from vec_vad_b200 import _lib, unet as vu, vad_datasets as vd
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    kind, kw, t_of = NET_KW[args.net]
+    cls = {'net4': vu.SelfCompleteNet4, 'full': vu.SelfCompleteNetFull}[kind]
+    torch.manual_seed(0)
+    model = cls(use_tensor_cores=not args.simt, **kw).cuda().train()
+    model.init_adam(lr=1e-3, eps=1e-7)
+    B, P = args.batch, args.pool
+    g = torch.Generator().manual_seed(1234 + rank)
+    host_raw = [torch.randint(0, 256, (B, 5, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(P)]
+    host_flow = [torch.randn((B, t_of, 32, 32, 2), generator=g).pin_memory() for _ in range(P)]
+    dev_raw = [t.to(dev) for t in host_raw]
+    dev_flow = [t.to(dev) for t in host_flow]
+    losses = torch.zeros(2, device=dev)
+    reduce = None
+    if world > 1:
+        def reduce(flat):
+            dist.all_reduce(flat)          # NCCL sum over NVLink/NVSwitch on the current stream; Adam applies 1/world
+            return 1.0 / world
+
+    def step_dev(i):
+        x, x_of = vd.cubes_to_device_tensors(dev_raw[i % P], dev_flow[i % P])
+        model.train_step(x, x_of, 1.0, 1.0, losses=losses, reduce_grads=reduce)
+
+    def step_e2e(i):
+        raw = host_raw[i % P].to(dev, non_blocking=True)
+        fl = host_flow[i % P].to(dev, non_blocking=True)
+        x, x_of = vd.cubes_to_device_tensors(raw, fl)
+        return model.train_step(x, x_of, 1.0, 1.0, reduce_grads=reduce).cpu()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = _lib.lib().vecvad_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, (_lib.lib().vecvad_launch_count() - n0) // steps
+
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()
+    ms_dev, launches = timed(step_dev, args.steps, args.warmup)
+    clocks = clk.stop() if rank == 0 else None
+    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    final_loss = losses.cpu().tolist()
+    if rank == 0:
+        pk, src = peaks()
+        value = world * B / (ms_dev * 1e-3)
+        tf = value * FLOPS_PER_STC[args.net] / 1e12 / world      # per-GPU tensor-pipe rate of the step's contractions
+        peak = pk['bf16_tflops_sustained'] if 'bf16_tflops_sustained' in pk else pk['bf16_tflops']
+        line = {'metric': 'STCs/sec (train step, device-timed)', 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'f32' if args.simt else 'tf32', 'data': 'synthetic',
+                'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': B, 'global_batch': world * B,
+                           'parallelism': 'dp%d' % world, 'input_pool_batches': P,
+                           'l2': 'per-step working set (activations + gradients, >3 GB at batch 128) exceeds the 126 MB L2; inputs rotate over %d batches' % P,
+                           'final_losses': final_loss},
+                'clocks': clocks, 'gpu_launches': int(launches),
+                'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'STC/s', 'ms_per_step': ms_e2e,
+                        'h2d_bytes_per_step': int(host_raw[0].numel() + 4 * host_flow[0].numel()), 'd2h_bytes_per_step': 8},
+                'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
+                             'note': 'whole-step contraction FLOPs (%.3f GFLOP/STC) / step time, per GPU; peak = %s sustained bf16 cuBLAS (%s)'
+                                     % (FLOPS_PER_STC[args.net] / 1e9, src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md')}}
+        if world == 1 and not args.no_cpu:
+            threads = os.cpu_count() or 1
+            v, dt = cpu_reference_steps(args.net, B, 4, 1, threads)
+            line['cpu_baseline'] = {'value': v, 'unit': 'STC/s', 'cores': threads, 'kind': 'port',
+                                    'sample': '4 train steps of batch %d after 1 warm-up (oracle port of model/unet.py + train.py:383-402, torch CPU fp32)' % B}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--net', default='net4', choices=sorted(NET_KW))
+    ap.add_argument('--batch', type=int, default=128, help='cubes per GPU per step')
+    ap.add_argument('--pool', type=int, default=8, help='distinct input batches rotated through')
+    ap.add_argument('--simt', action='store_true', help='fp32 SIMT tiles instead of tcgen05 tf32 tiles')
+    ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        args.warmup = 3
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -35,6 +35,8 @@ typedef void *vecvad_stream;  /* cudaStream_t */
 
 int vecvad_abi_version(void);
 const char *vecvad_last_error(void);
+/* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
+uint64_t vecvad_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------
  * (1) FlowNet2 ops.  All tensors are contiguous NCHW fp32 on the current device (the reference

@@ -1,0 +1,109 @@
+"""GPU parity of the FlowNet2 ops (libvecvad.so through vec_vad_b200.flow_ops) against oracle/flow_oracle.py on seeded inputs.
+Tolerance: fp32 allclose; the summation order over channels differs from the reference's."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import flow_oracle as fo
+from vec_vad_b200 import flow_ops as ops
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# (B, C, H, W, pad, k, md, s1, s2)
+CORR = [
+    (1, 32, 12, 16, 20, 1, 20, 1, 2),      # FlowNetC parameters (fast path), small map
+    (2, 256, 10, 70, 20, 1, 20, 1, 2),     # FlowNetC channels, ragged width (two x tiles, second partial)
+    (1, 7, 9, 11, 20, 1, 20, 1, 2),        # channel count not a multiple of the staging chunk
+    (2, 5, 9, 11, 4, 1, 4, 1, 2),          # general kernel
+    (1, 6, 9, 11, 3, 3, 4, 1, 2),
+    (1, 4, 12, 13, 5, 3, 3, 2, 1),
+    (1, 3, 8, 9, 0, 1, 2, 1, 2),
+]
+
+
+@pytest.mark.parametrize('case', CORR)
+def test_correlation_forward(case):
+    b, c, h, w, pad, k, md, s1, s2 = case
+    rng = np.random.RandomState(sum(case))
+    a, bb = rng.randn(b, c, h, w).astype(np.float32), rng.randn(b, c, h, w).astype(np.float32)
+    got = ops.Correlation(pad, k, md, s1, s2, 1)(_t(a), _t(bb)).cpu().numpy()
+    want = fo.correlation_forward(a, bb, pad, k, md, s1, s2)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('case', [(1, 3, 6, 7, 4, 1, 4, 1, 2), (2, 2, 5, 6, 3, 3, 2, 1, 1), (1, 2, 5, 6, 1, 1, 2, 1, 2)])
+def test_correlation_backward(case):
+    b, c, h, w, pad, k, md, s1, s2 = case
+    rng = np.random.RandomState(sum(case))
+    a, bb = rng.randn(b, c, h, w).astype(np.float32), rng.randn(b, c, h, w).astype(np.float32)
+    ta, tb = _t(a).requires_grad_(), _t(bb).requires_grad_()
+    out = ops.Correlation(pad, k, md, s1, s2, 1)(ta, tb)
+    go = rng.randn(*out.shape).astype(np.float32)
+    out.backward(_t(go))
+    g1, g2 = fo.correlation_backward(a, bb, go, pad, k, md, s1, s2)
+    np.testing.assert_allclose(ta.grad.cpu().numpy(), g1, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(tb.grad.cpu().numpy(), g2, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('shape,amp', [((2, 3, 24, 40), 4.0), ((1, 2, 17, 19), 30.0), ((1, 3, 436, 1024), 4.0)])
+def test_resample2d_forward(shape, amp):
+    b, c, h, w = shape
+    rng = np.random.RandomState(h)
+    img = rng.rand(b, c, h, w).astype(np.float32)
+    flow = (rng.randn(b, 2, h, w) * amp).astype(np.float32)      # amp 30 on a 17x19 map: most samples leave the image (border clamp)
+    got = ops.Resample2d()(_t(img), _t(flow)).cpu().numpy()
+    want = fo.resample2d_forward(img, flow)
+    np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-7)
+
+
+def test_resample2d_backward():
+    rng = np.random.RandomState(8)
+    b, c, h, w = 2, 3, 14, 18
+    img = rng.rand(b, c, h, w).astype(np.float32)
+    flow = (rng.randn(b, 2, h, w) * 3).astype(np.float32)
+    go = rng.randn(b, c, h, w).astype(np.float32)
+    ti, tf = _t(img).requires_grad_(), _t(flow).requires_grad_()
+    ops.Resample2d()(ti, tf).backward(_t(go))
+    g_img, g_flow = fo.resample2d_backward(img, flow, go)
+    np.testing.assert_allclose(ti.grad.cpu().numpy(), g_img, rtol=1e-4, atol=1e-5)      # atomicAdd order differs
+    np.testing.assert_allclose(tf.grad.cpu().numpy(), g_flow, rtol=1e-4, atol=1e-5)
+
+
+def test_channelnorm_forward_backward():
+    rng = np.random.RandomState(9)
+    x = rng.randn(2, 3, 20, 33).astype(np.float32)
+    t = _t(x).requires_grad_()
+    out = ops.ChannelNorm()(t)
+    want = fo.channelnorm_forward(x)
+    np.testing.assert_allclose(out.detach().cpu().numpy(), want, rtol=1e-6, atol=1e-7)
+    go = rng.randn(2, 1, 20, 33).astype(np.float32)
+    out.backward(_t(go))
+    np.testing.assert_allclose(t.grad.cpu().numpy(), fo.channelnorm_backward(x, want, go), rtol=1e-5, atol=1e-6)
+
+
+def test_warp_diff_norm_fused():
+    rng = np.random.RandomState(10)
+    b, c, h, w = 2, 3, 30, 50
+    img0, img1 = rng.rand(b, c, h, w).astype(np.float32), rng.rand(b, c, h, w).astype(np.float32)
+    flow = (rng.randn(b, 2, h, w) * 5).astype(np.float32)
+    warped, diff, norm = ops.warp_diff_norm(_t(img0), _t(img1), _t(flow))
+    w_, d_, n_ = fo.warp_diff_norm(img0, img1, flow)
+    np.testing.assert_allclose(warped.cpu().numpy(), w_, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(diff.cpu().numpy(), d_, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(norm.cpu().numpy(), n_, rtol=1e-5, atol=1e-6)
+    # and the unfused module chain gives the same thing (flownet2.py:79-81)
+    w2 = ops.Resample2d()(_t(img1), _t(flow))
+    n2 = ops.ChannelNorm()((_t(img0) - w2).contiguous())
+    assert torch.equal(w2, warped)
+    np.testing.assert_allclose(n2.cpu().numpy(), norm.cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_rejects_cpu_tensors():
+    with pytest.raises(RuntimeError, match='CUDA'):
+        ops.ChannelNorm()(torch.zeros(1, 2, 3, 3))

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    'vecvad_abi_version', 'vecvad_last_error',
+    'vecvad_abi_version', 'vecvad_last_error', 'vecvad_launch_count',
     'vecvad_correlation_out_shape', 'vecvad_correlation_forward', 'vecvad_correlation_backward',
     'vecvad_resample2d_forward', 'vecvad_resample2d_backward',
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
@@ -58,6 +58,7 @@ def lib():
     ip = C.POINTER(C.c_int)
     L.vecvad_abi_version.restype = i
     L.vecvad_last_error.restype = C.c_char_p
+    L.vecvad_launch_count.restype = C.c_uint64
     L.vecvad_correlation_out_shape.argtypes = [i] * 7 + [ip, ip, ip]
     L.vecvad_correlation_forward.argtypes = [p, p, p] + [i] * 10 + [p]
     L.vecvad_correlation_backward.argtypes = [p, p, p, p, p] + [i] * 10 + [p]

@@ -40,7 +40,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError('nvcc failed')
     if procs or not os.path.exists(LIB):
-        cmd = [nvcc, '-shared', '-o', LIB] + objs + ['-lcudart']
+        cmd = [nvcc, '-gencode', 'arch=compute_100a,code=sm_100a', '-shared', '-o', LIB] + objs + ['-lcudart']
         subprocess.check_call(cmd)
     return LIB
 

@@ -16,7 +16,12 @@ int vv_set_err(int code, const char *fmt, ...);
         if (e_ != cudaSuccess)                                                                             \
             return vv_set_err(-2, "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));    \
     } while (0)
-#define VV_CKL() VV_CK(cudaGetLastError())
+extern unsigned long long g_vv_launches;   // kernels launched by this library (bench.py reports it as gpu_launches)
+#define VV_CKL()                      \
+    do {                              \
+        g_vv_launches++;              \
+        VV_CK(cudaGetLastError());    \
+    } while (0)
 #define VV_REQUIRE(cond, ...)                          \
     do {                                               \
         if (!(cond)) return vv_set_err(-1, __VA_ARGS__); \

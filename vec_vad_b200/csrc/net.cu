@@ -20,6 +20,8 @@ int vv_set_err(int code, const char *fmt, ...) {
 
 extern "C" const char *vecvad_last_error(void) { return g_err; }
 extern "C" int vecvad_abi_version(void) { return VECVAD_ABI_VERSION; }
+unsigned long long g_vv_launches = 0;
+extern "C" uint64_t vecvad_launch_count(void) { return g_vv_launches; }
 
 namespace {
 
