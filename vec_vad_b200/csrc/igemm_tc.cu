@@ -1,6 +1,382 @@
-// tcgen05 (kind::tf32) implicit-GEMM tiles -- placeholder until the TMA/TMEM kernels land.
+// tcgen05 (kind::tf32) implicit-GEMM tiles for the conv / transposed-conv / input-gradient contractions of the
+// completion UNets (reference: the cuDNN calls behind model/unet.py:9-16,54,66 and their autograd backward).
+//
+//   out[m, n] = bias[n] + sum_t sum_k A[shift(m, t), k] * Wt[t][n][k]          (VvIGemm, common.h)
+//
+// One CTA = 128 output pixels (a TMA box of bw x bh pixels of bn images) x BN output channels.
+//   warp 0 / lane 0 : TMA producer.  Per (tap, 32-channel slab): one 4-D box load of the NHWC activations shifted by
+//                     the tap (out-of-image pixels are zero-filled by TMA = the conv's zero padding) + one 3-D box
+//                     load of the weights, both SWIZZLE_128B, into a ring of smem stages.
+//   warp 1 / lane 0 : issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=BN, K=8) x4 per stage, accumulating over
+//                     all taps and slabs in TMEM; tcgen05.commit frees the stage / publishes the accumulator.
+//   warps 0-3       : epilogue. tcgen05.ld 32 lanes x 32 columns per warp, + bias, store NHWC (optionally pixel-
+//                     shuffled for the transposed conv), BatchNorm batch statistics by a shuffle butterfly.
+// fp32 activations are fed to the tensor core as-is (kind::tf32 reads the top 19 bits); accumulation, bias,
+// statistics and everything downstream stay fp32.
+#include <cuda.h>
+
 #include "common.h"
-bool vv_igemm_tc_supported(const VvIGemm &) { return false; }
+
+namespace {
+
+constexpr int BM = 128;            // pixels per CTA (TMEM lanes)
+constexpr int KS = 32;             // channels per stage (128-byte rows)
+constexpr int A_STAGE = BM * KS * 4;
+
+// ------------------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra.uni WAIT_DONE;\n\t"
+        "bra.uni WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
+__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)2 << 61);
+}
+// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = n
+__device__ __forceinline__ uint32_t idesc_tf32(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+struct TcParams {
+    int B, H, W, G;
+    int bw, bh, bn;                 // pixel box of one CTA tile: bw * bh * bn == 128
+    int tiles_x, tiles_y, tiles_n;  // tiles per group = tiles_n * tiles_y * tiles_x
+    int ntaps, kchunks, cq;         // cq: channels per space-to-depth phase (a_s2d), else 0
+    int dy[9], dx[9];
+    int N;
+    float *O;
+    long long o_gs;
+    int ldo, o_coff, o_d2s;
+    const float *bias;
+    long long bias_gs;
+    double *stats;
+    long long stats_gs;
+};
+
+template <int BN, int STAGES>
+struct Smem {
+    static constexpr int B_STAGE = BN * KS * 4;
+    static constexpr int STAGE = A_STAGE + B_STAGE;
+    static constexpr int BYTES = STAGES * STAGE + 1024 /*alignment slack*/ + 256 /*barriers*/ + 3 * BN * 4;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128) k_igemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                                                  const TcParams p) {
+    using SM = Smem<BN, STAGES>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // SWIZZLE_128B tiles need 1024-byte alignment
+    uint64_t *full = (uint64_t *)(smem + STAGES * SM::STAGE);
+    uint64_t *empty = full + STAGES;
+    uint64_t *accum = empty + STAGES;
+    uint32_t *tmem_slot = (uint32_t *)(accum + 1);
+    float *s_bias = (float *)(smem + STAGES * SM::STAGE + 256);
+    float *s_sum = s_bias + BN, *s_sq = s_sum + BN;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.z;
+    const int n0 = blockIdx.y * BN;
+    int tile = blockIdx.x;
+    const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+    const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+    const int img0 = tile * p.bn, y0 = ty * p.bh, x0 = tx * p.bw;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(accum, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    if (warp == 1) {   // TMEM allocation: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int i = threadIdx.x; i < BN; i += 128) {
+        s_bias[i] = p.bias ? p.bias[g * p.bias_gs + (p.o_d2s ? (n0 + i) % (p.N >> 2) : (n0 + i))] : 0.f;
+        s_sum[i] = 0.f; s_sq[i] = 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int nsteps = p.ntaps * p.kchunks;
+
+    if (warp == 0 && lane == 0) {
+        // ---------------- TMA producer
+        for (int it = 0; it < nsteps; it++) {
+            const int s = it % STAGES, round = it / STAGES;
+            if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+            const int t = it / p.kchunks, kc = it - t * p.kchunks;
+            uint8_t *sa = smem + s * SM::STAGE, *sb = sa + A_STAGE;
+            mbar_expect_tx(&full[s], SM::STAGE);
+            int c = kc * KS, xx = x0 + p.dx[t], yy = y0 + p.dy[t];
+            if (p.cq) {                     // space-to-depth source: channel slab -> (phase, channel), stride-2 pixel walk
+                const int ph = c / p.cq;
+                c -= ph * p.cq;
+                xx = 2 * xx + (ph & 1);
+                yy = 2 * yy + (ph >> 1);
+            }
+            tma_load_4d(sa, &tmA, &full[s], c, xx, yy, g * p.B + img0);
+            tma_load_3d(sb, &tmB, &full[s], kc * KS, n0, g * p.ntaps + t);
+        }
+    } else if (warp == 1 && lane == 0) {
+        // ---------------- MMA issuer
+        const uint32_t idesc = idesc_tf32(BN);
+        for (int it = 0; it < nsteps; it++) {
+            const int s = it % STAGES, round = it / STAGES;
+            mbar_wait(&full[s], round & 1);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + s * SM::STAGE), sb = sa + A_STAGE;
+            const uint64_t da = smem_desc_k_sw128(sa), db = smem_desc_k_sw128(sb);
+#pragma unroll
+            for (int k = 0; k < KS / 8; k++)      // 8 tf32 = 32 bytes per MMA along K: +2 in the (>>4) start-address field
+                tc_mma_tf32(tmem, da + 2 * k, db + 2 * k, idesc, (it | k) ? 1u : 0u);
+            tc_commit(&empty[s]);                 // stage reusable once these MMAs have read it
+        }
+        tc_commit(accum);                          // accumulator complete
+    }
+    __syncwarp();
+
+    // ---------------- epilogue (all four warps; warp w owns TMEM lanes 32w .. 32w+31 = tile rows)
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int row = warp * 32 + lane;
+    int r = row;
+    const int xx = r % p.bw; r /= p.bw;
+    const int yy = r % p.bh; r /= p.bh;
+    const int b = img0 + r, y = y0 + yy, x = x0 + xx;
+    const bool valid = b < p.B && y < p.H && x < p.W;
+    float *O = p.O + g * p.o_gs;
+    const int Co = p.o_d2s ? (p.N >> 2) : p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+        float v[32];
+        tc_ld32(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 32; j++) v[j] += s_bias[c0 + j];
+        if (valid) {
+            float *dst;
+            const int ncol = n0 + c0;
+            if (!p.o_d2s) {
+                dst = O + ((long long)(b * p.H + y) * p.W + x) * p.ldo + p.o_coff + ncol;
+            } else {             // N = 4*Co: column block (phase, co) -> pixel (2y+py, 2x+px); a 32-column block never straddles phases
+                const int ph = ncol / Co, co = ncol - ph * Co;
+                dst = O + ((long long)(b * 2 * p.H + 2 * y + (ph >> 1)) * (2 * p.W) + 2 * x + (ph & 1)) * p.ldo + p.o_coff + co;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        }
+        if (p.stats) {
+            // column sums over this warp's 32 rows: butterfly transpose-reduce, 31 shuffles per quantity; lane j ends with column c0+j
+            float s[32], q[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) { s[j] = valid ? v[j] : 0.f; q[j] = s[j] * s[j]; }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                const bool up = lane & w;
+#pragma unroll
+                for (int j = 0; j < w; j++) {
+                    float keep_s = up ? s[j + w] : s[j], send_s = up ? s[j] : s[j + w];
+                    float keep_q = up ? q[j + w] : q[j], send_q = up ? q[j] : q[j + w];
+                    s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
+                    q[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
+                }
+            }
+            atomicAdd(&s_sum[c0 + lane], s[0]);
+            atomicAdd(&s_sq[c0 + lane], q[0]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (p.stats) {
+        double *st = p.stats + g * p.stats_gs;
+        for (int i = threadIdx.x; i < BN; i += 128) {
+            if (n0 + i < p.N) {
+                atomicAdd(&st[n0 + i], (double)s_sum[i]);
+                atomicAdd(&st[p.N + n0 + i], (double)s_sq[i]);
+            }
+        }
+    }
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(BN) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+// pixel box of a 128-pixel tile
+bool tile_geometry(int H, int W, int &bw, int &bh, int &bn) {
+    if (W >= 32) {
+        if (W % 32) return false;
+        bw = 32;
+    } else {
+        if (!pow2(W) || W < 2) return false;
+        bw = W;
+    }
+    int rest = BM / bw;
+    if (H >= rest) {
+        if (H % rest) return false;
+        bh = rest; bn = 1;
+    } else {
+        if (!pow2(H)) return false;
+        bh = H; bn = rest / H;
+    }
+    return bw * bh * bn == BM;
+}
+
+int tmap_dtype() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECVAD_TMA_TF32_ROUND");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v;
+}
+
+int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
+
+template <int BN, int STAGES>
+int launch(const CUtensorMap &tmA, const CUtensorMap &tmB, const TcParams &tp, dim3 grid, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        VV_CK(cudaFuncSetAttribute(k_igemm_tc<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<BN, STAGES>::BYTES));
+        attr = true;
+    }
+    k_igemm_tc<BN, STAGES><<<grid, 128, Smem<BN, STAGES>::BYTES, st>>>(tmA, tmB, tp);
+    VV_CKL();
+    return 0;
+}
+
+}  // namespace
+
+bool vv_igemm_tc_supported(const VvIGemm &p) {
+    int bw, bh, bn;
+    if (!encode_fn()) return false;
+    if (p.Kt % KS || p.N % 32 || p.N < 32) return false;
+    if (p.lda % 4 || p.a_coff % 4 || p.ldo % 4 || p.o_coff % 4) return false;
+    if (((uintptr_t)p.A) % 16 || ((uintptr_t)p.Wt) % 16 || ((uintptr_t)p.O) % 16) return false;
+    if (p.a_s2d && ((p.Kt / 4) % KS)) return false;
+    if (p.o_d2s && ((p.N / 4) % 32)) return false;
+    if (p.G > 1 && (p.a_gs != (long long)p.B * p.H * p.W * (p.a_s2d ? 4 : 1) * p.lda)) return false;   // groups must be contiguous images
+    if (p.G > 1 && p.w_gs != (long long)p.taps.n * p.N * p.Kt) return false;
+    if (!tile_geometry(p.H, p.W, bw, bh, bn)) return false;
+    return true;
+}
+
+int vv_launch_igemm_tc(const VvIGemm &p, cudaStream_t st) {
+    VV_REQUIRE(vv_igemm_tc_supported(p), "igemm_tc: unsupported shape (Kt=%d N=%d H=%d W=%d)", p.Kt, p.N, p.H, p.W);
+    EncodeTiledFn enc = encode_fn();
+    TcParams tp;
+    memset(&tp, 0, sizeof(tp));
+    tp.B = p.B; tp.H = p.H; tp.W = p.W; tp.G = p.G;
+    tile_geometry(p.H, p.W, tp.bw, tp.bh, tp.bn);
+    tp.tiles_x = p.W / tp.bw; tp.tiles_y = p.H / tp.bh; tp.tiles_n = (p.B + tp.bn - 1) / tp.bn;
+    tp.ntaps = p.taps.n; tp.kchunks = p.Kt / KS; tp.cq = p.a_s2d ? p.Kt / 4 : 0;
+    for (int t = 0; t < 9; t++) { tp.dy[t] = p.taps.dy[t]; tp.dx[t] = p.taps.dx[t]; }
+    tp.N = p.N; tp.O = p.O; tp.o_gs = p.o_gs; tp.ldo = p.ldo; tp.o_coff = p.o_coff; tp.o_d2s = p.o_d2s;
+    tp.bias = p.bias; tp.bias_gs = p.bias_gs; tp.stats = p.stats; tp.stats_gs = p.stats_gs;
+
+    const CUtensorMapDataType dt = tmap_dtype() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    alignas(64) CUtensorMap tmA, tmB;
+    {
+        const int sc = p.a_s2d ? 2 : 1;
+        const cuuint64_t C = p.a_s2d ? p.Kt / 4 : p.Kt;
+        cuuint64_t dims[4] = {C, (cuuint64_t)sc * p.W, (cuuint64_t)sc * p.H, (cuuint64_t)p.G * p.B};
+        cuuint64_t strides[3] = {(cuuint64_t)p.lda * 4, (cuuint64_t)sc * p.W * p.lda * 4, (cuuint64_t)sc * p.H * sc * p.W * p.lda * 4};
+        cuuint32_t box[4] = {KS, (cuuint32_t)(sc * tp.bw), (cuuint32_t)(sc * tp.bh), (cuuint32_t)tp.bn};
+        cuuint32_t estr[4] = {1, (cuuint32_t)sc, (cuuint32_t)sc, 1};
+        CUresult r = enc(&tmA, dt, 4, (void *)(p.A + p.a_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        VV_REQUIRE(r == CUDA_SUCCESS, "igemm_tc: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
+    }
+    const int bn_tile = pick_bn(p.N);
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)p.Kt, (cuuint64_t)p.N, (cuuint64_t)p.taps.n * p.G};
+        cuuint64_t strides[2] = {(cuuint64_t)p.Kt * 4, (cuuint64_t)p.N * p.Kt * 4};
+        cuuint32_t box[3] = {KS, (cuuint32_t)bn_tile, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = enc(&tmB, dt, 3, (void *)p.Wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        VV_REQUIRE(r == CUDA_SUCCESS, "igemm_tc: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
+    }
+    dim3 grid(tp.tiles_x * tp.tiles_y * tp.tiles_n, p.N / bn_tile, p.G);
+    if (bn_tile == 128) return launch<128, 3>(tmA, tmB, tp, grid, st);
+    if (bn_tile == 64) return launch<64, 4>(tmA, tmB, tp, grid, st);
+    return launch<32, 4>(tmA, tmB, tp, grid, st);
+}
+
+// weight-gradient contraction on tensor cores: not built yet (falls back to the fp32 SIMT tiles)
 bool vv_wgrad_tc_supported(const VvWGrad &) { return false; }
-int vv_launch_igemm_tc(const VvIGemm &, cudaStream_t) { return vv_set_err(-3, "tcgen05 igemm not built"); }
 int vv_launch_wgrad_tc(const VvWGrad &, cudaStream_t) { return vv_set_err(-3, "tcgen05 wgrad not built"); }
