@@ -171,6 +171,11 @@ int vecvad_net_debug_read(vecvad_net *net, int kind, int index, float *dst, int6
 int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
                            float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream);
 
+/* weight gradient of the same convolution: dw [cout,cin,3,3] (PyTorch layout, overwritten) from in [B,H,W,cin] and
+ * grad_out [B,H,W,cout] (NHWC, dense).  scratch: >= 9*cout*cin floats. */
+int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
+                         int cin, int cout, int use_tc, vecvad_stream stream);
+
 /* cube staging: uint8 cubes [N,T,S,S,3] (+ float flow [N,T_of,S,S,2]) -> x [N,3T,S,S] float /255, x_of [N,2*T_of,S,S]
  * == cube_to_train_dataset + ToTensor + collate (vad_datasets.py:130-168). */
 int vecvad_cubes_to_tensors(const uint8_t *raw, const float *flow, float *x, float *x_of, int n, int t_raw, int t_of, int patch,

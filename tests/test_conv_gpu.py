@@ -59,3 +59,24 @@ def test_tf32_error_is_unbiased():
     got, _ = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, 1, want_stats=False)
     rel = ((got.cpu().double() - want) / want)
     assert abs(rel.mean().item()) < 1e-4, rel.mean().item()
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('shape', SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32)])
+def test_conv3x3_wgrad(shape, use_tc):
+    """dW of the convolution = autograd of conv2d (what loss.backward() computes in train.py:401)."""
+    b, h, wd, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + 1)
+    x = torch.randn(b, cin, h, wd, generator=g)
+    go = torch.randn(b, cout, h, wd, generator=g)
+    w = torch.zeros(cout, cin, 3, 3, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x.double(), w, None, padding=1).backward(go.double())
+    want = w.grad
+    dw = torch.empty(cout, cin, 3, 3, device='cuda')
+    scratch = torch.empty(9 * cout * cin, device='cuda')
+    xn, gn = x.permute(0, 2, 3, 1).contiguous().cuda(), go.permute(0, 2, 3, 1).contiguous().cuda()
+    rc = _lib.lib().vecvad_conv3x3_wgrad(_lib.ptr(xn), cin, _lib.ptr(gn), _lib.ptr(dw), _lib.ptr(scratch), b, h, wd, cin, cout, int(use_tc),
+                                         _lib.cur_stream())
+    _lib.check(rc, 'conv3x3_wgrad')
+    err = (dw.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert err < (3e-3 if use_tc else 2e-5), err

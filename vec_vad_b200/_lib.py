@@ -23,7 +23,7 @@ SYMBOLS = [
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
     'vecvad_net_create', 'vecvad_net_destroy', 'vecvad_net_workspace_bytes', 'vecvad_net_bind',
     'vecvad_net_forward', 'vecvad_net_backward', 'vecvad_net_losses', 'vecvad_adam_step',
-    'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_cubes_to_tensors',
+    'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_cubes_to_tensors',
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
     L.vecvad_adam_step.argtypes = [p, p, p, p, i64, f, f, f, f, f, i, f, p]
     L.vecvad_net_debug_read.argtypes = [p, i, i, p, i64, C.POINTER(i64), p]
     L.vecvad_conv3x3_forward.argtypes = [p, i, p, p, p, p, p, i, i, i, i, i, i, p]
+    L.vecvad_conv3x3_wgrad.argtypes = [p, i, p, p, p, i, i, i, i, i, i, p]
     L.vecvad_cubes_to_tensors.argtypes = [p, p, p, p, i, i, i, i, p]
     if L.vecvad_abi_version() != ABI_VERSION:
         raise RuntimeError('vec_vad_b200: libvecvad.so ABI %d != binding ABI %d -- rebuild' % (L.vecvad_abi_version(), ABI_VERSION))

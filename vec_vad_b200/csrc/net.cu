@@ -529,6 +529,30 @@ extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w
     return vv_launch_igemm_simt(p, st);
 }
 
+// ---- single-op export: weight gradient of the 3x3 pad-1 convolution, dw[cout][cin][3][3] = sum_pixels grad_out x shifted in
+extern "C" int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
+                                    int cin, int cout, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(in && grad_out && dw && scratch, "conv3x3_wgrad: null argument");
+    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && ld_in >= cin && ld_in % 4 == 0, "conv3x3_wgrad: cin/cout must be multiples of 16");
+    cudaStream_t st = (cudaStream_t)stream;
+    VV_CK(cudaMemsetAsync(scratch, 0, 9LL * cout * cin * sizeof(float), st));
+    VvWGrad w;
+    memset(&w, 0, sizeof(w));
+    w.A = in; w.lda = ld_in; w.Kt = cin; w.B = batch; w.H = h; w.W = wd;
+    w.Gd = grad_out; w.ldg = cout; w.N = cout; w.taps = taps3x3(+1); w.dW = scratch; w.G = 1;
+    int r;
+    if (use_tc) {
+        VV_REQUIRE(vv_wgrad_tc_supported(w), "conv3x3_wgrad: shape not supported by the tcgen05 path");
+        r = vv_launch_wgrad_tc(w, st);
+    } else {
+        r = vv_launch_wgrad_simt(w, st);
+    }
+    if (r) return r;
+    VvIntG slot;
+    memset(&slot, 0, sizeof(slot));
+    return vv_scatter_conv_wgrad(scratch, 0, cout, cin, cin, dw, slot, 0, 0, 1, st);
+}
+
 extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
                                      vecvad_stream stream) {
     VV_REQUIRE(n && n->ws && dst && n_floats && n->lastB > 0, "debug_read: net not bound / no forward yet");
