@@ -185,14 +185,28 @@ def run_ours(args):
     clocks = clk.stop() if rank == 0 else None
     ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
     final_loss = losses.cpu().tolist()
+    # ---- per-kernel-class breakdown (separate, untimed pass; CUDA events on the launch stream around every launch)
+    prof = None
+    psteps = min(5, args.steps)
+    if rank == 0:
+        _lib.profile_begin()
+    for i in range(psteps):            # every rank steps (the gradient all-reduce is collective); rank 0 records
+        step_dev(i)
+    if rank == 0:
+        prof = {k: (ms / psteps, fl / psteps, la // psteps) for k, (ms, fl, la) in _lib.profile_end().items()}
+    barrier()
     if rank == 0:
         pk, src = peaks()
         value = world * B / (ms_dev * 1e-3)
-        tf = value * FLOPS_PER_STC[args.net] / 1e12 / world      # per-GPU tensor-pipe rate of the step's contractions
+        step_tf = value * FLOPS_PER_STC[args.net] / 1e12 / world      # per-GPU rate of the step's contractions over the WHOLE step
         peak = pk['bf16_tflops_sustained'] if 'bf16_tflops_sustained' in pk else pk['bf16_tflops']
+        dom = max((k for k in prof if prof[k][1] > 0), key=lambda k: prof[k][0])
+        dom_ms, dom_fl, dom_n = prof[dom]
+        dom_tf = dom_fl / (dom_ms * 1e-3) / 1e12
+        tf32 = not args.simt
         line = {'metric': 'STCs/sec (train step, device-timed)', 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'f32' if args.simt else 'tf32', 'data': 'synthetic',
+                'dtype': 'tf32' if tf32 else 'f32', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': B, 'global_batch': world * B,
                            'parallelism': 'dp%d' % world, 'input_pool_batches': P,
                            'l2': 'per-step working set (activations + gradients, >3 GB at batch 128) exceeds the 126 MB L2; inputs rotate over %d batches' % P,
@@ -200,9 +214,15 @@ def run_ours(args):
                 'clocks': clocks, 'gpu_launches': int(launches),
                 'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'STC/s', 'ms_per_step': ms_e2e,
                         'h2d_bytes_per_step': int(host_raw[0].numel() + 4 * host_flow[0].numel()), 'd2h_bytes_per_step': 8},
-                'roofline': {'bound': 'tensor', 'achieved': tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': tf / peak, 'traffic': None,
-                             'note': 'whole-step contraction FLOPs (%.3f GFLOP/STC) / step time, per GPU; peak = %s sustained bf16 cuBLAS (%s)'
-                                     % (FLOPS_PER_STC[args.net] / 1e9, src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md')}}
+                'roofline': {'bound': 'tensor', 'kernel': dom, 'achieved': dom_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dom_tf / peak,
+                             'traffic': None, 'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / ms_dev,
+                             'peak_tf32': peak / 2 if tf32 else None, 'frac_of_tf32_peak': dom_tf / (peak / 2) if tf32 else None,
+                             'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak,
+                             'note': 'achieved = algorithmic conv FLOPs of the dominant kernel class / its CUDA-event time (sum over its '
+                                     'launches in one step, measured live in a separate pass); peak = %s sustained bf16 cuBLAS (%s); the '
+                                     'tiles are kind::tf32 whose hardware rate is half the bf16 rate (peak_tf32)'
+                                     % (src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md fallback')},
+                'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in prof.items() if v[2] > 0}}
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             v, dt = cpu_reference_steps(args.net, B, 4, 1, threads)

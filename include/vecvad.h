@@ -38,6 +38,14 @@ const char *vecvad_last_error(void);
 /* number of CUDA kernels this library has launched so far in this process (bench.py: gpu_launches) */
 uint64_t vecvad_launch_count(void);
 
+/* per-kernel-class device timing (CUDA events on the launch stream) for bench.py's roofline leg.
+ * classes: 0 conv/dgrad tcgen05 tiles, 1 wgrad tcgen05 tiles, 2 conv/dgrad fp32 SIMT tiles, 3 wgrad fp32 SIMT tiles,
+ *          4 BatchNorm apply/backward passes, 5 (unused).  begin() resets and enables; end() synchronises the device, disables,
+ * and returns per class the summed milliseconds, algorithmic FLOPs and launch counts since begin(). */
+#define VECVAD_PROFILE_CLASSES 6
+int vecvad_profile_begin(void);
+int vecvad_profile_end(double *ms, double *flops, int64_t *launches, int n_classes);
+
 /* ------------------------------------------------------------------------------------------
  * (1) FlowNet2 ops.  All tensors are contiguous NCHW fp32 on the current device (the reference
  * asserts contiguity: functions/correlation.py:17-18, functions/resample2d.py:9-10).

@@ -1,0 +1,95 @@
+"""Host-side logic of the N>1 path on CPU: world_size-2 gloo processes exercise shard bounds, the summing gradient
+reduction + 1/world scale (== DataParallel's gradient of the global-batch mean loss), state broadcast and score gather.
+The oracle UNet set plays the model: 2 ranks x B/2 cubes with all-reduced gradients must match 1 process x B cubes up to
+the BatchNorm statistics being rank-local (checked with BatchNorm in eval mode so the comparison is exact)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from vec_vad_b200 import ddp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_shard_bounds_cover_exactly():
+    for n in (0, 1, 7, 128, 129, 1000):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                b, e = ddp.shard_bounds(n, r, world)
+                assert 0 <= b <= e <= n
+                seen += list(range(b, e))
+            assert seen == list(range(n))
+            sizes = [ddp.shard_bounds(n, r, world)[1] - ddp.shard_bounds(n, r, world)[0] for r in range(world)]
+            assert max(sizes) <= (n + world - 1) // world
+
+
+def _worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    r, local, w = ddp.init_from_env('gloo')
+    assert (r, w) == (rank, world)
+    from oracle import unet_oracle as orc
+    kw = dict(features_root=16, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
+    torch.manual_seed(100 + rank)                      # deliberately different initial weights per rank
+    m = orc.CompletionNetOracle('net4', **kw).eval()   # eval: BatchNorm uses (identical) running stats -> exact sharding identity
+
+    class Flat:                                        # the three tensors broadcast_state() touches
+        pass
+    flat = torch.cat([p.data.reshape(-1) for p in m.parameters()])
+    holder = Flat()
+    holder._pflat, holder._sflat, holder._nbt = flat, torch.zeros(4), torch.zeros(2, dtype=torch.long)
+    ddp.broadcast_state(holder, src=0)
+    off = 0
+    for p in m.parameters():
+        p.data.copy_(flat[off:off + p.numel()].view_as(p))
+        off += p.numel()
+    raw_u8, flow = orc.synthetic_cubes(6, t_of=1, seed=5)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    b, e = ddp.shard_bounds(6, rank, world)
+    mse = torch.nn.MSELoss()
+    of_o, raw_o, of_t, raw_t = m(x[b:e], x_of[b:e])
+    (mse(raw_t, raw_o) + mse(of_t, of_o)).backward()
+    g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+    scale = ddp.GradReducer(bucket_bytes=1 << 20)(g)
+    g = g * scale
+    scores = ((raw_t - raw_o.detach()) ** 2).sum(dim=(1, 2, 3))
+    allscores = ddp.gather_scores(scores, 6, rank, world)
+    if rank == 0:
+        ret['grad'] = g.numpy()
+        ret['scores'] = allscores.numpy()
+        ret['w0'] = flat.numpy()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_equals_global_batch_gradient():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, port, ret), nprocs=world, join=True)
+    from oracle import unet_oracle as orc
+    kw = dict(features_root=16, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
+    torch.manual_seed(100)
+    torch.set_num_threads(1)
+    m = orc.CompletionNetOracle('net4', **kw).eval()
+    np.testing.assert_array_equal(ret['w0'], torch.cat([p.data.reshape(-1) for p in m.parameters()]).numpy())   # rank 0's weights won
+    raw_u8, flow = orc.synthetic_cubes(6, t_of=1, seed=5)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    mse = torch.nn.MSELoss()
+    of_o, raw_o, of_t, raw_t = m(x, x_of)
+    (mse(raw_t, raw_o) + mse(of_t, of_o)).backward()
+    g = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).numpy()
+    np.testing.assert_allclose(ret['grad'], g, rtol=1e-4, atol=1e-7)
+    want = ((raw_t - raw_o.detach()) ** 2).sum(dim=(1, 2, 3)).numpy()
+    np.testing.assert_allclose(ret['scores'], want, rtol=1e-5)

@@ -17,7 +17,7 @@ ABI_VERSION = 1
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
-    'vecvad_abi_version', 'vecvad_last_error', 'vecvad_launch_count',
+    'vecvad_abi_version', 'vecvad_last_error', 'vecvad_launch_count', 'vecvad_profile_begin', 'vecvad_profile_end',
     'vecvad_correlation_out_shape', 'vecvad_correlation_forward', 'vecvad_correlation_backward',
     'vecvad_resample2d_forward', 'vecvad_resample2d_backward',
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
@@ -59,6 +59,7 @@ def lib():
     L.vecvad_abi_version.restype = i
     L.vecvad_last_error.restype = C.c_char_p
     L.vecvad_launch_count.restype = C.c_uint64
+    L.vecvad_profile_end.argtypes = [p, p, p, i]
     L.vecvad_correlation_out_shape.argtypes = [i] * 7 + [ip, ip, ip]
     L.vecvad_correlation_forward.argtypes = [p, p, p] + [i] * 10 + [p]
     L.vecvad_correlation_backward.argtypes = [p, p, p, p, p] + [i] * 10 + [p]
@@ -84,6 +85,21 @@ def lib():
         raise RuntimeError('vec_vad_b200: libvecvad.so ABI %d != binding ABI %d -- rebuild' % (L.vecvad_abi_version(), ABI_VERSION))
     _lib = L
     return L
+
+
+PROFILE_CLASSES = ['conv_dgrad_tcgen05', 'wgrad_tcgen05', 'conv_dgrad_simt', 'wgrad_simt', 'batchnorm', 'other']
+
+
+def profile_begin():
+    check(lib().vecvad_profile_begin(), 'profile_begin')
+
+
+def profile_end():
+    """-> {class: (ms, flops, launches)} accumulated since profile_begin()"""
+    n = len(PROFILE_CLASSES)
+    ms, fl, la = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+    check(lib().vecvad_profile_end(ms, fl, la, n), 'profile_end')
+    return {PROFILE_CLASSES[k]: (ms[k], fl[k], la[k]) for k in range(n)}
 
 
 def check(rc, what=''):

@@ -66,6 +66,16 @@ struct VvWGrad {
     int G;
 };
 
+// ---- per-kernel-class event timing (prof.cu)
+enum { VV_PROF_IGEMM_TC = 0, VV_PROF_WGRAD_TC, VV_PROF_IGEMM_SIMT, VV_PROF_WGRAD_SIMT, VV_PROF_BN, VV_PROF_OTHER, VV_PROF_CLASSES };
+bool vv_prof_on();
+struct VvProfScope {
+    int idx;
+    cudaStream_t st;
+    VvProfScope(int cls, double flops, cudaStream_t st);
+    ~VvProfScope();
+};
+
 int vv_launch_igemm_simt(const VvIGemm &p, cudaStream_t st);
 int vv_launch_wgrad_simt(const VvWGrad &p, cudaStream_t st);
 // tcgen05 (kind::tf32) tiles; return -3 if the shape is not supported by the tensor-core path.

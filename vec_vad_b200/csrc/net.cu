@@ -131,13 +131,18 @@ VvTaps taps2x2(int sign) {
     return t;
 }
 
-int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st) {
-    if (n->cfg.use_tensor_cores && vv_igemm_tc_supported(p)) return vv_launch_igemm_tc(p, st);
-    return vv_launch_igemm_simt(p, st);
+// algorithmic FLOPs of one contraction launch: 2 * pixels * N * K * taps over all groups
+double igemm_flops(int B, int H, int W, int N, int K, int taps, int G) { return 2.0 * B * H * W * (double)N * K * taps * G; }
+
+int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
+    const bool tc = n->cfg.use_tensor_cores && vv_igemm_tc_supported(p);
+    VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
+    return tc ? vv_launch_igemm_tc(p, st) : vv_launch_igemm_simt(p, st);
 }
-int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st) {
-    if (n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p)) return vv_launch_wgrad_tc(p, st);
-    return vv_launch_wgrad_simt(p, st);
+int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
+    const bool tc = n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p);
+    VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
+    return tc ? vv_launch_wgrad_tc(p, st) : vv_launch_wgrad_simt(p, st);
 }
 
 struct Flow {   // buffer wiring of one forward for batch B
@@ -301,8 +306,9 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         p.bias = n->vec[u]; p.bias_gs = 3LL * N;
         p.stats = training ? n->stats[u] : nullptr; p.stats_gs = 2LL * N;
         p.G = G;
-        int r = run_igemm(n, p, st);
+        int r = run_igemm(n, p, st, n->uC[u]);
         if (r) return r;
+        VvProfScope ps(VV_PROF_BN, 0, st);
         VvBnApply q;
         memset(&q, 0, sizeof(q));
         q.Z = n->Z[u]; q.z_gs = p.o_gs;
@@ -413,7 +419,11 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         q.save = n->save[u]; q.save_gs = 4LL * N;
         q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
         q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.gamma_off = c.bn_w[u]; q.beta_off = c.bn_b[u];
-        int rr = vv_bn_bwd(q, G, st);
+        int rr;
+        {
+            VvProfScope ps(VV_PROF_BN, 0, st);
+            rr = vv_bn_bwd(q, G, st);
+        }
         if (rr) return rr;
         // weight gradient
         const View &in = f.in[u];
@@ -423,7 +433,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.B = B; w.H = H; w.W = H;
         w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
         w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
-        if ((rr = run_wgrad(n, w, st))) return rr;
+        if ((rr = run_wgrad(n, w, st, n->uC[u]))) return rr;
         if ((rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, st)))
             return rr;
         // (pre-BN conv bias: its gradient is exactly zero in training mode -- left at the memset value; the reference

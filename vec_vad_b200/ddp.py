@@ -1,0 +1,86 @@
+"""Data-parallel plumbing for the completion-UNet set: one process per GPU, cubes sharded by batch, ONE summing
+all-reduce of the flat gradient buffer per step over NCCL (NVLink 5 / NVSwitch), BatchNorm statistics rank-local.
+
+Replaces the reference's single-process ``torch.nn.DataParallel`` (train.py:289,375), which scatters the batch along
+dim 0, keeps per-replica BatchNorm statistics and reduce-adds the gradients onto GPU 0.  Same arithmetic here:
+every rank runs the full UNet set on B/world cubes, the per-rank losses are means over the local shard, so the
+global-batch gradient is the average of the rank gradients = sum-all-reduce followed by 1/world (folded into Adam's
+``grad_scale``, include/vecvad.h vecvad_adam_step).  Rank 0's running statistics are the ones saved (DataParallel keeps
+replica 0's).
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n, rank, world):
+    """[begin, end) of rank's contiguous shard of n cubes; shard sizes differ by at most one (DataParallel's scatter
+    gives the first chunks ceil(n/world) items; the same rule is used here)."""
+    chunk = (n + world - 1) // world
+    b = min(n, rank * chunk)
+    return b, min(n, b + chunk)
+
+
+def init_from_env(backend=None):
+    """torchrun / torch.distributed.run rendezvous (RANK, LOCAL_RANK, WORLD_SIZE, MASTER_ADDR, MASTER_PORT)."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        kw = {}
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            kw['device_id'] = torch.device('cuda', local)
+        dist.init_process_group(backend, **kw)
+    return rank, local, world
+
+
+class GradReducer:
+    """Callable handed to ``CompletionNet.train_step(reduce_grads=...)``: sums the flat gradient buffer over the ranks
+    in place on the current stream and returns the scale Adam must apply (1/world)."""
+
+    def __init__(self, group=None, bucket_bytes=0):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_elems = bucket_bytes // 4
+
+    def __call__(self, flat):
+        if self.world == 1:
+            return 1.0
+        if self.bucket_elems and flat.numel() > self.bucket_elems:
+            # bucketed: lets NCCL pipeline the buckets; each is contiguous in the flat buffer
+            works = [dist.all_reduce(flat[o:o + self.bucket_elems], group=self.group, async_op=True)
+                     for o in range(0, flat.numel(), self.bucket_elems)]
+            for w in works:
+                w.wait()
+        else:
+            dist.all_reduce(flat, group=self.group)
+        return 1.0 / self.world
+
+
+def broadcast_state(model, src=0, group=None):
+    """Make every rank start from rank ``src``'s parameters, statistics and step counters (DataParallel replicates the
+    module from GPU 0 every step; here it is done once, the all-reduced gradients keep the replicas identical)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    for t in (model._pflat, model._sflat, model._nbt):
+        dist.broadcast(t, src=src, group=group)
+
+
+def gather_scores(local_scores, n_total, rank, world, group=None):
+    """Concatenate per-rank score vectors (shards from ``shard_bounds``) in rank order on every rank."""
+    if world == 1:
+        return local_scores
+    chunk = (n_total + world - 1) // world
+    pad = torch.zeros(chunk, dtype=local_scores.dtype, device=local_scores.device)
+    pad[:local_scores.numel()] = local_scores
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad, group=group)
+    parts = []
+    for r in range(world):
+        b, e = shard_bounds(n_total, r, world)
+        parts.append(out[r][:e - b])
+    return torch.cat(parts)
