@@ -137,7 +137,48 @@ def dataset_fixture():
     print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
 
 
+def index_fixture():
+    """context_range (vad_datasets.py:277-354) of the reference on synthetic video-length lists; -1 rows = it raised."""
+    class Obj:
+        pass
+    out = {}
+    layouts = {'a': [10, 7, 12], 'b': [5, 5], 'c': [3, 20], 'd': [9]}
+    for lname, lens in layouts.items():
+        fvi = []
+        for v, n in enumerate(lens):
+            fvi += [v + 1] * n
+        for mode in ('elastic', 'predict', 'hard'):
+            for c in (1, 2, 4):
+                o = Obj()
+                o.border_mode, o.context_frame_num, o.tot_frame_num, o.frame_video_idx = mode, c, len(fvi), fvi
+                width = c + 1 if mode == 'predict' else 2 * c + 1
+                res = -np.ones((len(fvi), width), dtype=np.int64)
+                for i in range(len(fvi)):
+                    try:
+                        import io, contextlib
+                        with contextlib.redirect_stdout(io.StringIO()):
+                            r = ref_ds.ped_dataset.context_range(o, i)
+                        res[i] = np.array(r)
+                    except NotImplementedError:
+                        pass
+                out['%s|%s|%d' % (lname, mode, c)] = res
+        out['layout_' + lname] = np.array(lens)
+    # AUROC of the reference's save_roc_pr_curve_data on seeded synthetic scores / labels
+    rng = np.random.RandomState(11)
+    labels = (rng.rand(400) > 0.7)
+    scores = rng.randn(400) + 1.2 * labels
+    import io, contextlib, tempfile
+    with contextlib.redirect_stdout(io.StringIO()):
+        auc = ref_utils.save_roc_pr_curve_data(scores, labels, os.path.join(tempfile.mkdtemp(), 'r.npz'))
+    path = os.path.join(HERE, 'index_paths.npz')
+    np.savez_compressed(path, roc_scores=scores, roc_labels=labels, roc_auc=np.float64(auc), **out)
+    print('wrote', path, os.path.getsize(path) // 1024, 'KiB')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'index':
+        index_fixture()
+        sys.exit(0)
     common = dict(features_root=32, tot_raw_num=5, border_mode='predict', rawRange=None)
     unet_fixture('net4_flow_b2', SelfCompleteNet4, dict(common, tot_of_num=1, useFlow=True, padding=False), 2, 1)
     unet_fixture('net4_noflow_b4', SelfCompleteNet4, dict(common, tot_of_num=1, useFlow=False, padding=False), 4, 1)
@@ -146,3 +187,4 @@ if __name__ == '__main__':
     unet_fixture('net1raw1of_b2', SelfCompleteNet1raw1of,
                  dict(features_root=32, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False), 2, 1)
     dataset_fixture()
+    index_fixture()

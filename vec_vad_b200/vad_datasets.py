@@ -1,6 +1,10 @@
 """Dataset surface of the reference's ``vad_datasets.py`` for the hot path.
 
 Kept API (same names, argument meaning, return types):
+  * ``unified_dataset_interface`` + ``ped_dataset`` / ``avenue_dataset`` / ``shanghaiTech_dataset``     vad_datasets.py:95-114,170,404,613
+    (frame-folder datasets; host I/O, not accelerated -- their integer index paths are restated bit-exactly:
+    ``context_range`` vad_datasets.py:277-354, bbox ceil/crop :74-75)
+  * ``bbox_collate``, ``get_inputs``                                                                    vad_datasets.py:18-25,48-68
   * ``cube_to_train_dataset(data, target=None, tranform=transform)``   vad_datasets.py:130-168
     (the misspelt ``tranform`` keyword is the reference's)
   * ``transform`` / ``ToTensor``                                        vad_datasets.py:12-14
@@ -14,6 +18,9 @@ New, device side (the feed for >100k STC/s):
     shuffled mini-batches gathered and converted on the device.
 """
 import ctypes as C
+import glob
+import os
+from collections import OrderedDict
 
 import numpy as np
 import torch
@@ -106,6 +113,232 @@ class cube_to_train_dataset(Dataset):
         if self.target is None:
             return tf(_fold_time(cur[:-1])), tf(cur[-1])
         return tf(_fold_time(cur)), tf(_fold_time(self.target[indice])), tf(_fold_time(cur.copy()))
+
+
+# ------------------------------------------------------------------------------------------ frame-folder datasets
+def get_inputs(file_addr):
+    ext = file_addr.split('.')[-1]
+    if ext == 'mat':
+        import scipy.io as sio
+        return sio.loadmat(file_addr, verify_compressed_data_integrity=False)['uv']
+    if ext == 'npy':
+        return np.load(file_addr)
+    import cv2
+    return cv2.imread(file_addr)
+
+
+def context_range(indice, frame_video_idx, context_frame_num, border_mode):
+    """Indices of the frames forming the temporal context of frame ``indice`` (vad_datasets.py:277-354; integer path, bit-exact).
+
+    ``frame_video_idx[i]`` is the 1-based video a frame belongs to.  A context never crosses a video boundary: missing frames
+    are replaced by repeating the first / last frame of the same video ('predict' and 'hard'), or the window slides inside
+    the video ('elastic').  Raises NotImplementedError (like the reference) when a video is shorter than the context."""
+    n, c = len(frame_video_idx), context_frame_num
+    if border_mode == 'elastic':
+        if indice - c < 0:
+            indice = c
+        elif indice + c > n - 1:
+            indice = n - 1 - c
+        start, end, need = indice - c, indice + c, 2 * c + 1
+    elif border_mode == 'predict':
+        start, end, need = max(indice - c, 0), indice, c + 1
+    else:
+        start, end, need = max(indice - c, 0), min(indice + c, n - 1), 2 * c + 1
+    center = frame_video_idx[indice]
+    vids = list(frame_video_idx[start:end + 1])
+    pad = need - len(vids)
+    if pad > 0:
+        vids = [vids[0]] * pad + vids if start == 0 else vids + [vids[-1]] * pad
+    rel = np.array(vids) - center
+    offset = int(rel.sum())
+    if rel[0] != 0 and rel[-1] != 0:
+        raise NotImplementedError('The video is too short or the context frame number is too large!')
+    if pad == 0 and offset == 0:
+        return list(range(start, end + 1))
+    if border_mode == 'elastic':
+        return list(range(start - offset, end - offset + 1))
+    if pad > 0 and abs(offset) > 0:
+        raise NotImplementedError('The video is too short or the context frame number is too large!')
+    if border_mode == 'predict':
+        idx = list(range(start - offset, end + 1))
+        return [idx[0]] * max(abs(offset), pad) + idx
+    if offset > 0:
+        idx = list(range(start, end - offset + 1))
+        return idx + [idx[-1]] * offset
+    if offset < 0:
+        idx = list(range(start - offset, end + 1))
+        return [idx[0]] * (-offset) + idx
+    if start == 0:
+        idx = list(range(start, end + 1))
+        return [idx[0]] * pad + idx
+    idx = list(range(start, end + 1))
+    return idx + [idx[-1]] * pad
+
+
+class bbox_collate:
+    def __init__(self, mode):
+        self.mode = mode
+
+    def collate(self, batch):
+        data, target = [x[0] for x in batch], [x[1] for x in batch]
+        if self.mode == 'train':
+            return torch.cat(data, dim=0), target
+        if self.mode == 'test':
+            return data, target
+        raise NotImplementedError
+
+
+class _frame_folder_dataset(Dataset):
+    """Shared body of the three reference dataset classes (which are copies of each other apart from the directory
+    layout and the ground-truth format).  ``__getitem__`` -> (img_batch, gt-or-zeros(1))."""
+
+    def __init__(self, dir, mode='train', context_frame_num=0, border_mode='elastic', file_format=None, all_bboxes=None, patch_size=32):
+        self.dir, self.mode = dir, mode
+        self.videos = OrderedDict()
+        self.all_frame_addr, self.frame_video_idx = [], []
+        self.tot_frame_num = 0
+        self.context_frame_num, self.border_mode = context_frame_num, border_mode
+        self.file_format, self.all_bboxes, self.patch_size = file_format, all_bboxes, patch_size
+        self.return_gt = False
+        if mode not in ('train', 'test'):
+            raise NotImplementedError
+        self.dataset_init()
+
+    def __len__(self):
+        return self.tot_frame_num
+
+    def _add_videos(self, video_dirs, name_filter=None, per_video=None):
+        idx = 1
+        for video in sorted(video_dirs):
+            name = video.split('/')[-1]
+            if name_filter is not None and name_filter not in name:
+                continue
+            frames = sorted(glob.glob(os.path.join(video, '*' + self.file_format)))
+            self.videos[name] = {'path': video, 'frame': frames, 'length': len(frames)}
+            self.frame_video_idx += [idx] * len(frames)
+            idx += 1
+            if per_video is not None:
+                per_video(name, len(frames))
+        for cont in self.videos.values():
+            self.all_frame_addr += cont['frame']
+        self.tot_frame_num = len(self.all_frame_addr)
+
+    def context_range(self, indice):
+        return context_range(indice, self.frame_video_idx, self.context_frame_num, self.border_mode)
+
+    def _gt(self, indice):
+        raise NotImplementedError
+
+    def __getitem__(self, indice):
+        if self.context_frame_num == 0:
+            img = np.transpose(get_inputs(self.all_frame_addr[indice]), [2, 0, 1])
+        else:
+            img = np.array([np.transpose(get_inputs(self.all_frame_addr[i]), [2, 0, 1]) for i in self.context_range(indice)])
+        if self.all_bboxes is not None:
+            img = get_foreground(img=img, bboxes=self.all_bboxes[indice], patch_size=self.patch_size)
+        img = torch.from_numpy(img)
+        if self.mode == 'test' and self.return_gt:
+            return img, torch.from_numpy(self._gt(indice))
+        return img, torch.zeros(1)
+
+
+class ped_dataset(_frame_folder_dataset):                      # UCSD ped1 / ped2          vad_datasets.py:170-402
+    def __init__(self, dir, mode='train', context_frame_num=0, border_mode='elastic', file_format='.tif', all_bboxes=None, patch_size=32):
+        self.h, self.w = (158, 238) if dir[-1] == '1' else (240, 360)
+        self.all_gt_addr, self.gts = [], OrderedDict()
+        super().__init__(dir, mode, context_frame_num, border_mode, file_format, all_bboxes, patch_size)
+
+    def dataset_init(self):
+        if self.mode == 'train':
+            self._add_videos(glob.glob(os.path.join(self.dir, 'Train', '*')), name_filter='Train')
+            return
+        entries = sorted(glob.glob(os.path.join(self.dir, 'Test', '*')))
+        gt_dirs = [d for d in entries if '_gt' in d]
+        self.return_gt = len(gt_dirs) > 0
+        self._add_videos([d for d in entries if '_gt' not in d and 'Test' in d.split('/')[-1]])
+        for gt in gt_dirs:
+            frames = sorted(glob.glob(os.path.join(gt, '*.bmp')))
+            self.gts[gt.split('/')[-1]] = {'gt_frame': frames}
+            self.all_gt_addr += frames
+
+    def _gt(self, indice):
+        import cv2
+        return cv2.imread(self.all_gt_addr[indice], cv2.IMREAD_GRAYSCALE)
+
+
+class avenue_dataset(_frame_folder_dataset):                   # vad_datasets.py:404-611
+    def __init__(self, dir, mode='train', context_frame_num=0, border_mode='elastic', file_format='.jpg', all_bboxes=None, patch_size=32):
+        self.all_gt = []
+        super().__init__(dir, mode, context_frame_num, border_mode, file_format, all_bboxes, patch_size)
+
+    def dataset_init(self):
+        sub = 'training' if self.mode == 'train' else 'testing'
+        self._add_videos(glob.glob(os.path.join(self.dir, sub, 'frames', '*')))
+        if self.mode == 'test':
+            gt_dir = os.path.join(self.dir, 'ground_truth_demo', 'testing_label_mask')
+            if os.path.exists(gt_dir):
+                import scipy.io as sio
+                self.return_gt = True
+                vols = [sio.loadmat(os.path.join(gt_dir, str(x + 1) + '_label.mat'))['volLabel'] for x in range(len(self.videos))]
+                self.all_gt = np.concatenate(vols, axis=1)
+
+    def _gt(self, indice):
+        return self.all_gt[0, indice]
+
+
+class shanghaiTech_dataset(_frame_folder_dataset):             # vad_datasets.py:613-835
+    def __init__(self, dir, mode='train', context_frame_num=0, border_mode='elastic', file_format='.jpg', all_bboxes=None, patch_size=32):
+        self.save_scene_idx, self.scene_idx, self.scene_num, self.all_gt = [], [], 0, []
+        super().__init__(dir, mode, context_frame_num, border_mode, file_format, all_bboxes, patch_size)
+
+    def dataset_init(self):
+        def per_video(name, nframes):
+            self.save_scene_idx += [int(name[:2])] * nframes      # frames are saved by scene
+            self.scene_idx += [1] * nframes                       # ... and processed as one scene
+        if self.mode == 'train':
+            dirs = sorted(glob.glob(os.path.join(self.dir, 'training', 'videosFrame', '*')))
+        else:   # the two test parts are each sorted, part 1 first (vad_datasets.py:679-681)
+            base = os.path.join(self.dir, 'Testing', 'frames_part')
+            dirs = sorted(glob.glob(os.path.join(base + '1', '*'))) + sorted(glob.glob(os.path.join(base + '2', '*')))
+        self._add_videos_in_order(dirs, per_video)
+        self.scene_num = len(set(self.scene_idx))
+        if self.mode == 'test':
+            gt_dir = os.path.join(self.dir, 'Testing', 'test_frame_mask')
+            if os.path.exists(gt_dir):
+                self.return_gt = True
+                self.all_gt = np.concatenate([np.load(g) for g in sorted(glob.glob(os.path.join(gt_dir, '*')))], axis=0)
+
+    def _add_videos_in_order(self, dirs, per_video):
+        idx = 1
+        for video in dirs:
+            name = video.split('/')[-1]
+            frames = sorted(glob.glob(os.path.join(video, '*' + self.file_format)))
+            self.videos[name] = {'path': video, 'frame': frames, 'length': len(frames)}
+            self.frame_video_idx += [idx] * len(frames)
+            idx += 1
+            per_video(name, len(frames))
+        for cont in self.videos.values():
+            self.all_frame_addr += cont['frame']
+        self.tot_frame_num = len(self.all_frame_addr)
+
+    def _gt(self, indice):
+        return np.array([self.all_gt[indice]])
+
+
+def unified_dataset_interface(dataset_name, dir, mode='train', context_frame_num=0, border_mode='elastic', file_format=None,
+                              all_bboxes=None, patch_size=32):
+    if file_format is None:
+        if dataset_name in ('UCSDped1', 'UCSDped2'):
+            file_format = '.tif'
+        elif dataset_name in ('avenue', 'ShanghaiTech'):
+            file_format = '.jpg'
+        else:
+            raise NotImplementedError
+    cls = {'UCSDped1': ped_dataset, 'UCSDped2': ped_dataset, 'avenue': avenue_dataset, 'ShanghaiTech': shanghaiTech_dataset}.get(dataset_name)
+    if cls is None:
+        raise NotImplementedError
+    return cls(dir=dir, context_frame_num=context_frame_num, mode=mode, border_mode=border_mode, all_bboxes=all_bboxes,
+               patch_size=patch_size, file_format=file_format)
 
 
 # ------------------------------------------------------------------------------------------ device feed
