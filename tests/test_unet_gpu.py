@@ -88,7 +88,7 @@ def test_fused_train_step_and_scoring_match_reference_fixture(name, path, golden
     names, ps, pe = digest(m.state_dict().items())
     ref = g['state_stats_1'][:, 2]
     isb = np.array([str(n).endswith(('conv.0.bias', 'conv.3.bias')) for n in names])
-    np.testing.assert_allclose(ps[~isb, 2], ref[~isb], rtol=5e-3 if not tc else 2e-2, atol=1e-6)
+    np.testing.assert_allclose(ps[~isb, 2], ref[~isb], rtol=5e-3 if not tc else 2e-2, atol=2e-4)   # atol: |step| < lr where |g| ~ eps
     l2 = m.train_step(x, x_of, float(lam[0]), float(lam[1])).cpu().numpy().copy()
     assert abs(l2[0] - float(g['loss_raw_2'])) <= max(50 * tol_loss, 2e-3) * abs(float(g['loss_raw_2']))
 
