@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""Kernel microbench of the FlowNet2 ops at BASELINE.json configs[4]: 1024x436 synthetic frame pairs, 1 GPU.
+
+correlation: conv3 feature maps [B,256,55,128] x2 -> cost volume [B,441,55,128]   (FlowNetC.py:24-30)
+warp       : image [B,3,436,1024] + flow [B,2,436,1024] -> warped (+ fused difference and channel norm)
+Prints one JSON line per op: device time (CUDA events, L2 flushed between iterations), achieved algorithmic GB/s against
+the measured HBM peak (MEASURED_PEAKS.json) and, for the correlation (59 FLOP/B: compute-bound on fp32 FMA), TFLOP/s."""
+import argparse
+import json
+import os
+import sys
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+
+def main():
+    import torch
+    from vec_vad_b200 import flow_ops as ops
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--iters', type=int, default=20)
+    a = ap.parse_args()
+    pk = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(REPO, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(0)
+    B = a.batch
+    f1 = torch.randn(B, 256, 55, 128, generator=g).to(dev)
+    f2 = torch.randn(B, 256, 55, 128, generator=g).to(dev)
+    img0 = torch.rand(B, 3, 436, 1024, generator=g).to(dev)
+    img1 = torch.rand(B, 3, 436, 1024, generator=g).to(dev)
+    flow = (torch.randn(B, 2, 436, 1024, generator=g) * 4).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    corr = ops.Correlation(20, 1, 20, 1, 2, 1)
+    warp = ops.Resample2d()
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        ts = []
+        for _ in range(a.iters):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ts.sort()
+        return ts[len(ts) // 2] * 1e-3
+    rows = [
+        ('correlation_forward', lambda: corr(f1, f2), B * (2 * 256 * 55 * 128 * 4 + 441 * 55 * 128 * 4), B * 2.0 * 441 * 256 * 55 * 128),
+        ('resample2d_forward', lambda: warp(img1, flow), B * (3 + 2 + 3) * 436 * 1024 * 4, 0.0),
+        ('warp_diff_norm_fused', lambda: ops.warp_diff_norm(img0, img1, flow), B * (3 + 3 + 2 + 3 + 3 + 1) * 436 * 1024 * 4, 0.0),
+    ]
+    for name, fn, nbytes, flops in rows:
+        t = timed(fn)
+        line = {'op': name, 'batch': B, 'us': t * 1e6, 'pairs_per_s': B / t, 'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / t / 1e9,
+                'hbm_peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': nbytes / t / 1e9 / pk['hbm_gbs'], 'l2': 'flushed (256 MiB memset) before every timed launch'}
+        if flops:
+            line['tflops_fp32'] = flops / t / 1e12
+        print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

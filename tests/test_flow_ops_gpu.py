@@ -37,6 +37,26 @@ def test_correlation_forward(case):
     np.testing.assert_allclose(got, want, rtol=2e-4, atol=2e-5)
 
 
+def test_correlation_forward_full_size_properties():
+    """BASELINE configs[4] size ([1,256,55,128] maps): size-independent properties instead of the full oracle --
+    (a) linearity in the first argument, (b) the zero-displacement channel equals the channel-mean of f1*f2,
+    (c) a sampled set of outputs equals the direct dot product."""
+    g = torch.Generator().manual_seed(4)
+    f1, f1b, f2 = (torch.randn(1, 256, 55, 128, generator=g).cuda() for _ in range(3))
+    corr = ops.Correlation(20, 1, 20, 1, 2, 1)
+    o1, o1b, o12 = corr(f1, f2), corr(f1b, f2), corr((2 * f1 - 3 * f1b).contiguous(), f2)
+    assert tuple(o1.shape) == (1, 441, 55, 128)
+    torch.testing.assert_close(o12, 2 * o1 - 3 * o1b, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(o1[:, 220], (f1 * f2).mean(1), rtol=1e-4, atol=1e-5)
+    rng = np.random.RandomState(0)
+    a, b = f1.cpu().double(), f2.cpu().double()
+    for _ in range(200):
+        tj, ti, y, x = rng.randint(-10, 11), rng.randint(-10, 11), rng.randint(55), rng.randint(128)
+        y2, x2 = y + 2 * tj, x + 2 * ti
+        want = (a[0, :, y, x] * b[0, :, y2, x2]).sum().item() / 256 if (0 <= y2 < 55 and 0 <= x2 < 128) else 0.0
+        assert abs(o1[0, (tj + 10) * 21 + ti + 10, y, x].item() - want) < 1e-4
+
+
 @pytest.mark.parametrize('case', [(1, 3, 6, 7, 4, 1, 4, 1, 2), (2, 2, 5, 6, 3, 3, 2, 1, 1), (1, 2, 5, 6, 1, 1, 2, 1, 2)])
 def test_correlation_backward(case):
     b, c, h, w, pad, k, md, s1, s2 = case
