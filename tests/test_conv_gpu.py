@@ -30,8 +30,8 @@ SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (5, 16, 16, 32, 64), (3, 8, 
           (1, 8, 8, 256, 128), (2, 16, 16, 128, 64)]
 
 
-@pytest.mark.parametrize('use_tc', [0, 1])
-@pytest.mark.parametrize('shape', SHAPES)
+@pytest.mark.parametrize('use_tc', [0, 1, 2])
+@pytest.mark.parametrize('shape', SHAPES + [(130, 32, 32, 32, 32), (70, 16, 16, 64, 64), (150, 4, 4, 256, 256)])
 def test_conv3x3_forward(shape, use_tc):
     b, h, wd, cin, cout = shape
     g = torch.Generator().manual_seed(sum(shape))
@@ -56,13 +56,13 @@ def test_tf32_error_is_unbiased():
     x = torch.rand(4, 64, 16, 16, generator=g) + 0.5
     w = torch.rand(64, 64, 3, 3, generator=g) + 0.5
     want = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1)
-    got, _ = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, 1, want_stats=False)
+    got, _ = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, 2, want_stats=False)
     rel = ((got.cpu().double() - want) / want)
     assert abs(rel.mean().item()) < 1e-4, rel.mean().item()
 
 
-@pytest.mark.parametrize('use_tc', [0, 1])
-@pytest.mark.parametrize('shape', SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32)])
+@pytest.mark.parametrize('use_tc', [0, 1, 2])
+@pytest.mark.parametrize('shape', SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32), (130, 32, 32, 32, 32), (3, 8, 8, 32, 64)])
 def test_conv3x3_wgrad(shape, use_tc):
     """dW of the convolution = autograd of conv2d (what loss.backward() computes in train.py:401)."""
     b, h, wd, cin, cout = shape

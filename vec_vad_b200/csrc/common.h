@@ -82,4 +82,10 @@ int vv_launch_wgrad_simt(const VvWGrad &p, cudaStream_t st);
 int vv_launch_igemm_tc(const VvIGemm &p, cudaStream_t st);
 int vv_launch_wgrad_tc(const VvWGrad &p, cudaStream_t st);
 bool vv_igemm_tc_supported(const VvIGemm &p);
+// persistent tap-reuse variant (igemm_tc2.cu); falls back to vv_launch_igemm_tc when the driver refuses its tensor map
+bool vv_igemm_tc2_supported(const VvIGemm &p);
+int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st);
 bool vv_wgrad_tc_supported(const VvWGrad &p);
+// tap-reuse variant (wgrad_tc2.cu)
+bool vv_wgrad_tc2_supported(const VvWGrad &p);
+int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st);

@@ -13,85 +13,11 @@
 //                     shuffled for the transposed conv), BatchNorm batch statistics by a shuffle butterfly.
 // fp32 activations are fed to the tensor core as-is (kind::tf32 reads the top 19 bits); accumulation, bias,
 // statistics and everything downstream stay fp32.
-#include <cuda.h>
-
-#include "common.h"
+#include "tc_common.cuh"
 
 namespace {
 
-constexpr int BM = 128;            // pixels per CTA (TMEM lanes)
-constexpr int KS = 32;             // channels per stage (128-byte rows)
 constexpr int A_STAGE = BM * KS * 4;
-
-// ------------------------------------------------------------------------------------------------ PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra.uni WAIT_DONE;\n\t"
-        "bra.uni WAIT_LOOP;\n\t"
-        "WAIT_DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t *bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, float *v) {
-    uint32_t *r = reinterpret_cast<uint32_t *>(v);
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
-        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor: rows of 128 bytes, 8-row groups 1024 bytes apart.
-__device__ __forceinline__ uint64_t smem_desc_k_sw128(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)2 << 61);
-}
-// instruction descriptor: D fp32, A/B tf32, both K-major, M = 128, N = n
-__device__ __forceinline__ uint32_t idesc_tf32(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-}
 
 struct TcParams {
     int B, H, W, G;
@@ -258,52 +184,7 @@ __global__ void __launch_bounds__(128) k_igemm_tc(const __grid_constant__ CUtens
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *ptr = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)ptr;
-    }
-    return fn;
-}
-
-bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
-
-// pixel box of a 128-pixel tile
-bool tile_geometry(int H, int W, int &bw, int &bh, int &bn) {
-    if (W >= 32) {
-        if (W % 32) return false;
-        bw = 32;
-    } else {
-        if (!pow2(W) || W < 2) return false;
-        bw = W;
-    }
-    int rest = BM / bw;
-    if (H >= rest) {
-        if (H % rest) return false;
-        bh = rest; bn = 1;
-    } else {
-        if (!pow2(H)) return false;
-        bh = H; bn = rest / H;
-    }
-    return bw * bh * bn == BM;
-}
-
-int tmap_dtype() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("VECVAD_TMA_TF32_ROUND");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v;
-}
+bool tile_geometry(int H, int W, int &bw, int &bh, int &bn) { return tile_geometry_n(H, W, BM, bw, bh, bn); }
 
 int pick_bn(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
 
@@ -348,7 +229,7 @@ int vv_launch_igemm_tc(const VvIGemm &p, cudaStream_t st) {
     tp.N = p.N; tp.O = p.O; tp.o_gs = p.o_gs; tp.ldo = p.ldo; tp.o_coff = p.o_coff; tp.o_d2s = p.o_d2s;
     tp.bias = p.bias; tp.bias_gs = p.bias_gs; tp.stats = p.stats; tp.stats_gs = p.stats_gs;
 
-    const CUtensorMapDataType dt = tmap_dtype() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType dt = tmap_dtype();
     alignas(64) CUtensorMap tmA, tmB;
     {
         const int sc = p.a_s2d ? 2 : 1;
@@ -392,12 +273,6 @@ namespace {
 constexpr int WPB = 64;                 // pixels per slab / pipeline stage
 constexpr int W_SLAB = WPB * KS * 4;    // 8 KiB
 
-__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2, int c3, int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
 // MN-major tf32 operands exist in one shared-memory layout only: 128-byte swizzle with 32-byte atomicity
 // (UMMA layout type 1 = SWIZZLE_128B_BASE32B; TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B).  32 channels (128 B) are contiguous,
 // the swizzle pattern repeats every 4 pixel rows (512 B = SBO), 32-channel slabs are `lbo` bytes apart.
@@ -496,21 +371,25 @@ __global__ void __launch_bounds__(128) k_wgrad_tc(const __grid_constant__ CUtens
                     tma_load_5d(sg + j * W_SLAB, &tmG, &full[s], c, xx, yy, img0, g);
                 }
             }
-        } else if (warp == 1 && lane == 0) {
-            // ---------------- MMA issuer: D[128 x NT] += A_slabs^T[128 x 8 px] * Gd_slabs[8 px x NT], 8 times per stage
+        } else if (warp == 1) {
+            // ---------------- MMA issuer: D[128 x NT] += A_slabs^T[128 x 8 px] * Gd_slabs[8 px x NT], 8 times per stage.
+            // Warp-uniform loop, one elected lane issues (descriptors stay in uniform registers).
             const uint32_t idesc = idesc_tf32_mn(NT);
+            const uint32_t smem_base = smem_u32(smem);
             for (int it = 0; it < nsteps; it++) {
                 const int s = it % STAGES, round = it / STAGES;
                 mbar_wait(&full[s], round & 1);
                 tc_fence_after();
-                const uint32_t sa = smem_u32(smem + s * SM::STAGE), sg = sa + 4 * W_SLAB;
+                const uint32_t sa = smem_base + s * SM::STAGE, sg = sa + 4 * W_SLAB;
                 const uint64_t da = smem_desc_mn_sw128(sa, W_SLAB), dg = smem_desc_mn_sw128(sg, W_SLAB);
 #pragma unroll
                 for (int k = 0; k < WPB / 8; k++)     // 8 pixels = 1024 bytes per MMA: +64 in the (>>4) start-address field
-                    tc_mma_tf32(tmem, da + 64 * k, dg + 64 * k, idesc, (it | k) ? 1u : 0u);
-                tc_commit(&empty[s]);
+                    if (elect_one()) tc_mma_tf32(tmem, da + 64 * k, dg + 64 * k, idesc, (it | k) ? 1u : 0u);
+                if (elect_one()) tc_commit(&empty[s]);
+                __syncwarp();
             }
-            tc_commit(accum);
+            if (elect_one()) tc_commit(accum);
+            __syncwarp();
         }
         __syncwarp();
         // ---------------- epilogue: lane = input channel within the slab (contiguous in dW), column = output channel
@@ -533,24 +412,7 @@ __global__ void __launch_bounds__(128) k_wgrad_tc(const __grid_constant__ CUtens
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(NT) : "memory");
 }
 
-bool tile_geometry64(int H, int W, int &bw, int &bh, int &bn) {
-    if (W >= 32) {
-        if (W % 32) return false;
-        bw = 32;
-    } else {
-        if (!pow2(W) || W < 2) return false;
-        bw = W;
-    }
-    int rest = WPB / bw;
-    if (H >= rest) {
-        if (H % rest) return false;
-        bh = rest; bn = 1;
-    } else {
-        if (!pow2(H)) return false;
-        bh = H; bn = rest / H;
-    }
-    return bw * bh * bn == WPB;
-}
+bool tile_geometry64(int H, int W, int &bw, int &bh, int &bn) { return tile_geometry_n(H, W, WPB, bw, bh, bn); }
 
 template <int NT, int STAGES>
 int launch_wg(const CUtensorMap &tmA, const CUtensorMap &tmG, const WgParams &wp, dim3 grid, cudaStream_t st) {
@@ -590,7 +452,7 @@ int vv_launch_wgrad_tc(const VvWGrad &p, cudaStream_t st) {
     wp.N = p.N; wp.Kt = p.Kt; wp.cq = p.g_s2d ? p.N / 4 : 0;
     wp.dW = p.dW; wp.dw_gs = p.dw_gs;
 
-    const CUtensorMapDataType dt = tmap_dtype() ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+    const CUtensorMapDataType dt = tmap_dtype();
     alignas(64) CUtensorMap tmA, tmG;
     {
         cuuint64_t dims[5] = {(cuuint64_t)p.Kt, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B, (cuuint64_t)p.G};

@@ -137,12 +137,14 @@ double igemm_flops(int B, int H, int W, int N, int K, int taps, int G) { return 
 int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
     const bool tc = n->cfg.use_tensor_cores && vv_igemm_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
-    return tc ? vv_launch_igemm_tc(p, st) : vv_launch_igemm_simt(p, st);
+    if (tc) return vv_igemm_tc2_supported(p) ? vv_launch_igemm_tc2(p, st) : vv_launch_igemm_tc(p, st);
+    return vv_launch_igemm_simt(p, st);
 }
 int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
     const bool tc = n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
-    return tc ? vv_launch_wgrad_tc(p, st) : vv_launch_wgrad_simt(p, st);
+    if (tc) return vv_wgrad_tc2_supported(p) ? vv_launch_wgrad_tc2(p, st) : vv_launch_wgrad_tc(p, st);
+    return vv_launch_wgrad_simt(p, st);
 }
 
 struct Flow {   // buffer wiring of one forward for batch B
@@ -534,6 +536,10 @@ extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w
     p.O = out; p.ldo = cout; p.bias = bias; p.stats = stats; p.G = 1;
     if (use_tc) {
         VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_forward: shape not supported by the tcgen05 path");
+        if (use_tc == 2) {       // persistent tap-reuse tiles
+            VV_REQUIRE(vv_igemm_tc2_supported(p), "conv3x3_forward: shape not supported by the persistent tcgen05 path");
+            return vv_launch_igemm_tc2(p, st);
+        }
         return vv_launch_igemm_tc(p, st);
     }
     return vv_launch_igemm_simt(p, st);
@@ -553,7 +559,8 @@ extern "C" int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *gra
     int r;
     if (use_tc) {
         VV_REQUIRE(vv_wgrad_tc_supported(w), "conv3x3_wgrad: shape not supported by the tcgen05 path");
-        r = vv_launch_wgrad_tc(w, st);
+        if (use_tc == 2) VV_REQUIRE(vv_wgrad_tc2_supported(w), "conv3x3_wgrad: shape not supported by the tap-reuse tcgen05 path");
+        r = use_tc == 2 ? vv_launch_wgrad_tc2(w, st) : vv_launch_wgrad_tc(w, st);
     } else {
         r = vv_launch_wgrad_simt(w, st);
     }
