@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) k_igemm_tc2(const __grid_consta
                     const int s = it % p.stages, round = it / p.stages;
                     mbar_wait(&full[s], round & 1);
                     tc_fence_after();
-                    const uint32_t sa = smem_base + s * stage_bytes;
+                    const uint32_t sa = smem_base + ((p.dbg & 8) ? 0 : s * stage_bytes);
 #pragma unroll
                     for (int dyi = 0; dyi < 3; dyi++) {
                         if (dyi < p.ndy) {
@@ -319,6 +319,11 @@ int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st) {
     const int stage_bytes = tp.a_bytes + (tp.stationary ? 0 : tp.ndy * b_tap);
     int stages = (SMEM_MAX - fixed - (tp.stationary ? b_all : 0)) / stage_bytes;
     if (stages > 8) stages = 8;
+    {
+        static int cap = -1;
+        if (cap < 0) { const char *e = getenv("VECVAD_TC2_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap >= 2 && stages > cap) stages = cap;
+    }
     VV_REQUIRE(stages >= 2, "igemm_tc2: tile does not fit in shared memory");
     tp.stages = stages;
     const int smem = fixed + (tp.stationary ? b_all : 0) + stages * stage_bytes;
@@ -351,6 +356,11 @@ int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st) {
     }
     const int n_tiles = p.N / bn_tile;
     int gx = 148 / (n_tiles * p.G);
+    {
+        static int div = -1;
+        if (div < 0) { const char *e = getenv("VECVAD_TC2_GRID_DIV"); div = e ? atoi(e) : 1; }
+        if (div > 1) gx /= div;
+    }
     if (gx < 1) gx = 1;
     if (gx > tp.m_tiles) gx = tp.m_tiles;
     dim3 grid(gx, n_tiles, p.G);
