@@ -276,12 +276,29 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     const vecvad_net_config &c = n->cfg;
     Flow f;
     wire(n, B, f);
-    // 1. weights into GEMM layouts (they change every optimiser step)
-    for (int u = 0; u < NU; u++) {
-        int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
-                               n->uCp[u], n->Wf[u], 9LL * n->uN[u] * n->uCp[u], (training && u > 0) ? n->Wd[u] : nullptr,
-                               9LL * n->uN[u] * n->uCp[u], n->vec[u], 3LL * n->uN[u], G, st);
+    // 1. weights into GEMM layouts (they change every optimiser step): one launch for all conv units when they tile by 32
+    bool batched = true;
+    for (int u = 0; u < NU; u++) batched = batched && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
+    if (batched) {
+        VvPrepAll all;
+        memset(&all, 0, sizeof(all));
+        all.n = NU;
+        for (int u = 0; u < NU; u++) {
+            VvPrepUnit &pu = all.u[u];
+            pu.w_off = c.conv_w[u]; pu.b_off = c.conv_b[u]; pu.g_off = c.bn_w[u]; pu.beta_off = c.bn_b[u];
+            pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
+            pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
+            pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
+        }
+        int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, st);
         if (r) return r;
+    } else {
+        for (int u = 0; u < NU; u++) {
+            int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
+                                   n->uCp[u], n->Wf[u], 9LL * n->uN[u] * n->uCp[u], (training && u > 0) ? n->Wd[u] : nullptr,
+                                   9LL * n->uN[u] * n->uCp[u], n->vec[u], 3LL * n->uN[u], G, st);
+            if (r) return r;
+        }
     }
     for (int k = 0; k < NT; k++) {
         int r = vv_prep_ct_w(n->params, n->slot, c.slot_param_stride, c.up_w[k], c.up_b[k], n->tCi[k], n->tCo[k], n->tWf[k],
@@ -408,6 +425,8 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         if ((r = vv_outconv_bwd(q, G, st))) return r;
     }
     const VvTaps t3f = taps3x3(+1), t3b = taps3x3(-1), t2f = taps2x2(+1), t2b = taps2x2(-1);
+    bool batched_scatter = true;       // conv weight gradients go back to PyTorch's layout in one launch at the end
+    for (int u = 0; u < NU; u++) batched_scatter = batched_scatter && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
 
     // gradient of the post-ReLU output of unit u lives in dyv; produces d(input of unit u) into `din` (if u > 0)
     auto unit_bwd = [&](int u, const View &dyv, float *dz_buf, const View *din) -> int {
@@ -436,7 +455,8 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
         w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
         if ((rr = run_wgrad(n, w, st, n->uC[u]))) return rr;
-        if ((rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, st)))
+        if (!batched_scatter &&
+            (rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, st)))
             return rr;
         // (pre-BN conv bias: its gradient is exactly zero in training mode -- left at the memset value; the reference
         //  produces round-off noise there)
@@ -514,6 +534,17 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             if ((r = vv_maxpool_bwd(ysk.p, ysk.gs, ysk.ld, ysk.coff, dpool.p, dpool.gs, dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B, Hs, Hs, Cs, st)))
                 return r;
         }
+    }
+    if (batched_scatter) {
+        VvPrepAll all;
+        memset(&all, 0, sizeof(all));
+        all.n = NU;
+        for (int u = 0; u < NU; u++) {
+            VvPrepUnit &pu = all.u[u];
+            pu.w_off = c.conv_w[u]; pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
+            pu.dWf = n->dWf[u]; pu.wf_gs = 9LL * n->uN[u] * n->uCp[u];
+        }
+        if ((r = vv_scatter_conv_wgrad_all(n->grads, n->slot, c.slot_param_stride, all, G, st))) return r;
     }
     return 0;
 }

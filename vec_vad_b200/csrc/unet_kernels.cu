@@ -71,6 +71,101 @@ __global__ void k_prep_conv_w(const float *__restrict__ params, VvIntG slot, lon
     }
 }
 
+// Same re-layout, tiled through shared memory: block = 32 output channels x 32 input channels x 9 taps, so the reads
+// (288 contiguous floats per output channel) and both writes (128-byte runs along c for Wf, along n for Wd) are coalesced.
+__global__ void __launch_bounds__(256) k_prep_conv_w_tiled(const float *__restrict__ params, VvIntG slot, long long slot_stride,
+                                                           long long w_off, long long b_off, long long g_off, long long beta_off, int N,
+                                                           int C, int Cp, float *__restrict__ Wf, long long wf_gs, float *__restrict__ Wd,
+                                                           long long wd_gs, float *__restrict__ vec, long long vec_gs) {
+    __shared__ float tile[32][32 * 9 + 1];
+    const int g = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const float *P = params + slot.v[g] * slot_stride;
+    const int cw = min(32, C - c0);                       // real input channels in this tile (<= 0: all padding)
+    for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+        const int n = i / 288, r = i - n * 288;           // r = c_local * 9 + t
+        tile[n][r] = (r < cw * 9) ? P[w_off + ((long long)(n0 + n) * C + c0) * 9 + r] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+        const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
+        Wf[g * wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c] = tile[n][c * 9 + t];
+    }
+    if (Wd) {
+        for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+            const int n = i & 31, c = (i >> 5) & 31, t = i >> 10;
+            if (c < cw) Wd[g * wd_gs + ((long long)t * C + c0 + c) * N + n0 + n] = tile[n][c * 9 + t];
+        }
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && vec) {
+        for (int n = threadIdx.x; n < N; n += 256) {
+            vec[g * vec_gs + n] = P[b_off + n];
+            vec[g * vec_gs + N + n] = P[g_off + n];
+            vec[g * vec_gs + 2 * N + n] = P[beta_off + n];
+        }
+    }
+}
+
+// one launch for every conv unit of the net: block -> (unit, 32 x 32 channel tile)
+__device__ __forceinline__ int find_unit(const VvPrepAll &all, int blk) {
+    int u = 0;
+    while (u + 1 < all.n && blk >= all.u[u + 1].blk0) u++;
+    return u;
+}
+__global__ void __launch_bounds__(256) k_prep_conv_w_all(const float *__restrict__ params, VvIntG slot, long long slot_stride,
+                                                         const VvPrepAll all) {
+    __shared__ float tile[32][32 * 9 + 1];
+    const int ui = find_unit(all, blockIdx.x);
+    const VvPrepUnit &U = all.u[ui];
+    const int lb = blockIdx.x - U.blk0, nbx = U.N / 32;
+    const int g = blockIdx.z, n0 = (lb % nbx) * 32, c0 = (lb / nbx) * 32;
+    const float *P = params + slot.v[g] * slot_stride;
+    const int N = U.N, C = U.C, Cp = U.Cp;
+    const int cw = min(32, C - c0);
+    for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+        const int n = i / 288, r = i - n * 288;
+        tile[n][r] = (r < cw * 9) ? P[U.w_off + ((long long)(n0 + n) * C + c0) * 9 + r] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+        const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
+        U.Wf[g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c] = tile[n][c * 9 + t];
+    }
+    if (U.Wd) {
+        for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+            const int n = i & 31, c = (i >> 5) & 31, t = i >> 10;
+            if (c < cw) U.Wd[g * U.wd_gs + ((long long)t * C + c0 + c) * N + n0 + n] = tile[n][c * 9 + t];
+        }
+    }
+    if (lb == 0) {
+        for (int n = threadIdx.x; n < N; n += 256) {
+            U.vec[g * U.vec_gs + n] = P[U.b_off + n];
+            U.vec[g * U.vec_gs + N + n] = P[U.g_off + n];
+            U.vec[g * U.vec_gs + 2 * N + n] = P[U.beta_off + n];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_scatter_conv_wgrad_all(float *__restrict__ grads, VvIntG slot, long long slot_stride,
+                                                                const VvPrepAll all) {
+    __shared__ float tile[32][32 * 9 + 1];
+    const int ui = find_unit(all, blockIdx.x);
+    const VvPrepUnit &U = all.u[ui];
+    const int lb = blockIdx.x - U.blk0, nbx = U.N / 32;
+    const int g = blockIdx.z, n0 = (lb % nbx) * 32, c0 = (lb / nbx) * 32;
+    const int N = U.N, C = U.C, Cp = U.Cp;
+    const int cw = min(32, C - c0);
+    if (cw <= 0) return;
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+        const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
+        tile[n][c * 9 + t] = U.dWf[g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c];
+    }
+    __syncthreads();
+    float *Gp = grads + slot.v[g] * slot_stride + U.w_off;
+    for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+        const int n = i / 288, r = i - n * 288;
+        if (r < cw * 9) Gp[((long long)(n0 + n) * C + c0) * 9 + r] = tile[n][r];
+    }
+}
+
 // ConvTranspose2d(k3,s2,p1,op1) weight [Ci][Co][3][3] -> 2x2-tap "big" matrices over the 4 output phases:
 //   out[2y+py, 2x+px, co] = sum_{sy,sx in {0,1}} in[y+sy, x+sx, :] . Wt[:, co, ky, kx],  ky = py+1-2sy, kx = px+1-2sx (if in 0..2)
 //   Wbf[s][(p,co)][ci]  (forward, N = 4Co, Kt = Ci)      Wbd[s][ci][(p,co)]  (input gradient, N = Ci, Kt = 4Co)
@@ -403,63 +498,84 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
 }
 
 // backward of the 1x1 conv: dU[m][c] = sum_j dout[m][j] w[j][c];  dW[j][c] += sum_m dout[m][j] U[m][c];  db[j] += sum_m dout[m][j]
-// warp = 32 channels of one pixel at a time (lane = channel), grid-stride over pixels; F is processed in slabs of 32.
+// thread = (pixel slot, 4 channels): float4 loads of U / stores of dU, 256/(F/4) pixels per block iteration, two iterations in
+// flight; the weight / bias gradients are reduced in shared memory and flushed with one atomic per element per block.
 __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
+    extern __shared__ float sm_ob[];            // dW partial [3][F], db partial [4]
     const int g = blockIdx.y;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int F = p.F;
+    const int F = p.F, FQ = F >> 2;
+    const int q = threadIdx.x % FQ, ps = threadIdx.x / FQ, npix = 256 / FQ;
     const int oc = p.out_channels.v[g];
     const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
     float *G = p.grads + p.slot.v[g] * p.slot_param_stride;
     const float *U = p.U + g * p.u_gs;
     float *dU = p.dU + g * p.du_gs;
     const int SS = p.S * p.S;
-    // external NCHW gradient or the internal staged [m][4]
     const bool flow = p.target_is_flow.v[g] != 0;
-    const float *ext = flow ? p.grad_of_out : p.grad_raw_out;
+    const float *ext = flow ? p.grad_of_out : p.grad_raw_out;      // external NCHW gradient, else the staged [m][4]
     const int ext_ctot = flow ? p.of_out_channels : p.raw_out_channels;
     const int ext_c0 = p.out_slot.v[g] * (flow ? 2 : 3);
-    __shared__ float red[8][3][32];
-    __shared__ float redb[8][4];
-    for (int f0 = 0; f0 < F; f0 += 32) {
-        float w0 = oc > 0 ? P[p.w_off + 0 * F + f0 + lane] : 0.f;
-        float w1 = oc > 1 ? P[p.w_off + 1 * F + f0 + lane] : 0.f;
-        float w2 = oc > 2 ? P[p.w_off + 2 * F + f0 + lane] : 0.f;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, db = 0.f;
-        for (int m = blockIdx.x * 8 + warp; m < p.M; m += gridDim.x * 8) {
-            float d0, d1, d2;
-            if (ext) {
-                int b = m / SS, pix = m - b * SS;
-                const float *e = ext + ((long long)b * ext_ctot + ext_c0) * SS + pix;
-                d0 = e[0];
-                d1 = oc > 1 ? e[SS] : 0.f;
-                d2 = oc > 2 ? e[2 * SS] : 0.f;
-            } else {
-                float4 d = *reinterpret_cast<const float4 *>(p.dout + ((long long)g * p.M + m) * 4);
-                d0 = d.x; d1 = d.y; d2 = d.z;
-            }
-            float u = U[(long long)m * F + f0 + lane];
-            a0 = fmaf(d0, u, a0); a1 = fmaf(d1, u, a1); a2 = fmaf(d2, u, a2);
-            dU[(long long)m * F + f0 + lane] = d0 * w0 + d1 * w1 + d2 * w2;
-            if (f0 == 0) db += (lane == 0) ? d0 : (lane == 1) ? d1 : (lane == 2) ? d2 : 0.f;
+    for (int i = threadIdx.x; i < 3 * F + 4; i += 256) sm_ob[i] = 0.f;
+    __syncthreads();
+    float4 w[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++)
+        w[j] = j < oc ? *reinterpret_cast<const float4 *>(P + p.w_off + j * F + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float db[3] = {0.f, 0.f, 0.f};
+    auto load_d = [&](int m, float *d) {
+        if (ext) {
+            int b = m / SS, pix = m - b * SS;
+            const float *e = ext + ((long long)b * ext_ctot + ext_c0) * SS + pix;
+            d[0] = e[0];
+            d[1] = oc > 1 ? e[SS] : 0.f;
+            d[2] = oc > 2 ? e[2 * SS] : 0.f;
+        } else {
+            float4 v = *reinterpret_cast<const float4 *>(p.dout + ((long long)g * p.M + m) * 4);
+            d[0] = v.x; d[1] = v.y; d[2] = v.z;
         }
-        red[warp][0][lane] = a0; red[warp][1][lane] = a1; red[warp][2][lane] = a2;
-        if (lane < 4) redb[warp][lane] = db;
-        __syncthreads();
-        if (threadIdx.x < 96) {
-            int j = threadIdx.x >> 5;
-            float s = 0.f;
-            for (int wv = 0; wv < 8; wv++) s += red[wv][j][lane];
-            if (j < oc) atomicAdd(G + p.w_off + j * F + f0 + lane, s);
+    };
+    auto body = [&](int m, const float *d, const float4 &u) {
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            a[j].x = fmaf(d[j], u.x, a[j].x); a[j].y = fmaf(d[j], u.y, a[j].y);
+            a[j].z = fmaf(d[j], u.z, a[j].z); a[j].w = fmaf(d[j], u.w, a[j].w);
+            db[j] += d[j];
         }
-        if (f0 == 0 && threadIdx.x >= 96 && threadIdx.x < 96 + 3) {
-            int j = threadIdx.x - 96;
-            float s = 0.f;
-            for (int wv = 0; wv < 8; wv++) s += redb[wv][j];
-            if (j < oc) atomicAdd(G + p.b_off + j, s);
-        }
-        __syncthreads();
+        float4 o;
+        o.x = d[0] * w[0].x + d[1] * w[1].x + d[2] * w[2].x; o.y = d[0] * w[0].y + d[1] * w[1].y + d[2] * w[2].y;
+        o.z = d[0] * w[0].z + d[1] * w[1].z + d[2] * w[2].z; o.w = d[0] * w[0].w + d[1] * w[1].w + d[2] * w[2].w;
+        *reinterpret_cast<float4 *>(dU + (long long)m * F + 4 * q) = o;
+    };
+    const int stride = gridDim.x * npix;
+    int m = blockIdx.x * npix + ps;
+    for (; m + stride < p.M; m += 2 * stride) {          // two pixels in flight per thread
+        float d0[3], d1[3];
+        load_d(m, d0);
+        load_d(m + stride, d1);
+        const float4 u0 = *reinterpret_cast<const float4 *>(U + (long long)m * F + 4 * q);
+        const float4 u1 = *reinterpret_cast<const float4 *>(U + (long long)(m + stride) * F + 4 * q);
+        body(m, d0, u0);
+        body(m + stride, d1, u1);
     }
+    if (m < p.M) {
+        float d0[3];
+        load_d(m, d0);
+        const float4 u0 = *reinterpret_cast<const float4 *>(U + (long long)m * F + 4 * q);
+        body(m, d0, u0);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        atomicAdd(&sm_ob[j * F + 4 * q + 0], a[j].x); atomicAdd(&sm_ob[j * F + 4 * q + 1], a[j].y);
+        atomicAdd(&sm_ob[j * F + 4 * q + 2], a[j].z); atomicAdd(&sm_ob[j * F + 4 * q + 3], a[j].w);
+        if (q == 0) atomicAdd(&sm_ob[3 * F + j], db[j]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * F; i += 256)
+        if (i / F < oc) atomicAdd(G + p.w_off + i, sm_ob[i]);
+    if (threadIdx.x < oc) atomicAdd(G + p.b_off + threadIdx.x, sm_ob[3 * F + threadIdx.x]);
 }
 
 // ---- gradient re-layout back to PyTorch's parameter layouts
@@ -471,6 +587,26 @@ __global__ void k_scatter_conv_wgrad(const float *__restrict__ dWf, long long gs
     if (i >= total) return;
     int t = i % 9, c = (i / 9) % C, n = i / (9 * C);
     grads[slot.v[g] * slot_stride + w_off + i] = dWf[g * gs + ((long long)t * N + n) * Cp + c];
+}
+
+// tiled variant: block = 32 output channels x 32 input channels x 9 taps through shared memory, coalesced on both sides
+__global__ void __launch_bounds__(256) k_scatter_conv_wgrad_tiled(const float *__restrict__ dWf, long long gs, int N, int C, int Cp,
+                                                                  float *__restrict__ grads, VvIntG slot, long long slot_stride,
+                                                                  long long w_off) {
+    __shared__ float tile[32][32 * 9 + 1];
+    const int g = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int cw = min(32, C - c0);
+    if (cw <= 0) return;
+    for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
+        const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
+        tile[n][c * 9 + t] = dWf[g * gs + ((long long)t * N + n0 + n) * Cp + c0 + c];
+    }
+    __syncthreads();
+    float *G = grads + slot.v[g] * slot_stride + w_off;
+    for (int i = threadIdx.x; i < 32 * 288; i += 256) {
+        const int n = i / 288, r = i - n * 288;
+        if (r < cw * 9) G[((long long)(n0 + n) * C + c0) * 9 + r] = tile[n][r];
+    }
 }
 
 __global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, int Ci, int Co, float *__restrict__ grads,
@@ -579,8 +715,33 @@ int vv_prep_input(const float *x, float *X0, int G, int B, int T, int S, int cin
 int vv_prep_conv_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, long long g_off,
                    long long beta_off, int N, int C, int Cp, float *Wf, long long wf_gs, float *Wd, long long wd_gs, float *vec,
                    long long vec_gs, int G, cudaStream_t st) {
-    k_prep_conv_w<<<dim3(vv_cdiv(9LL * N * Cp, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C,
-                                                                     Cp, Wf, wf_gs, Wd, wd_gs, vec, vec_gs);
+    if (N % 32 == 0 && Cp % 32 == 0)
+        k_prep_conv_w_tiled<<<dim3(N / 32, Cp / 32, G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C, Cp, Wf,
+                                                                    wf_gs, Wd, wd_gs, vec, vec_gs);
+    else
+        k_prep_conv_w<<<dim3(vv_cdiv(9LL * N * Cp, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C,
+                                                                         Cp, Wf, wf_gs, Wd, wd_gs, vec, vec_gs);
+    VV_CKL();
+    return 0;
+}
+
+static void layout_blocks(VvPrepAll &all) {
+    int blk = 0;
+    for (int i = 0; i < all.n; i++) {
+        all.u[i].blk0 = blk;
+        blk += (all.u[i].N / 32) * (all.u[i].Cp / 32);
+    }
+    all.total_blocks = blk;
+}
+int vv_prep_conv_w_all(const float *params, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st) {
+    layout_blocks(all);
+    k_prep_conv_w_all<<<dim3(all.total_blocks, 1, G), 256, 0, st>>>(params, slot, slot_stride, all);
+    VV_CKL();
+    return 0;
+}
+int vv_scatter_conv_wgrad_all(float *grads, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st) {
+    layout_blocks(all);
+    k_scatter_conv_wgrad_all<<<dim3(all.total_blocks, 1, G), 256, 0, st>>>(grads, slot, slot_stride, all);
     VV_CKL();
     return 0;
 }
@@ -657,17 +818,22 @@ int vv_outconv_fwd(const VvOutFwd &p, int G, cudaStream_t st) {
 }
 
 int vv_outconv_bwd(const VvOutBwd &p, int G, cudaStream_t st) {
-    VV_REQUIRE(p.F % 32 == 0, "outconv backward needs features_root %% 32 == 0");
-    int gx = vv_cdiv(p.M, 8 * 32);
-    if (gx > 148 * 4) gx = 148 * 4;
-    k_outconv_bwd<<<dim3(gx, G), 256, 0, st>>>(p);
+    VV_REQUIRE(p.F % 16 == 0 && p.F <= 1024 && 256 % (p.F / 4) == 0, "outconv backward: unsupported features_root %d", p.F);
+    const int npix = 256 / (p.F / 4);
+    int gx = vv_cdiv(p.M, npix * 8);
+    if (gx > 148 * 8) gx = 148 * 8;
+    if (gx < 1) gx = 1;
+    k_outconv_bwd<<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
     VV_CKL();
     return 0;
 }
 
 int vv_scatter_conv_wgrad(const float *dWf, long long gs, int N, int C, int Cp, float *grads, const VvIntG &slot, long long slot_stride,
                           long long w_off, int G, cudaStream_t st) {
-    k_scatter_conv_wgrad<<<dim3(vv_cdiv(9LL * N * C, 256), G), 256, 0, st>>>(dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
+    if (N % 32 == 0 && Cp % 32 == 0)
+        k_scatter_conv_wgrad_tiled<<<dim3(N / 32, Cp / 32, G), 256, 0, st>>>(dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
+    else
+        k_scatter_conv_wgrad<<<dim3(vv_cdiv(9LL * N * C, 256), G), 256, 0, st>>>(dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
     VV_CKL();
     return 0;
 }

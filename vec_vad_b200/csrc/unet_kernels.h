@@ -56,6 +56,21 @@ struct VvOutBwd {
     const float *grad_of_out;  int of_out_channels;
 };
 
+// all conv units of a net in one launch (weight re-layout forward, gradient re-layout backward)
+struct VvPrepUnit {
+    long long w_off, b_off, g_off, beta_off;
+    int N, C, Cp;
+    float *Wf, *Wd, *vec;          // Wd may be NULL
+    const float *dWf;              // scatter direction
+    long long wf_gs, wd_gs, vec_gs;
+    int blk0;                      // first block of this unit
+};
+struct VvPrepAll {
+    VvPrepUnit u[VECVAD_N_UNITS];
+    int n, total_blocks;
+};
+int vv_prep_conv_w_all(const float *params, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st);
+int vv_scatter_conv_wgrad_all(float *grads, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st);
 int vv_prep_input(const float *x, float *X0, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st);
 int vv_prep_conv_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, long long g_off,
                    long long beta_off, int N, int C, int Cp, float *Wf, long long wf_gs, float *Wd, long long wd_gs, float *vec,
