@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 1
+#define VECVAD_ABI_VERSION 2
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -56,11 +56,17 @@ int vecvad_profile_end(double *ms, double *flops, int64_t *launches, int n_class
 int vecvad_correlation_out_shape(int in_h, int in_w, int pad_size, int kernel_size, int max_displacement,
                                  int stride1, int stride2, int *out_c, int *out_h, int *out_w);
 
+/* scratch bytes the fast (FlowNetC-parameter, TMA-fed) forward kernel wants: two column-parity-split copies of the inputs.
+ * 0 when the parameters are served by the general kernel, which needs none. */
+int vecvad_correlation_workspace_bytes(int batch, int channels, int in_h, int in_w, int pad_size, int kernel_size,
+                                       int max_displacement, int stride1, int stride2, int64_t *bytes);
+
 /* replaces Correlation_forward_cuda (correlation_cuda.c:11-93; kernels correlation_cuda_kernel.cu:10-106).
- * out[n,tc,y,x] = 1/(k*k*C) * sum_{j,i,c} in1[n,c,y1+j,x1+i] * in2[n,c,y1+tj*s2+j,x1+ti*s2+i] (zero padded). */
+ * out[n,tc,y,x] = 1/(k*k*C) * sum_{j,i,c} in1[n,c,y1+j,x1+i] * in2[n,c,y1+tj*s2+j,x1+ti*s2+i] (zero padded).
+ * workspace (16-byte aligned, >= vecvad_correlation_workspace_bytes) may be NULL: the general kernel is used then. */
 int vecvad_correlation_forward(const float *in1, const float *in2, float *out, int batch, int channels, int in_h, int in_w,
                                int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
-                               int corr_type_multiply, vecvad_stream stream);
+                               int corr_type_multiply, void *workspace, int64_t workspace_bytes, vecvad_stream stream);
 
 /* replaces Correlation_backward_cuda (correlation_cuda.c:95-180; kernels :108-290). grad_in1/2 are fully written. */
 int vecvad_correlation_backward(const float *in1, const float *in2, const float *grad_out, float *grad_in1, float *grad_in2,

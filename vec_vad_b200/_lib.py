@@ -13,12 +13,12 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     'vecvad_abi_version', 'vecvad_last_error', 'vecvad_launch_count', 'vecvad_profile_begin', 'vecvad_profile_end',
-    'vecvad_correlation_out_shape', 'vecvad_correlation_forward', 'vecvad_correlation_backward',
+    'vecvad_correlation_out_shape', 'vecvad_correlation_workspace_bytes', 'vecvad_correlation_forward', 'vecvad_correlation_backward',
     'vecvad_resample2d_forward', 'vecvad_resample2d_backward',
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
     'vecvad_net_create', 'vecvad_net_destroy', 'vecvad_net_workspace_bytes', 'vecvad_net_bind',
@@ -61,7 +61,8 @@ def lib():
     L.vecvad_launch_count.restype = C.c_uint64
     L.vecvad_profile_end.argtypes = [p, p, p, i]
     L.vecvad_correlation_out_shape.argtypes = [i] * 7 + [ip, ip, ip]
-    L.vecvad_correlation_forward.argtypes = [p, p, p] + [i] * 10 + [p]
+    L.vecvad_correlation_workspace_bytes.argtypes = [i] * 9 + [C.POINTER(i64)]
+    L.vecvad_correlation_forward.argtypes = [p, p, p] + [i] * 10 + [p, i64, p]
     L.vecvad_correlation_backward.argtypes = [p, p, p, p, p] + [i] * 10 + [p]
     L.vecvad_resample2d_forward.argtypes = [p, p, p] + [i] * 7 + [p]
     L.vecvad_resample2d_backward.argtypes = [p, p, p, p, p] + [i] * 7 + [p]

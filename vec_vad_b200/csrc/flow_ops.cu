@@ -10,6 +10,10 @@
 // stride-2 displacement grid de-interleaved by column parity so every operand fetch is a 128-bit shared load.
 #include "common.h"
 
+long long vv_corr_tma_workspace(int batch, int channels, int h, int w);
+int vv_launch_corr_tma(const float *in1, const float *in2, float *out, int batch, int channels, int h, int w, int pad, int md, int oc, int oh,
+                       int ow, void *workspace, cudaStream_t st);
+
 namespace {
 
 __device__ __forceinline__ int cdiv_trunc(int a, int b) { return a / b; }   // C semantics (toward zero), as in the reference
@@ -332,17 +336,35 @@ extern "C" int vecvad_correlation_out_shape(int in_h, int in_w, int pad_size, in
     return 0;
 }
 
+static bool corr_fast_params(const CorrGeom &g, int batch, int kernel_size, int stride1, int stride2) {
+    return kernel_size == 1 && stride1 == 1 && stride2 == 2 && g.D == FD && g.OH <= 65535 && batch <= 32767;
+}
+
+extern "C" int vecvad_correlation_workspace_bytes(int batch, int channels, int in_h, int in_w, int pad_size, int kernel_size,
+                                                  int max_displacement, int stride1, int stride2, int64_t *bytes) {
+    VV_REQUIRE(bytes, "correlation_workspace_bytes: null pointer");
+    CorrGeom g;
+    int r = corr_geom(g, batch, channels, in_h, in_w, pad_size, kernel_size, max_displacement, stride1, stride2);
+    if (r) return r;
+    *bytes = (corr_fast_params(g, batch, kernel_size, stride1, stride2) && pad_size == max_displacement)
+                 ? vv_corr_tma_workspace(batch, channels, in_h, in_w) : 0;
+    return 0;
+}
+
 extern "C" int vecvad_correlation_forward(const float *in1, const float *in2, float *out, int batch, int channels, int in_h, int in_w,
                                           int pad_size, int kernel_size, int max_displacement, int stride1, int stride2,
-                                          int corr_type_multiply, vecvad_stream stream) {
+                                          int corr_type_multiply, void *workspace, int64_t workspace_bytes, vecvad_stream stream) {
     (void)corr_type_multiply;   // ignored by the reference kernels as well (always a product)
     VV_REQUIRE(in1 && in2 && out, "correlation_forward: null pointer");
     CorrGeom g;
     int r = corr_geom(g, batch, channels, in_h, in_w, pad_size, kernel_size, max_displacement, stride1, stride2);
     if (r) return r;
     cudaStream_t st = (cudaStream_t)stream;
-    const bool fast = kernel_size == 1 && stride1 == 1 && stride2 == 2 && g.D == FD && g.OH <= 65535 && batch <= 65535;
-    if (fast) {
+    const bool fast = corr_fast_params(g, batch, kernel_size, stride1, stride2);
+    const long long need = fast ? vv_corr_tma_workspace(batch, channels, in_h, in_w) : 0;
+    if (fast && pad_size == max_displacement && workspace && need > 0 && workspace_bytes >= need)
+        return vv_launch_corr_tma(in1, in2, out, batch, channels, in_h, in_w, pad_size, max_displacement, g.OC, g.OH, g.OW, workspace, st);
+    if (fast) {                  // FlowNetC parameters without scratch: cp.async-staged kernel reading the inputs in place
         const size_t smem = 2 * F_STAGE * sizeof(float);
         static bool attr = false;
         if (!attr) {

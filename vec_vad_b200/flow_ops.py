@@ -41,9 +41,13 @@ class CorrelationFunction(Function):
         _lib.check(L.vecvad_correlation_out_shape(h, w, pad_size, kernel_size, max_displacement, stride1, stride2, C.byref(oc),
                                                   C.byref(oh), C.byref(ow)), 'correlation_out_shape')
         out = input1.new_empty((b, oc.value, oh.value, ow.value))
+        nb = C.c_int64()
+        _lib.check(L.vecvad_correlation_workspace_bytes(b, c, h, w, pad_size, kernel_size, max_displacement, stride1, stride2, C.byref(nb)),
+                   'correlation_workspace_bytes')
+        ws = torch.empty(nb.value // 4, dtype=torch.float32, device=input1.device) if nb.value else None   # caller-owned scratch
         _lib.check(L.vecvad_correlation_forward(_lib.ptr(input1), _lib.ptr(input2), _lib.ptr(out), b, c, h, w, pad_size, kernel_size,
-                                                max_displacement, stride1, stride2, corr_multiply, _lib.cur_stream()),
-                   'correlation_forward')
+                                                max_displacement, stride1, stride2, corr_multiply, _lib.ptr(ws), nb.value,
+                                                _lib.cur_stream()), 'correlation_forward')
         return out
 
     @staticmethod
