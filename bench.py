@@ -24,6 +24,10 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
+# DRAM traffic of the contraction kernel classes over ONE train step (batch 128, 5raw1of), from the ncu pass whose raw output is
+# committed as profiles/r01_tc_v3_step_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
+NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': (1.879e9 + 0.591e9, 33), 'wgrad_tcgen05': (1.920e9 + 0.002e9, 17)}
+
 # algorithmic FLOPs of one train step per STC (fwd + dgrad + wgrad of every conv; SURVEY.md section 8a / BASELINE.md section 2)
 FLOPS_PER_STC = {'net4': 5.524e9, 'full': 9.206e9, 'noflow': 4.604e9}
 NET_KW = {
@@ -215,7 +219,10 @@ def run_ours(args):
                 'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'STC/s', 'ms_per_step': ms_e2e,
                         'h2d_bytes_per_step': int(host_raw[0].numel() + 4 * host_flow[0].numel()), 'd2h_bytes_per_step': 8},
                 'roofline': {'bound': 'tensor', 'kernel': dom, 'achieved': dom_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dom_tf / peak,
-                             'traffic': None, 'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / ms_dev,
+                             'traffic': (NCU_DRAM_BYTES_PER_STEP[dom][0] / NCU_DRAM_BYTES_PER_STEP[dom][1]
+                                         if (dom in NCU_DRAM_BYTES_PER_STEP and args.net == 'net4' and B == 128) else None),
+                             'traffic_note': 'mean DRAM bytes per launch of this kernel class (ncu, profiles/r01_tc_v3_step_metrics.csv)',
+                             'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / ms_dev,
                              'peak_tf32': peak / 2 if tf32 else None, 'frac_of_tf32_peak': dom_tf / (peak / 2) if tf32 else None,
                              'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak,
                              'note': 'achieved = algorithmic conv FLOPs of the dominant kernel class / its CUDA-event time (sum over its '
