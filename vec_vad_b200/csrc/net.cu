@@ -5,6 +5,7 @@
 // (SelfCompleteNetFull.forward), :619-652 (SelfCompleteNet1raw1of.forward); one UNet = inc -> down x3
 // -> up x3 -> outc (model/unet.py:187-196); loss + backward = train.py:385-402.
 #include <new>
+#include <stdlib.h>
 
 #include "unet_kernels.h"
 
@@ -36,6 +37,7 @@ constexpr int NT = VECVAD_N_UPS;
 
 }  // namespace
 
+#define VV_NEV 48
 struct vecvad_net {
     vecvad_net_config cfg;
     int G, F, S, T, cin_real, cinp;
@@ -58,6 +60,10 @@ struct vecvad_net {
     char *zero_bwd;  size_t zero_bwd_bytes;   // weight-gradient accumulators + BN backward sums
     // state of the last forward
     int lastB, last_training, have_dout;
+    // weight-gradient tiles run on a side stream (they are off the backward critical path: nothing downstream reads dW)
+    cudaStream_t wg_stream;
+    cudaEvent_t ev[VV_NEV];
+    int ev_next, use_side;
 };
 
 namespace {
@@ -229,11 +235,30 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
     int H[NU] = {S, S, S / 2, S / 2, S / 4, S / 4, S / 8, S / 8, S / 4, S / 4, S / 2, S / 2, S, S};
     for (int u = 0; u < NU; u++) { n->uC[u] = C[u]; n->uCp[u] = (u == 0) ? n->cinp : C[u]; n->uN[u] = N[u]; n->uH[u] = H[u]; }
     for (int k = 0; k < NT; k++) { n->tCi[k] = F << (3 - k); n->tCo[k] = F << (2 - k); n->tH[k] = S >> (3 - k); }
+    {
+        const char *e = getenv("VECVAD_WGRAD_STREAM");
+        n->use_side = !(e && e[0] == '0');
+        if (n->use_side) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);          // lo = least priority: the critical path keeps the SMs
+            if (cudaStreamCreateWithPriority(&n->wg_stream, cudaStreamNonBlocking, lo) != cudaSuccess) n->use_side = 0;
+            for (int i = 0; n->use_side && i < VV_NEV; i++)
+                if (cudaEventCreateWithFlags(&n->ev[i], cudaEventDisableTiming) != cudaSuccess) n->use_side = 0;
+        }
+    }
     *out = n;
     return 0;
 }
 
-extern "C" void vecvad_net_destroy(vecvad_net *net) { delete net; }
+extern "C" void vecvad_net_destroy(vecvad_net *net) {
+    if (!net) return;
+    if (net->use_side) {
+        cudaStreamSynchronize(net->wg_stream);
+        for (int i = 0; i < VV_NEV; i++) cudaEventDestroy(net->ev[i]);
+        cudaStreamDestroy(net->wg_stream);
+    }
+    delete net;
+}
 
 extern "C" int vecvad_net_workspace_bytes(const vecvad_net *net, int batch, int64_t *bytes) {
     VV_REQUIRE(net && bytes && batch >= 1, "workspace_bytes: bad arguments");
@@ -425,6 +450,36 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         if ((r = vv_outconv_bwd(q, G, st))) return r;
     }
     const VvTaps t3f = taps3x3(+1), t3b = taps3x3(-1), t2f = taps2x2(+1), t2b = taps2x2(-1);
+    // ---- side stream for the weight-gradient tiles.  fork: sB waits for everything issued so far on st, runs the wgrad, and
+    // leaves an event; a kernel on st that overwrites the gradient buffer (GA / GB) the wgrad still reads waits for it first.
+    cudaStream_t sB = n->use_side ? n->wg_stream : st;
+    cudaEvent_t pend[2] = {nullptr, nullptr}, last_wg = nullptr;
+    n->ev_next = 0;
+    auto next_ev = [&]() { return n->ev[(n->ev_next++) % VV_NEV]; };
+    auto before_write = [&](const float *ptr) -> int {
+        const int i = ptr == n->GA ? 0 : (ptr == n->GB ? 1 : -1);
+        if (n->use_side && i >= 0 && pend[i]) {
+            VV_CK(cudaStreamWaitEvent(st, pend[i], 0));
+            pend[i] = nullptr;
+        }
+        return 0;
+    };
+    auto fork = [&]() -> int {
+        if (!n->use_side) return 0;
+        cudaEvent_t e = next_ev();
+        VV_CK(cudaEventRecord(e, st));
+        VV_CK(cudaStreamWaitEvent(sB, e, 0));
+        return 0;
+    };
+    auto mark = [&](const float *reads) -> int {
+        if (!n->use_side) return 0;
+        cudaEvent_t e = next_ev();
+        VV_CK(cudaEventRecord(e, sB));
+        const int i = reads == n->GA ? 0 : (reads == n->GB ? 1 : -1);
+        if (i >= 0) pend[i] = e;
+        last_wg = e;
+        return 0;
+    };
     bool batched_scatter = true;       // conv weight gradients go back to PyTorch's layout in one launch at the end
     for (int u = 0; u < NU; u++) batched_scatter = batched_scatter && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
 
@@ -441,6 +496,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
         q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.gamma_off = c.bn_w[u]; q.beta_off = c.bn_b[u];
         int rr;
+        if ((rr = before_write(dz_buf))) return rr;
         {
             VvProfScope ps(VV_PROF_BN, 0, st);
             rr = vv_bn_bwd(q, G, st);
@@ -454,10 +510,12 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.B = B; w.H = H; w.W = H;
         w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
         w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
-        if ((rr = run_wgrad(n, w, st, n->uC[u]))) return rr;
+        if ((rr = fork())) return rr;
+        if ((rr = run_wgrad(n, w, sB, n->uC[u]))) return rr;
         if (!batched_scatter &&
-            (rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, st)))
+            (rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, sB)))
             return rr;
+        if ((rr = mark(dz_buf))) return rr;
         // (pre-BN conv bias: its gradient is exactly zero in training mode -- left at the memset value; the reference
         //  produces round-off noise there)
         if (din) {
@@ -468,6 +526,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             p.Wt = n->Wd[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3b; p.N = n->uC[u];
             p.O = din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
             p.bias = nullptr; p.stats = nullptr; p.G = G;
+            if ((rr = before_write(din->p))) return rr;
             if ((rr = run_igemm(n, p, st))) return rr;
         }
         return 0;
@@ -486,8 +545,10 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.B = B; w.H = Hi; w.W = Hi;
         w.Gd = dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
         w.taps = t2f; w.dW = n->tdW[k]; w.dw_gs = 16LL * Co * Ci; w.G = G;
-        if ((rr = run_wgrad(n, w, st))) return rr;
-        if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, st))) return rr;
+        if ((rr = fork())) return rr;
+        if ((rr = run_wgrad(n, w, sB))) return rr;
+        if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, sB))) return rr;
+        if ((rr = mark(nullptr))) return rr;
         VvIGemm p;
         memset(&p, 0, sizeof(p));
         p.A = dhalf.p; p.a_gs = dhalf.gs; p.lda = dhalf.ld; p.a_coff = dhalf.coff; p.a_s2d = 1; p.Kt = 4 * Co;
@@ -495,6 +556,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         p.Wt = n->tWd[k]; p.w_gs = 16LL * Co * Ci; p.taps = t2b; p.N = Ci;
         p.O = ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
         p.bias = nullptr; p.stats = nullptr; p.G = G;
+        if ((rr = before_write(ddeep.p))) return rr;
         return run_igemm(n, p, st);
     };
 
@@ -535,6 +597,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
                 return r;
         }
     }
+    if (n->use_side && last_wg) VV_CK(cudaStreamWaitEvent(st, last_wg, 0));      // join: every weight gradient is complete
     if (batched_scatter) {
         VvPrepAll all;
         memset(&all, 0, sizeof(all));
