@@ -167,9 +167,12 @@ def test_against_oracle_fresh_inputs(batch, path):
         assert abs(got[1] - lo_) <= tol * abs(lo_), (step, got, lo_)
         if step == 0:
             check_stats(1e-4 if not tc else 1e-2, 1)         # statistics of the first batch: no optimiser history involved
-    # after three steps the weights themselves have drifted apart by round-off x Adam(eps=1e-7); the 4x4-resolution
-    # layers see only batch*16 samples per channel, so their means are the most sensitive
-    check_stats(3e-2 if not tc else 0.2, 3)
+    # after three steps: (a) the reference's pre-BN biases have random-walked by up to lr per step (round-off gradients
+    # through Adam(eps=1e-7)) and its running_mean has integrated those biases with momentum weights, so running_mean - bias
+    # agrees only up to ~3*lr = 3e-3 absolute (values are ~3e-2 at the 4x4 layers, which see batch*16 samples per channel);
+    # (b) the split weight-gradient reduction here is summed in a run-dependent order.  Hence a 10 % bound on this check;
+    # the tight gates are the step-1 statistics above and the per-step losses.
+    check_stats(0.1 if not tc else 0.2, 3)
 
 
 def test_cubes_to_tensors_bit_exact(golden_dir):
