@@ -206,3 +206,34 @@ def test_reference_style_loop_with_torch_adam():
         opt.step()
         tol = 1e-5 if step == 0 else 1e-3
         assert abs(loss_raw.item() - lr_) <= tol * lr_ and abs(loss_of.item() - lo_) <= tol * lo_
+
+
+@pytest.mark.parametrize('tc', [False, True])
+def test_side_stream_weight_gradients_equal_single_stream(tc, monkeypatch):
+    """The weight-gradient tiles run on a side stream with event-tracked buffer hazards (net.cu).  Same weights, same cubes:
+    the flat gradient buffer must equal the single-stream schedule's up to the run-dependent order of the split fp32
+    reductions -- partial sums over ~10^5 pixels that cancel to gradients ~10^3 times smaller, measured run-to-run spread
+    2e-4 (fp32 tiles) / 1e-3 (tf32 tiles) of the gradient range even on one stream -- repeatedly, at a batch large enough to
+    keep both streams busy.  A hazard violation (a tile reading a half-rewritten gradient buffer) shows up at O(1)."""
+    kind, kw = CONFIGS['net4_flow_b2']
+    raw_u8, flow = orc.synthetic_cubes(64, t_of=1, seed=7)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    x, x_of = x.cuda(), x_of.cuda()
+    grads = {}
+    for side in ('0', '1'):
+        monkeypatch.setenv('VECVAD_WGRAD_STREAM', side)          # read when the engine is created
+        torch.manual_seed(3)
+        m = vu.SelfCompleteNet4(use_tensor_cores=tc, **kw).cuda().train()
+        sse = torch.empty((6, 64), device='cuda')
+        runs = []
+        for rep in range(4):
+            m._run_forward(x, x_of, training=True, sse=sse, want_outputs=False)
+            m._run_backward(None, None)
+            torch.cuda.synchronize()
+            runs.append(m.flat_grads.clone())
+        grads[side] = runs
+    ref = grads['0'][0]
+    scale = ref.abs().max().item()
+    for side in ('0', '1'):
+        for g_ in grads[side]:
+            assert (g_ - ref).abs().max().item() <= (5e-3 if tc else 1e-3) * scale, side
