@@ -227,7 +227,8 @@ def run_ours(args):
                              'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak,
                              'note': 'achieved = algorithmic conv FLOPs of the dominant kernel class / its CUDA-event time (sum over its '
                                      'launches in one step, measured live in a separate pass); peak = %s sustained bf16 cuBLAS (%s); the '
-                                     'tiles are kind::tf32 whose hardware rate is half the bf16 rate (peak_tf32)'
+                                     'tiles are kind::tf32 whose hardware rate is half the bf16 rate (peak_tf32); the weight-gradient tiles run '
+                                     'concurrently on a side stream, so class times overlap and include their mutual contention'
                                      % (src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md fallback')},
                 'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in prof.items() if v[2] > 0}}
         if world == 1 and not args.no_cpu:
@@ -243,8 +244,8 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=30)
-    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--net', default='net4', choices=sorted(NET_KW))
     ap.add_argument('--batch', type=int, default=128, help='cubes per GPU per step')
