@@ -237,3 +237,35 @@ def test_side_stream_weight_gradients_equal_single_stream(tc, monkeypatch):
     for side in ('0', '1'):
         for g_ in grads[side]:
             assert (g_ - ref).abs().max().item() <= (5e-3 if tc else 1e-3) * scale, side
+
+
+@pytest.mark.parametrize('tc', [False, True])
+def test_full_batch_properties(tc):
+    """BASELINE.json batch (128 cubes, 5raw1of): properties that need no oracle run.
+    (a) the two losses of the fused train step are the means of the per-cube SSE it reports;
+    (b) eval-mode scoring is idempotent (bit-identical on a second pass);
+    (c) eval-mode scores are per-cube: permuting the batch permutes them, bit for bit (every output row of a tile is
+        computed from its own operand row, whichever cubes share the tile);
+    (d) a batch made of one cube repeated scores every copy identically."""
+    kind, kw = CONFIGS['net4_flow_b2']
+    torch.manual_seed(9)
+    m = vu.SelfCompleteNet4(use_tensor_cores=tc, **kw).cuda()
+    raw_u8, flow = orc.synthetic_cubes(128, t_of=1, seed=21)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    x, x_of = x.cuda(), x_of.cuda()
+    m.train()
+    m.init_adam()
+    sse = torch.empty((6, 128), device='cuda')
+    losses = m.train_step(x, x_of, sse=sse).cpu().numpy()
+    s = sse.double().cpu().numpy()
+    np.testing.assert_allclose(losses[0], s[:5].sum() / (128 * 15 * 1024), rtol=1e-5)
+    np.testing.assert_allclose(losses[1], s[5].sum() / (128 * 2 * 1024), rtol=1e-5)
+    m.eval()
+    r1, o1 = m.score(x, x_of)
+    r2, o2 = m.score(x, x_of)
+    assert torch.equal(r1, r2) and torch.equal(o1, o2)
+    perm = torch.randperm(128, generator=torch.Generator().manual_seed(1)).cuda()
+    rp, op_ = m.score(x[perm].contiguous(), x_of[perm].contiguous())
+    assert torch.equal(rp, r1[perm]) and torch.equal(op_, o1[perm])
+    rr, _ = m.score(x[:1].expand(128, -1, -1, -1).contiguous(), x_of[:1].expand(128, -1, -1, -1).contiguous())
+    assert torch.equal(rr, rr[:1].expand(128)) and torch.equal(rr[0], r1[0])
