@@ -67,3 +67,23 @@ def test_train_and_test_entry_points_end_to_end(tmp_path):
     assert float(res['roc_auc']) > 0.9          # fast squares score higher than the slow ones the UNets were trained on
     mask = torch.load(os.path.join(root, 'results', 'UCSDped2', 'score_mask', '7'), weights_only=False)
     assert mask.shape == (240, 360) and mask.min() == -100000
+
+
+@pytest.mark.gpu
+def test_batched_frame_scoring_equals_frame_by_frame(tmp_path, monkeypatch):
+    """score_frames batches the cubes of many frames per model call; the per-frame score masks must equal the reference's
+    one-forward-per-(frame, block) schedule (max_cubes=1 forces it) bit for bit."""
+    root = syn.make(str(tmp_path / 'ws'), cfg_overrides={'context_of_num': 0})
+    monkeypatch.chdir(root)
+    cfg = pl.Config('config.cfg', 'test')
+    probe = pl.vd.unified_dataset_interface('UCSDped2', os.path.join('raw_datasets', 'UCSDped2'), context_frame_num=1, mode='test',
+                                            border_mode='hard')
+    fs, fs2, fb, scene = pl.extract_foreground_test(cfg, pl.load_or_make_bboxes(cfg, probe))
+    torch.manual_seed(0)
+    net = pl.build_network(cfg).cuda().eval()
+    dev = torch.device('cuda', 0)
+    a = pl.score_frames(cfg, lambda s, h, w: net, lambda s, h, w: ((3.0, 2.0), (1.0, 0.5)), fs, fs2, fb, dev)
+    b = pl.score_frames(cfg, lambda s, h, w: net, lambda s, h, w: ((3.0, 2.0), (1.0, 0.5)), fs, fs2, fb, dev, max_cubes=1)
+    assert len(a) == len(b) == 10
+    for ma, mb in zip(a, b):
+        assert np.array_equal(ma, mb) and ma.max() > -100000

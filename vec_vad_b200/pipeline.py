@@ -387,33 +387,64 @@ def _stats(scores):
 
 
 @torch.no_grad()
-def score_frames(cfg, net_for, stats_for, foreground_set, foreground_set2, foreground_bbox_set, device, out_dir=None, scene_idx=None):
+def score_frames(cfg, net_for, stats_for, foreground_set, foreground_set2, foreground_bbox_set, device, out_dir=None, scene_idx=None,
+                 max_cubes=4096):
     """test.py:270-358: per frame, per block: forward all cubes of the block, per-cube SSE, z-normalise with the training
-    statistics, weight, paint the bbox rectangles with a running max.  Returns the list of per-frame score masks."""
+    statistics, weight, paint the bbox rectangles with a running max.  Returns the list of per-frame score masks.
+
+    The reference forwards one tiny batch per (frame, block) (about 17 cubes per frame on UCSDped2: launch-bound).  Eval-mode
+    scores are per-cube and independent of what else is in the batch -- bit for bit, tests/test_unet_gpu.py::
+    test_full_batch_properties -- so the cubes of consecutive frames that use the same model are scored in batches of up to
+    ``max_cubes`` and scattered back; the masks are identical to frame-by-frame scoring."""
     h, w = vd.frame_size[cfg.dataset_name][:2]
-    masks = []
-    for f in range(len(foreground_set)):
-        if out_dir is not None:
-            print('Calculating scores for {}-th frame'.format(f))
-        pix = -1 * np.ones(shape=(h, w)) * BIG_NUMBER
-        s = scene_idx[f] - 1 if scene_idx is not None else None
+    n_frames = len(foreground_set)
+    scores = [[[None for _ in foreground_set[f][hh]] for hh in range(len(foreground_set[f]))] for f in range(n_frames)]
+    pending = {}          # model key -> list of (f, hh, ww, n)
+
+    def flush(key):
+        items = pending.pop(key, [])
+        if not items:
+            return
+        s_, hh, ww = key
+        net = net_for(s_, hh, ww)
+        raw_np = np.concatenate([foreground_set[f][a][b] for (f, a, b, _) in items], axis=0)
+        flow_np = np.concatenate([foreground_set2[f][a][b] for (f, a, b, _) in items], axis=0)
+        x, x_of = vd.cubes_to_device_tensors(torch.as_tensor(raw_np).to(device), torch.as_tensor(flow_np).to(device, torch.float32))
+        raw, of = net.score(x, x_of)
+        (rm, rs), (om, os_) = stats_for(s_, hh, ww)
+        sc = cfg.w_raw * ((raw.cpu().numpy() - rm) / rs)
+        if cfg.useFlow:
+            sc = sc + cfg.w_of * ((of.cpu().numpy() - om) / os_)
+        o = 0
+        for (f, a, b, n) in items:
+            scores[f][a][b] = sc[o:o + n]
+            o += n
+
+    for f in range(n_frames):
+        s_ = scene_idx[f] - 1 if scene_idx is not None else None
         for hh in range(len(foreground_set[f])):
             for ww in range(len(foreground_set[f][hh])):
                 cubes = foreground_set[f][hh][ww]
                 if len(cubes) == 0:
                     continue
-                net = net_for(s, hh, ww)
-                if net is None:                          # objects where training saw none: anomaly (test.py:307-309)
-                    scores = np.ones(cubes.shape[0]) * BIG_NUMBER
-                else:
-                    x, x_of = vd.cubes_to_device_tensors(torch.as_tensor(cubes).to(device),
-                                                         torch.as_tensor(foreground_set2[f][hh][ww]).to(device, torch.float32))
-                    raw, of = net.score(x, x_of)
-                    (rm, rs), (om, os_) = stats_for(s, hh, ww)
-                    scores = cfg.w_raw * ((raw.cpu().numpy() - rm) / rs)
-                    if cfg.useFlow:
-                        scores = scores + cfg.w_of * ((of.cpu().numpy() - om) / os_)
-                paint_score_mask(pix, scores, foreground_bbox_set[f][hh][ww], BIG_NUMBER)
+                key = (s_, hh, ww)
+                if net_for(s_, hh, ww) is None:          # objects where training saw none: anomaly (test.py:307-309)
+                    scores[f][hh][ww] = np.ones(cubes.shape[0]) * BIG_NUMBER
+                    continue
+                pending.setdefault(key, []).append((f, hh, ww, cubes.shape[0]))
+                if sum(it[3] for it in pending[key]) >= max_cubes:
+                    flush(key)
+    for key in list(pending):
+        flush(key)
+    masks = []
+    for f in range(n_frames):
+        if out_dir is not None:
+            print('Calculating scores for {}-th frame'.format(f))
+        pix = -1 * np.ones(shape=(h, w)) * BIG_NUMBER
+        for hh in range(len(foreground_set[f])):
+            for ww in range(len(foreground_set[f][hh])):
+                if scores[f][hh][ww] is not None:
+                    paint_score_mask(pix, scores[f][hh][ww], foreground_bbox_set[f][hh][ww], BIG_NUMBER)
         if out_dir is not None:
             torch.save(pix, os.path.join(out_dir, '{}'.format(f)))
         masks.append(pix)
