@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 2
+#define VECVAD_ABI_VERSION 3
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -130,6 +130,10 @@ typedef struct vecvad_net_config {
     int64_t out_w, out_b;
     int64_t run_mean[VECVAD_N_UNITS], run_var[VECVAD_N_UNITS];
     int use_tensor_cores;                     /* 1: tcgen05 kind::tf32 implicit-GEMM tiles; 0: fp32 SIMT tiles   */
+    /* A UNet set may be split over several nets (one per stream) that share the flat buffers and the output tensors:
+     * the loss means and the external gradient tensors then span ALL raw / flow outputs, not only this net's.
+     * 0 = this net's own count. */
+    int n_raw_total, n_of_total;
 } vecvad_net_config;
 
 typedef struct vecvad_net vecvad_net;

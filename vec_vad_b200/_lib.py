@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -38,7 +38,7 @@ class NetConfig(C.Structure):
         ('up_w', C.c_int64 * N_UPS), ('up_b', C.c_int64 * N_UPS),
         ('out_w', C.c_int64), ('out_b', C.c_int64),
         ('run_mean', C.c_int64 * N_UNITS), ('run_var', C.c_int64 * N_UNITS),
-        ('use_tensor_cores', C.c_int),
+        ('use_tensor_cores', C.c_int), ('n_raw_total', C.c_int), ('n_of_total', C.c_int),
     ]
 
 

@@ -323,6 +323,8 @@ int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st) {
         static int cap = -1;
         if (cap < 0) { const char *e = getenv("VECVAD_TC2_STAGES"); cap = e ? atoi(e) : 0; }
         if (cap >= 2 && stages > cap) stages = cap;
+        else if (cap == 0 && stages > 3) stages = 3;      // deeper rings buy nothing (measured) and their shared memory keeps
+                                                          // the elementwise kernels of the other streams off the SM
     }
     VV_REQUIRE(stages >= 2, "igemm_tc2: tile does not fit in shared memory");
     tp.stages = stages;

@@ -42,7 +42,7 @@ struct vecvad_net {
     vecvad_net_config cfg;
     int G, F, S, T, cin_real, cinp;
     VvIntG slot, erase, outc, isflow, tidx, oslot;
-    int n_raw_out, n_of_out;
+    int n_raw_out, n_of_out, n_raw_tot, n_of_tot;
     // unit geometry: conv unit u maps C -> N at resolution H
     int uC[NU], uCp[NU], uN[NU], uH[NU];
     int tCi[NT], tCo[NT], tH[NT];          // transposed convs: Ci -> Co, input resolution tH
@@ -228,6 +228,8 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
         else max_raw = cfg->out_slot[g] > max_raw ? cfg->out_slot[g] : max_raw;
     }
     n->n_raw_out = max_raw + 1; n->n_of_out = max_of + 1;
+    n->n_raw_tot = cfg->n_raw_total > 0 ? cfg->n_raw_total : n->n_raw_out;
+    n->n_of_tot = cfg->n_of_total > 0 ? cfg->n_of_total : n->n_of_out;
     const int F = n->F, S = n->S;
     // conv units: (C -> N @H)
     int C[NU] = {n->cin_real, F, F, 2 * F, 2 * F, 4 * F, 4 * F, 8 * F, 8 * F, 4 * F, 4 * F, 2 * F, 2 * F, F};
@@ -398,8 +400,8 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     q.sse = sse;
     q.dout = (sse && training) ? n->DOUT : nullptr;
     // loss = lambda_raw * mean_{B,3*n_raw,S,S} + lambda_of * mean_{B,2*n_of,S,S}   (train.py:385-392)
-    q.coef_raw = n->n_raw_out ? 2.f * lambda_raw / ((float)B * 3.f * n->n_raw_out * S * S) : 0.f;
-    q.coef_of = n->n_of_out ? 2.f * lambda_of / ((float)B * 2.f * n->n_of_out * S * S) : 0.f;
+    q.coef_raw = n->n_raw_tot ? 2.f * lambda_raw / ((float)B * 3.f * n->n_raw_tot * S * S) : 0.f;
+    q.coef_of = n->n_of_tot ? 2.f * lambda_of / ((float)B * 2.f * n->n_of_tot * S * S) : 0.f;
     if ((r = vv_outconv_fwd(q, G, st))) return r;
     n->lastB = B; n->last_training = training; n->have_dout = (sse && training) ? 1 : 0;
     return 0;
@@ -407,8 +409,8 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
 
 extern "C" int vecvad_net_losses(vecvad_net *n, const float *sse, int batch, float *losses, vecvad_stream stream) {
     VV_REQUIRE(n && sse && losses && batch >= 1, "net_losses: bad arguments");
-    float inv_raw = n->n_raw_out ? 1.f / ((float)batch * 3.f * n->n_raw_out * n->S * n->S) : 0.f;
-    float inv_of = n->n_of_out ? 1.f / ((float)batch * 2.f * n->n_of_out * n->S * n->S) : 0.f;
+    float inv_raw = n->n_raw_tot ? 1.f / ((float)batch * 3.f * n->n_raw_tot * n->S * n->S) : 0.f;
+    float inv_of = n->n_of_tot ? 1.f / ((float)batch * 2.f * n->n_of_tot * n->S * n->S) : 0.f;
     return vv_losses(sse, n->G, batch, n->isflow, inv_raw, inv_of, losses, (cudaStream_t)stream);
 }
 
@@ -445,8 +447,8 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         q.out_channels = n->outc; q.target_is_flow = n->isflow; q.out_slot = n->oslot;
         q.M = B * S * S; q.S = S; q.F = F;
         q.dout = n->DOUT;
-        q.grad_raw_out = grad_raw_out; q.raw_out_channels = 3 * n->n_raw_out;
-        q.grad_of_out = grad_of_out; q.of_out_channels = 2 * n->n_of_out;
+        q.grad_raw_out = grad_raw_out; q.raw_out_channels = 3 * n->n_raw_tot;
+        q.grad_of_out = grad_of_out; q.of_out_channels = 2 * n->n_of_tot;
         if ((r = vv_outconv_bwd(q, G, st))) return r;
     }
     const VvTaps t3f = taps3x3(+1), t3b = taps3x3(-1), t2f = taps2x2(+1), t2b = taps2x2(-1);

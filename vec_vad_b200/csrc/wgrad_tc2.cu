@@ -244,6 +244,12 @@ int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st) {
     wp.g_stages = 2;
     int a_stages = (WG2_SMEM_MAX - fixed - wp.g_stages * g_stage) / wp.a_bytes;
     if (a_stages > 8) a_stages = 8;
+    {
+        static int cap = -1;
+        if (cap < 0) { const char *e = getenv("VECVAD_WG2_STAGES"); cap = e ? atoi(e) : 0; }
+        if (cap >= 2 && a_stages > cap) a_stages = cap;
+        else if (cap == 0 && a_stages > 3) a_stages = 3;  // see igemm_tc2.cu: leaves shared memory for co-resident BN kernels
+    }
     VV_REQUIRE(a_stages >= 2, "wgrad_tc2: tile does not fit in shared memory");
     wp.a_stages = a_stages;
     const int smem = fixed + wp.g_stages * g_stage + a_stages * wp.a_bytes;

@@ -172,8 +172,7 @@ class CompletionNet(nn.Module):
         self._init_reference_order()          # seeded-init parity with the reference constructors
         self._register_tree()
         # ---- engine state
-        self._net = None
-        self._ws = None
+        self._parts = None                    # [dict(net, ws, g0, g1, stream)]: the UNets split over concurrent streams
         self._ws_batch = 0
         self._gen = 0
         self._adam = None
@@ -387,12 +386,14 @@ class CompletionNet(nn.Module):
         assert len({p[0] for p in plan}) == len(plan), 'a UNet would run twice in one forward'
         self._plan_list, self._n_raw_out, self._n_of_out = plan, n_raw, n_of
 
-    def _config(self):
+    def _config(self, g0=0, g1=None):
+        plan = self._plan_list[g0:g1]
         cfg = _lib.NetConfig()
-        cfg.n_unets = len(self._plan_list)
+        cfg.n_unets = len(plan)
+        cfg.n_raw_total, cfg.n_of_total = self._n_raw_out, self._n_of_out
         cfg.features_root, cfg.tot_raw_num, cfg.patch = self.features_root, self.tot_raw_num, self.patch_size
         cfg.padding = int(bool(self.padding))
-        for g, (slot, erase, oc, isflow, tidx, oslot) in enumerate(self._plan_list):
+        for g, (slot, erase, oc, isflow, tidx, oslot) in enumerate(plan):
             cfg.param_slot[g], cfg.erase_frame[g], cfg.out_channels[g] = slot, erase, oc
             cfg.target_is_flow[g], cfg.target_index[g], cfg.out_slot[g] = isflow, tidx, oslot
         cfg.slot_param_stride, cfg.slot_stat_stride = self._pstride, self._sstride
@@ -409,9 +410,9 @@ class CompletionNet(nn.Module):
         return cfg
 
     def _release_engine(self):
-        if getattr(self, '_net', None) is not None:
-            _lib.lib().vecvad_net_destroy(self._net)
-        self._net, self._ws, self._ws_batch = None, None, 0
+        for part in (getattr(self, '_parts', None) or []):
+            _lib.lib().vecvad_net_destroy(part['net'])
+        self._parts, self._ws_batch = None, 0
 
     def __del__(self):
         try:
@@ -433,25 +434,59 @@ class CompletionNet(nn.Module):
         new.train(self.training)
         return new
 
+    def _split(self):
+        """The G UNets are independent and MAY be split into parts that run on concurrent streams (VECVAD_NET_PARTS=k).
+        Measured on B200 at batch 128 (5raw1of): 1 part 4.45 ms/step, 2 parts 5.27, 3 parts 4.73 -- the persistent
+        tensor-core tiles of two parts end up co-resident and contend for the same SM ingress, so the default is one part;
+        the overlap that pays is inside the engine (weight-gradient tiles on a side stream, csrc/net.cu)."""
+        import os
+        G = len(self._plan_list)
+        want = int(os.environ.get('VECVAD_NET_PARTS', '1'))
+        k = max(1, min(want, G // 2 if G >= 4 else 1))
+        bounds = [round(i * G / k) for i in range(k + 1)]
+        return [(bounds[i], bounds[i + 1]) for i in range(k)]
+
     def _engine(self, batch):
         _lib.require_cuda(self._pflat)
         L = _lib.lib()
         if self._gflat is None:
             self._gflat = torch.zeros_like(self._pflat)
-        if self._net is None:
-            h = C.c_void_p()
-            cfg = self._config()
-            _lib.check(L.vecvad_net_create(C.byref(cfg), C.byref(h)), 'net_create')
-            self._net = h
+        if self._parts is None:
+            self._parts = []
+            for i, (g0, g1) in enumerate(self._split()):
+                h = C.c_void_p()
+                cfg = self._config(g0, g1)
+                _lib.check(L.vecvad_net_create(C.byref(cfg), C.byref(h)), 'net_create')
+                self._parts.append(dict(net=h, ws=None, g0=g0, g1=g1,
+                                        stream=None if i == 0 else torch.cuda.Stream(device=self._pflat.device)))
         if batch > self._ws_batch:
-            nb = C.c_int64()
-            _lib.check(L.vecvad_net_workspace_bytes(self._net, batch, C.byref(nb)), 'workspace_bytes')
-            self._ws = torch.empty(nb.value + 256, dtype=torch.uint8, device=self._pflat.device)
-            base = (self._ws.data_ptr() + 255) // 256 * 256
-            _lib.check(L.vecvad_net_bind(self._net, _lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(self._sflat),
-                                         C.c_void_p(base), nb.value, batch), 'net_bind')
+            for part in self._parts:
+                nb = C.c_int64()
+                _lib.check(L.vecvad_net_workspace_bytes(part['net'], batch, C.byref(nb)), 'workspace_bytes')
+                part['ws'] = torch.empty(nb.value + 256, dtype=torch.uint8, device=self._pflat.device)
+                base = (part['ws'].data_ptr() + 255) // 256 * 256
+                _lib.check(L.vecvad_net_bind(part['net'], _lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(self._sflat),
+                                             C.c_void_p(base), nb.value, batch), 'net_bind')
             self._ws_batch = batch
-        return self._net
+        return self._parts
+
+    def _on_parts(self, fn):
+        """Run fn(part, stream_handle) for every part: part 0 on the caller's stream, the others on their own stream, forked
+        after everything already queued and joined back before anything queued afterwards."""
+        cur = torch.cuda.current_stream()
+        start = None
+        for part in self._parts:
+            st = part['stream']
+            if st is None:
+                fn(part, C.c_void_p(cur.cuda_stream))
+            else:
+                if start is None:
+                    start = cur.record_event()
+                st.wait_event(start)
+                fn(part, C.c_void_p(st.cuda_stream))
+        for part in self._parts:
+            if part['stream'] is not None:
+                cur.wait_stream(part['stream'])
 
     def _run_forward(self, x, x_of, training, sse, lambda_raw=1.0, lambda_of=1.0, want_outputs=True):
         _lib.require_cuda(x, x_of if torch.is_tensor(x_of) else None)
@@ -463,21 +498,28 @@ class CompletionNet(nn.Module):
         if self._n_of_out > 0 and torch.is_tensor(x_of):
             xo = x_of.contiguous().float()
             xoc = xo.shape[1]
-        net = self._engine(B)
+        self._engine(B)
         S = self.patch_size
         raw_out = x.new_empty((B, RAW_CH * self._n_raw_out, S, S)) if want_outputs else None
         of_out = x.new_empty((B, OF_CH * self._n_of_out, S, S)) if (want_outputs and self._n_of_out > 0) else None
         self._gen += 1
-        _lib.check(_lib.lib().vecvad_net_forward(net, _lib.ptr(x), _lib.ptr(xo), xoc, B, int(training), _lib.ptr(raw_out),
-                                                RAW_CH * self._n_raw_out, _lib.ptr(of_out), OF_CH * self._n_of_out, _lib.ptr(sse),
-                                                float(lambda_raw), float(lambda_of), _lib.cur_stream()), 'net_forward')
+        L = _lib.lib()
+
+        def fwd(part, stream):
+            sse_p = None if sse is None else C.c_void_p(sse.data_ptr() + 4 * part['g0'] * B)      # sse is [G][B]: rows g0..g1
+            _lib.check(L.vecvad_net_forward(part['net'], _lib.ptr(x), _lib.ptr(xo), xoc, B, int(training), _lib.ptr(raw_out),
+                                            RAW_CH * self._n_raw_out, _lib.ptr(of_out), OF_CH * self._n_of_out, sse_p,
+                                            float(lambda_raw), float(lambda_of), stream), 'net_forward')
+        self._on_parts(fwd)
         if training:
             self._nbt += 1                                  # BatchNorm2d.num_batches_tracked
         self._keep = (x, xo)                                # inputs must outlive the asynchronous kernels
         return raw_out, of_out
 
     def _run_backward(self, g_raw, g_of):
-        _lib.check(_lib.lib().vecvad_net_backward(self._net, _lib.ptr(g_raw), _lib.ptr(g_of), _lib.cur_stream()), 'net_backward')
+        L = _lib.lib()
+        self._on_parts(lambda part, stream: _lib.check(L.vecvad_net_backward(part['net'], _lib.ptr(g_raw), _lib.ptr(g_of), stream),
+                                                       'net_backward'))
 
     # ------------------------------------------------------------------ reference surface
     def _targets(self, x, x_of):
@@ -542,7 +584,14 @@ class CompletionNet(nn.Module):
             losses = torch.empty(2, dtype=torch.float32, device=x.device)
         L = _lib.lib()
         self._run_forward(x, x_of, training=True, sse=sse, lambda_raw=lambda_raw, lambda_of=lambda_of, want_outputs=False)
-        _lib.check(L.vecvad_net_losses(self._net, _lib.ptr(sse), B, _lib.ptr(losses), _lib.cur_stream()), 'net_losses')
+        if len(self._parts) == 1:
+            _lib.check(L.vecvad_net_losses(self._parts[0]['net'], _lib.ptr(sse), B, _lib.ptr(losses), _lib.cur_stream()), 'net_losses')
+        else:                                               # each part: its share of the two means (global normalisation)
+            part_losses = torch.empty((len(self._parts), 2), dtype=torch.float32, device=x.device)
+            for i, part in enumerate(self._parts):
+                _lib.check(L.vecvad_net_losses(part['net'], C.c_void_p(sse.data_ptr() + 4 * part['g0'] * B), B,
+                                               C.c_void_p(part_losses.data_ptr() + 8 * i), _lib.cur_stream()), 'net_losses')
+            torch.sum(part_losses, dim=0, out=losses)
         self._run_backward(None, None)
         scale = 1.0
         if reduce_grads is not None:
