@@ -1,0 +1,26 @@
+"""Microbenchmark: per-dx-box tiles (use_tc 2) against flattened-sequence tiles (use_tc 4) on the 32x32-resolution layers.
+Each call also runs the (small) weight re-layout kernel.  Knobs: VECVAD_DBG_TC2 (1 skip stores, 2 skip statistics, 4 skip MMAs),
+VECVAD_FLAT_STAGES, VECVAD_TC2_STAGES."""
+import os, sys, torch
+sys.path.insert(0, '.')
+from vec_vad_b200 import _lib
+def run(b, h, cin, cout, use_tc, iters=int(os.environ.get('VV_ITERS', '30'))):
+    x = torch.randn(b, h, h, cin, device='cuda'); w = torch.randn(cout, cin, 3, 3, device='cuda'); bias = torch.randn(cout, device='cuda')
+    out = torch.empty(b, h, h, cout, device='cuda'); stats = torch.zeros(2*cout, dtype=torch.float64, device='cuda'); scratch = torch.empty(9*cout*cin, device='cuda')
+    L = _lib.lib()
+    def f():
+        _lib.check(L.vecvad_conv3x3_forward(_lib.ptr(x), cin, _lib.ptr(w), _lib.ptr(bias), _lib.ptr(out), _lib.ptr(stats), _lib.ptr(scratch), b, h, h, cin, cout, use_tc, _lib.cur_stream()))
+    for _ in range(3): f()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters): f()
+    e1.record(); torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) / iters * 1e3
+    fl = 2.0 * b * h * h * cout * cin * 9
+    print('[%s] B=%d H=%d %d->%d tc=%d: %.1f us  %.1f TFLOP/s' % (TAG, b, h, cin, cout, use_tc, t, fl / t / 1e6), flush=True)
+NB = int(os.environ.get('VV_B', '768'))
+TAG = ' '.join('%s=%s' % (k[7:], v) for k, v in sorted(os.environ.items()) if k.startswith('VECVAD_'))
+for cfg in [(NB, 32, 32, 32), (NB, 32, 64, 32), (NB, 32, 32, 64)]:
+    for tc in (2, 3):
+        run(*cfg, tc)

@@ -29,7 +29,7 @@ def run(shape, mode, tap=None, seed=0):
 
 
 if __name__ == '__main__':
-    for mode in (3, 4):
+    for mode in (3,):
         for shape in [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (2, 32, 32, 32, 64), (130, 32, 32, 32, 32), (2, 64, 64, 32, 32), (5, 16, 16, 32, 64)]:
             try:
                 err, s_err, d = run(shape, mode)

@@ -85,11 +85,11 @@ bool vv_igemm_tc_supported(const VvIGemm &p);
 // persistent tap-reuse variant (igemm_tc2.cu); falls back to vv_launch_igemm_tc when the driver refuses its tensor map
 bool vv_igemm_tc2_supported(const VvIGemm &p);
 int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st);
-// flattened-sequence 3x3 tiles (igemm_flat.cu): one activation box serves all nine taps.  bo_override: 0 = VECVAD_FLAT decides,
-// 1 / 2 = force the descriptor base-offset convention (unit tests)
+// flattened-sequence 3x3 tiles (igemm_flat.cu): one activation box serves all nine taps.  _shape_ok: what the kernel can run;
+// _supported: where the net engine prefers it (full-width rows, VECVAD_FLAT != 0)
 bool vv_igemm_flat_shape_ok(const VvIGemm &p);
 bool vv_igemm_flat_supported(const VvIGemm &p);
-int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st, int bo_override);
+int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st);
 bool vv_wgrad_tc_supported(const VvWGrad &p);
 // tap-reuse variant (wgrad_tc2.cu)
 bool vv_wgrad_tc2_supported(const VvWGrad &p);

@@ -3,22 +3,29 @@
 //   out[m, n] = bias[n] + sum_t sum_k A[shift(m, t), k] * Wt[t][n][k]          (VvIGemm, common.h; 3x3 taps of either sign)
 //
 // k_igemm_tc2 (igemm_tc2.cu) loads one box per distinct dx because a dx step inside a [rows][W] box wraps around the image
-// edge.  At 32x32 resolution that is 3 boxes of 6 rows per 4 output rows = 4.5 x the activation bytes through L2 -> shared
-// memory, and shared-memory bandwidth (TMA writes + the UMMA re-reading its 128-row A slice per tap) is what bounds those
-// layers.  Here the box is (W + 1) pixels wide: TMA zero-fills the out-of-range column x = W, so in
-// shared memory image rows sit P = W + 1 pixel-rows apart with ONE zero pixel between them, which is both the right padding
-// of row y and the left padding of row y + 1.  In that flattened sequence every tap (dy, dx) of every pixel is the constant
-// offset dy * P + dx, so the A operand of a tap is the SAME box read through a UMMA descriptor that starts (dy * P + dx) * 128
-// bytes further in -- 9 taps from one load.  A tile is 128 consecutive sequence positions of one image (positions on the
-// separator column or past the image are computed and discarded: W/P * L/(128*ceil(L/128)) = 86 % useful rows at 32x32);
-// its box is the 7 image rows those positions and their halo touch: 1.8 x the activation bytes instead of 4.5 x.
-//   Descriptor starts are 128-byte but not 1024-byte aligned: the swizzle phase of the start row goes into the descriptor's
-//   base-offset field (VECVAD_FLAT = 1 or 2 selects the convention; validated on the device by tests/test_conv_gpu.py).
-//   warp 0: TMA producer | warp 1: MMA issuer (+ TMEM alloc) | warps 2-5: epilogue (bias, NHWC stores, BatchNorm statistics).
+// edge: at 32x32 resolution that is 3 boxes of 6 rows per 4 output rows = 4.5 x the activation bytes through L2 -> shared
+// memory.  Here the box is (W + 1) pixels wide: TMA zero-fills the out-of-range column x = W, so in shared memory image rows
+// sit P = W + 1 pixel-rows apart with ONE zero pixel between them, which is both the right padding of row y and the left
+// padding of row y + 1.  In that flattened sequence every tap (dy, dx) of every pixel is the constant offset dy * P + dx, so
+// the A operand of a tap is the SAME box read through a UMMA descriptor that starts (dy * P + dx) * 128 bytes further in --
+// 9 taps from one load.  A tile is 128 consecutive sequence positions of one image (positions on the separator column or past
+// the image are computed and discarded: 86 % useful rows at 32x32); its box is the 7 image rows those positions and their
+// halo touch: 1.8 x the activation bytes instead of 4.5 x.
+//   Descriptor starts are 128-byte but not 1024-byte aligned.  Measured on the device (scratch/flat_probe.py): the UMMA applies
+//   the 128B swizzle to the absolute shared-memory address, so such a start reads the TMA-written box correctly with the
+//   descriptor's base-offset field left at 0 (setting it to the start row's phase gives wrong operands).
+//
+// Roles (352 threads): warp 0 TMA producer | warps 1-2 MMA issuers, alternating tiles, each with its own accumulator and its
+// own ring of TMA stages (one warp issues an MMA every ~75 cycles, the tensor pipe retires an N = 32 MMA in 40) | warps 3-6 and
+// 7-10: two epilogue sets, one per accumulator: tcgen05.ld, release the accumulator at once, then bias, BatchNorm statistics
+// and NHWC stores through a padded shared-memory staging tile (column sums without shuffles, full 128-byte lines per store
+// instruction).  At N = 32 the UMMA's operand reads take every shared-memory cycle (4 KB of A + 1 KB of B per 40-cycle MMA), so
+// everything the epilogue does through shared memory is slow (~2300 cycles per 128 x 32 block, measured): two sets keep it off
+// the critical path.
 #include "tc_common.cuh"
 
 #ifndef VECVAD_FLAT_DEFAULT
-#define VECVAD_FLAT_DEFAULT 0
+#define VECVAD_FLAT_DEFAULT 1
 #endif
 
 namespace {
@@ -26,11 +33,13 @@ namespace {
 struct FlatParams {
     int B, H, W, G;
     int P, L, tpi, m_tiles;         // row pitch W+1, positions per image H*P, tiles per image, tiles in total
+    unsigned mP, mtpi;              // ceil(2^32 / P), ceil(2^32 / tpi): n / d == __umulhi(n, m) for n * d < 2^32
     int rows;                       // image rows per box
-    int kchunks, stages;
+    int kchunks, spr;               // 32-channel slabs per tile; TMA stages per ring (two rings, one per MMA warp)
     int tap[3][3];                  // [dy+1][dx+1] -> tap index of the weight tensor
     int a_bytes, stage_bytes;
-    int bo_mode, dbg;
+    int dbg;                        // VECVAD_DBG_TC2 bits (timing experiments only): 1 skip stores, 2 skip statistics, 4 skip MMAs
+    unsigned long long *trace;      // VECVAD_FLAT_TRACE: cycle counters of CTA (0,0,0), see launch_flat
     int N;
     float *O;
     long long o_gs;
@@ -41,28 +50,26 @@ struct FlatParams {
     long long stats_gs;
 };
 
-constexpr int FL_THREADS = 192;
+constexpr int FL_THREADS = 352;
 constexpr int FL_SMEM_MAX = 227 * 1024;
-constexpr int FL_GUARD = 1024;      // zeroed bytes in front of stage 0 (a tile starting at x = 0 reads one pixel-row before its box)
-
-__device__ __forceinline__ uint64_t smem_desc_flat(uint32_t saddr, int bo_mode) {
-    uint64_t d = smem_desc_k_sw128(saddr);
-    if (bo_mode) d |= (uint64_t)((saddr >> 7) & 7) << 49;     // matrix base offset: phase of the start row in the 8-row swizzle atom
-    return d;
-}
+constexpr int FL_GUARD = 128;       // zeroed bytes in front of stage 0 (a tile starting at x = 0 reads one pixel-row before its box)
+constexpr int FL_STG_LD = 36;       // floats per staging row: 16-byte aligned, conflict-free for row writes and column reads
+constexpr int FL_STG_BYTES = 32 * FL_STG_LD * 4;
+constexpr int FL_MAX_RING = 4;
 
 template <int BN>
 __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const FlatParams p) {
     constexpr int B_TAP = BN * KS * 4;                       // one (tap, slab) weight tile
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t *stage0 = smem + FL_GUARD;
-    uint8_t *b_stat = stage0 + p.stages * p.stage_bytes;
-    uint8_t *tail = b_stat + 9 * p.kchunks * B_TAP;
-    uint64_t *full = (uint64_t *)tail;                       // [stages]
-    uint64_t *empty = full + 8;                              // [stages]
-    uint64_t *acc_full = empty + 8;                          // [2]
+    uint8_t *stage0 = (uint8_t *)(((uintptr_t)smem_raw + FL_GUARD + 1023) & ~(uintptr_t)1023);   // >= FL_GUARD bytes of ours in front
+                                                             // stage (ring r, slot j) at stage0 + (r * spr + j) * stage_bytes
+    uint8_t *b_stat = stage0 + 2 * p.spr * p.stage_bytes;
+    uint8_t *stg_base = b_stat + 9 * p.kchunks * B_TAP;
+    uint8_t *tail = stg_base + 8 * FL_STG_BYTES;
+    uint64_t *full = (uint64_t *)tail;                       // [2][FL_MAX_RING]
+    uint64_t *empty = full + 2 * FL_MAX_RING;                // [2][FL_MAX_RING]
+    uint64_t *acc_full = empty + 2 * FL_MAX_RING;            // [2]
     uint64_t *acc_empty = acc_full + 2;                      // [2]
     uint64_t *bfull = acc_empty + 2;                         // [1]
     uint32_t *tmem_slot = (uint32_t *)(bfull + 1);
@@ -72,9 +79,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.z;
     const int n0 = blockIdx.y * BN;
+    const bool tracer = p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < p.stages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2 * FL_MAX_RING; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], 4); }
         mbar_init(bfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -90,10 +98,10 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
         s_sum[i] = 0.f; s_sq[i] = 0.f;
     }
     // zero what TMA never writes but the MMAs may read: the guard in front of stage 0 and the slack behind every box
-    for (int i = threadIdx.x; i < FL_GUARD / 16; i += FL_THREADS) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < FL_GUARD / 16; i += FL_THREADS) reinterpret_cast<uint4 *>(stage0 - FL_GUARD)[i] = make_uint4(0, 0, 0, 0);
     {
         const int slack16 = (p.stage_bytes - p.a_bytes) / 16;
-        for (int i = threadIdx.x; i < p.stages * slack16; i += FL_THREADS) {
+        for (int i = threadIdx.x; i < 2 * p.spr * slack16; i += FL_THREADS) {
             const int s = i / slack16, j = i - s * slack16;
             reinterpret_cast<uint4 *>(stage0 + s * p.stage_bytes + p.a_bytes)[j] = make_uint4(0, 0, 0, 0);
         }
@@ -106,118 +114,189 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------- TMA producer: weights once, then one box per (tile, 32-channel slab)
+            // ---------------- TMA producer: weights once, then one box per (tile, 32-channel slab) into the ring of the MMA warp
+            // that owns the tile (tile parity)
             mbar_expect_tx(bfull, 9 * p.kchunks * B_TAP);
             for (int t = 0; t < 9; t++)
                 for (int kc = 0; kc < p.kchunks; kc++)
                     tma_load_3d(b_stat + (t * p.kchunks + kc) * B_TAP, &tmB, bfull, kc * KS, n0, g * 9 + t);
-            int it = 0;
-            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x) {
-                const int img = tile / p.tpi, tt = tile - img * p.tpi;
-                const int r_lo = (tt * BM) / p.P;                      // first image row with a position in this tile
-                for (int kc = 0; kc < p.kchunks; kc++, it++) {
-                    const int s = it % p.stages, round = it / p.stages;
-                    if (round > 0) mbar_wait(&empty[s], (round - 1) & 1);
+            int slot0 = 0, slot1 = 0, round0 = 0, round1 = 0;
+            long long t_wait = 0;
+            const long long t_begin = clock64();
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, tcount++) {
+                const int r = tcount & 1;
+                const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
+                const int r_lo = (int)__umulhi((unsigned)(tt * BM), p.mP);                      // first image row with a position in this tile
+                int slot = r ? slot1 : slot0, round = r ? round1 : round0;
+                for (int kc = 0; kc < p.kchunks; kc++) {
+                    const int s = r * FL_MAX_RING + slot;
+                    if (round > 0) {
+                        const long long t0 = clock64();
+                        mbar_wait(&empty[s], (round - 1) & 1);
+                        t_wait += clock64() - t0;
+                    }
                     mbar_expect_tx(&full[s], p.a_bytes);
-                    tma_load_4d(stage0 + s * p.stage_bytes, &tmA, &full[s], kc * KS, 0, r_lo - 1, g * p.B + img);
+                    tma_load_4d(stage0 + (r * p.spr + slot) * p.stage_bytes, &tmA, &full[s], kc * KS, 0, r_lo - 1, g * p.B + img);
+                    if (++slot == p.spr) { slot = 0; round++; }
                 }
+                if (r) { slot1 = slot; round1 = round; } else { slot0 = slot; round0 = round; }
             }
+            if (tracer) { p.trace[0] = t_wait; p.trace[1] = clock64() - t_begin; }
         }
-    } else if (warp == 1) {
-        // ---------------- MMA issuer: warp-uniform loop, one elected lane issues
+    } else if (warp <= 2) {
+        // ---------------- MMA issuers: warp 1 takes this CTA's even tiles (accumulator 0, ring 0), warp 2 the odd ones.
+        // The loop is warp-uniform and free of divisions per MMA; one elected lane issues.
+        const int mw = warp - 1;
         const uint32_t idesc = idesc_tf32(BN);
-        const uint32_t st0 = smem_u32(stage0), bstat_base = smem_u32(b_stat);
+        const uint32_t ring0 = smem_u32(stage0) + mw * p.spr * p.stage_bytes;
+        const uint32_t b_lo0 = (smem_u32(b_stat) & 0x3FFFF) >> 4;
+        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+        const uint32_t d_tmem = tmem + mw * BN;
+        uint64_t *rfull = full + mw * FL_MAX_RING, *rempty = empty + mw * FL_MAX_RING;
+        long long t_wacc = 0, t_wfull = 0, t_wb;
+        const long long t_begin = clock64();
         mbar_wait(bfull, 0);
-        int it = 0, tcount = 0;
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, tcount++) {
-            const int buf = tcount & 1, use = tcount >> 1;
-            const int img = tile / p.tpi, tt = tile - img * p.tpi;
-            const int r_lo = (tt * BM) / p.P;
+        t_wb = clock64() - t_begin;
+        int use = 0, s = 0, ph = 0;
+        for (int tile = blockIdx.x + mw * gridDim.x; tile < p.m_tiles; tile += 2 * gridDim.x, use++) {
+            const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
+            const int r_lo = (int)__umulhi((unsigned)(tt * BM), p.mP);
             const int q0 = tt * BM - r_lo * p.P + p.P;                 // box row of the tile's first position (box row 0 = image row r_lo-1, x=0)
-            if (use > 0) mbar_wait(&acc_empty[buf], (use - 1) & 1);
+            if (use > 0) {
+                const long long t0 = clock64();
+                mbar_wait(&acc_empty[mw], (use - 1) & 1);
+                t_wacc += clock64() - t0;
+            }
             tc_fence_after();
-            const uint32_t d_tmem = tmem + buf * BN;
             uint32_t acc = 0;
-            for (int kc = 0; kc < p.kchunks; kc++, it++) {
-                const int s = it % p.stages, round = it / p.stages;
-                mbar_wait(&full[s], round & 1);
+            for (int kc = 0; kc < p.kchunks; kc++) {
+                {
+                    const long long t0 = clock64();
+                    mbar_wait(&rfull[s], ph);
+                    t_wfull += clock64() - t0;
+                }
                 tc_fence_after();
-                const uint32_t sa = st0 + s * p.stage_bytes;
+                // descriptor low words (address >> 4); rows are 128 B = 8 units; row offset >= -1: the guard / the previous stage's slack
+                const uint32_t a_lo0 = (((ring0 + s * p.stage_bytes) & 0x3FFFF) >> 4) + (uint32_t)((q0 - p.P - 1) * 8);
+                const uint32_t b_lok = b_lo0 + (uint32_t)(kc * (B_TAP >> 4));
+                if (!(p.dbg & 4)) {
 #pragma unroll
-                for (int dyi = 0; dyi < 3; dyi++) {
+                    for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
-                    for (int dxi = 0; dxi < 3; dxi++) {
-                        const int rowoff = q0 + (dyi - 1) * p.P + (dxi - 1);       // >= -1: the guard / the previous stage's slack
-                        const uint64_t da = smem_desc_flat(sa + rowoff * (KS * 4), p.bo_mode);
-                        const uint64_t db = smem_desc_k_sw128(bstat_base + (p.tap[dyi][dxi] * p.kchunks + kc) * B_TAP);
-                        if (!(p.dbg & 4)) {
+                        for (int dxi = 0; dxi < 3; dxi++) {
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((dyi * p.P + dxi) * 8);
+                            const uint32_t b_lo = b_lok + (uint32_t)(p.tap[dyi][dxi] * p.kchunks * (B_TAP >> 4));
 #pragma unroll
                             for (int k = 0; k < KS / 8; k++) {
-                                if (elect_one()) tc_mma_tf32(d_tmem, da + 2 * k, db + 2 * k, idesc, (acc | k) ? 1u : 0u);
+                                const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2 * k | (1u << 16));
+                                const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * k | (1u << 16));
+                                if (elect_one()) tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
                             }
                         }
-                        acc = 1;
                     }
                 }
-                if (elect_one()) tc_commit(&empty[s]);
+                acc = 1;
+                if (elect_one()) tc_commit(&rempty[s]);
                 __syncwarp();
+                if (++s == p.spr) { s = 0; ph ^= 1; }
             }
-            if (elect_one()) tc_commit(&acc_full[buf]);
+            if (elect_one()) tc_commit(&acc_full[mw]);
             __syncwarp();
+        }
+        if (tracer && lane == 0) {
+            unsigned long long *tr = p.trace + 2 + 5 * mw;
+            tr[0] = t_wacc; tr[1] = t_wfull; tr[2] = clock64() - t_begin; tr[3] = use; tr[4] = t_wb;
         }
     } else {
-        // ---------------- epilogue warps 2..5; warp w may touch TMEM lanes 32*(w%4) .. +31 (= tile rows)
-        const int q = warp & 3;
+        // ---------------- epilogue warps 3..6 (set 0: even tiles, accumulator 0) and 7..10 (set 1); warp w may touch TMEM lanes
+        // 32*(w%4) .. +31 (= tile rows)
+        const int q = warp & 3, es = (warp - 3) >> 2;
         const int row = q * 32 + lane;
-        float *O = p.O + g * p.o_gs;
-        int tcount = 0;
-        for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, tcount++) {
-            const int buf = tcount & 1, use = tcount >> 1;
-            const int img = tile / p.tpi, tt = tile - img * p.tpi;
+        float *O = p.O + g * p.o_gs + p.o_coff + n0;
+        float *stg = (float *)(stg_base + (warp - 3) * FL_STG_BYTES);
+        const int HW = p.H * p.W;
+        long long t_wfull = 0, t_ld = 0, t_stage = 0, t_stat = 0, t_store = 0;
+        float c_sum[BN / 32], c_sq[BN / 32];                 // lane j: running sums of columns c0 + j over this warp's rows
+#pragma unroll
+        for (int c = 0; c < BN / 32; c++) { c_sum[c] = 0.f; c_sq[c] = 0.f; }
+        const long long t_begin = clock64();
+        int use = 0;
+        for (int tile = blockIdx.x + es * gridDim.x; tile < p.m_tiles; tile += 2 * gridDim.x, use++) {
+            const int buf = es;
+            const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
             const int pos = tt * BM + row;
-            const int y = pos / p.P, x = pos - y * p.P;
+            const int y = (int)__umulhi((unsigned)pos, p.mP), x = pos - y * p.P;
             const bool valid = x < p.W && y < p.H;                    // not the separator column, not past the image
-            mbar_wait(&acc_full[buf], use & 1);
-            tc_fence_after();
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
-                float v[32];
-                tc_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v);
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] += s_bias[c0 + j];
-                if (valid && !(p.dbg & 1)) {
-                    float *dst = O + ((long long)(img * p.H + y) * p.W + x) * p.ldo + p.o_coff + n0 + c0;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (p.stats && !(p.dbg & 2)) {
-                    // column sums over this warp's 32 rows: butterfly transpose-reduce (31 shuffles per quantity); lane j gets column c0+j
-                    float s[32], sq[32];
-#pragma unroll
-                    for (int j = 0; j < 32; j++) { s[j] = valid ? v[j] : 0.f; sq[j] = s[j] * s[j]; }
-#pragma unroll
-                    for (int w = 16; w >= 1; w >>= 1) {
-                        const bool up = lane & w;
-#pragma unroll
-                        for (int j = 0; j < w; j++) {
-                            float keep_s = up ? s[j + w] : s[j], send_s = up ? s[j] : s[j + w];
-                            float keep_q = up ? sq[j + w] : sq[j], send_q = up ? sq[j] : sq[j + w];
-                            s[j] = keep_s + __shfl_xor_sync(0xffffffffu, send_s, w);
-                            sq[j] = keep_q + __shfl_xor_sync(0xffffffffu, send_q, w);
-                        }
-                    }
-                    atomicAdd(&s_sum[c0 + lane], s[0]);
-                    atomicAdd(&s_sq[c0 + lane], sq[0]);
-                }
+            const int pix = img * HW + pos - y;                       // output pixel index: y * W + x = pos - y
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            {
+                const long long t0 = clock64();
+                mbar_wait(&acc_full[buf], use & 1);
+                t_wfull += clock64() - t0;
             }
+            tc_fence_after();
+            long long t1 = clock64();
+            float v[BN];
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) tc_ld32_nowait(tmem + ((uint32_t)(q * 32) << 16) + buf * BN + c0, v + c0);
+            tc_wait_ld();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&acc_empty[buf]);       // this warp has drained its quarter of the accumulator
+            if (lane == 0) mbar_arrive(&acc_empty[buf]);       // accumulator quarter is in registers: the MMA warp may reuse it
+            { const long long t2 = clock64(); t_ld += t2 - t1; t1 = t2; }
+#pragma unroll
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                // bias, then this warp's 32 x 32 block into the staging tile (rows of invalid positions as zeros)
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 b4 = *reinterpret_cast<const float4 *>(s_bias + c0 + j);
+                    float4 o;
+                    o.x = valid ? v[c0 + j] + b4.x : 0.f;
+                    o.y = valid ? v[c0 + j + 1] + b4.y : 0.f;
+                    o.z = valid ? v[c0 + j + 2] + b4.z : 0.f;
+                    o.w = valid ? v[c0 + j + 3] + b4.w : 0.f;
+                    *reinterpret_cast<float4 *>(stg + lane * FL_STG_LD + j) = o;
+                }
+                __syncwarp();
+                { const long long t2 = clock64(); t_stage += t2 - t1; t1 = t2; }
+                if (p.stats && !(p.dbg & 2)) {          // lane j sums column c0 + j over the 32 rows
+                    float s = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r++) {
+                        const float xv = stg[r * FL_STG_LD + lane];
+                        s += xv;
+                        sq = fmaf(xv, xv, sq);
+                    }
+                    c_sum[c0 / 32] += s;
+                    c_sq[c0 / 32] += sq;
+                }
+                { const long long t2 = clock64(); t_stat += t2 - t1; t1 = t2; }
+                if (!(p.dbg & 1)) {                      // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = 4 * i + (lane >> 3);
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + r * FL_STG_LD + 4 * (lane & 7));
+                        const int rp = __shfl_sync(0xffffffffu, pix, r);
+                        if ((vmask >> r) & 1) *reinterpret_cast<float4 *>(O + (long long)rp * p.ldo + c0 + 4 * (lane & 7)) = o;
+                    }
+                }
+                __syncwarp();
+                { const long long t2 = clock64(); t_store += t2 - t1; t1 = t2; }
+            }
+        }
+        if (tracer && threadIdx.x == 96) {
+            p.trace[12] = t_wfull; p.trace[13] = clock64() - t_begin; p.trace[14] = t_ld; p.trace[15] = t_stage; p.trace[16] = t_stat; p.trace[17] = t_store;
         }
         if (p.stats) {
-            asm volatile("bar.sync 1, 128;" ::: "memory");      // the four epilogue warps only
+#pragma unroll
+            for (int c = 0; c < BN / 32; c++) {
+                atomicAdd(&s_sum[c * 32 + lane], c_sum[c]);
+                atomicAdd(&s_sq[c * 32 + lane], c_sq[c]);
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");      // the eight epilogue warps only
             double *st = p.stats + g * p.stats_gs;
-            for (int i = threadIdx.x - 64; i < BN; i += 128) {
+            for (int i = threadIdx.x - 96; i < BN; i += 256) {
                 if (n0 + i < p.N) {
                     atomicAdd(&st[n0 + i], (double)s_sum[i]);
                     atomicAdd(&st[p.N + n0 + i], (double)s_sq[i]);
@@ -245,9 +324,9 @@ bool analyse_3x3(const VvTaps &t, FlatParams &fp) {
     return true;
 }
 
-inline int flat_bn_tile(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 32); }
+inline int flat_bn_tile(int N) { return N % 64 == 0 ? 64 : 32; }
 
-// 0: off; 1: descriptors carry the base offset (documented convention); 2: base offset left at 0
+// VECVAD_FLAT=0 keeps the net engine on the per-dx-box tiles (igemm_tc2.cu)
 int flat_mode() {
     static int v = -1;
     if (v < 0) {
@@ -266,6 +345,14 @@ int launch_flat(const CUtensorMap &tmA, const CUtensorMap &tmB, const FlatParams
     }
     k_igemm_flat<BN><<<grid, FL_THREADS, smem, st>>>(tmA, tmB, fp);
     VV_CKL();
+    if (fp.trace) {      // debugging aid: synchronous
+        unsigned long long h[18];
+        VV_CK(cudaStreamSynchronize(st));
+        VV_CK(cudaMemcpy(h, fp.trace, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "[flat trace BN=%d Kt=%d] producer: wait_empty %llu of %llu | mma0 (%llu tiles): wait_weights %llu wait_acc %llu wait_full %llu of %llu | "
+                "mma1 (%llu tiles): wait_acc %llu wait_full %llu of %llu | epilogue: wait_acc_full %llu of %llu cycles (ld %llu stage %llu stats %llu stores %llu)\n",
+                BN, fp.kchunks * KS, h[0], h[1], h[5], h[6], h[2], h[3], h[4], h[10], h[7], h[8], h[9], h[12], h[13], h[14], h[15], h[16], h[17]);
+    }
     return 0;
 }
 
@@ -283,7 +370,7 @@ bool vv_igemm_flat_shape_ok(const VvIGemm &p) {
 // used by the net engine: only where the flattened tiles beat the per-dx boxes (full-width rows, i.e. W >= 32)
 bool vv_igemm_flat_supported(const VvIGemm &p) { return flat_mode() != 0 && p.W >= 32 && vv_igemm_flat_shape_ok(p); }
 
-int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st, int bo_override) {
+int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     EncodeTiledFn enc = encode_fn();
     FlatParams fp;
     memset(&fp, 0, sizeof(fp));
@@ -294,10 +381,9 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st, int bo_override) {
         if (dbg < 0) { const char *e = getenv("VECVAD_DBG_TC2"); dbg = e ? atoi(e) : 0; }
         fp.dbg = dbg;
     }
-    const int mode = bo_override ? bo_override : (flat_mode() ? flat_mode() : 1);
-    fp.bo_mode = mode == 1 ? 1 : 0;
     fp.B = p.B; fp.H = p.H; fp.W = p.W; fp.G = p.G;
     fp.P = p.W + 1; fp.L = p.H * fp.P; fp.tpi = (fp.L + BM - 1) / BM; fp.m_tiles = fp.tpi * p.B;
+    fp.mP = (unsigned)((0x100000000ULL + fp.P - 1) / fp.P); fp.mtpi = (unsigned)((0x100000000ULL + fp.tpi - 1) / fp.tpi);
     fp.rows = (BM - 1) / fp.P + 4;                    // rows holding 128 consecutive positions (<= 127/P + 2) + one halo row either side
     fp.kchunks = p.Kt / KS;
     fp.a_bytes = fp.rows * fp.P * KS * 4;
@@ -306,17 +392,24 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st, int bo_override) {
     fp.bias = p.bias; fp.bias_gs = p.bias_gs; fp.stats = p.stats; fp.stats_gs = p.stats_gs;
     const int bn_tile = flat_bn_tile(p.N);
     const int b_all = 9 * fp.kchunks * bn_tile * KS * 4;
-    const int fixed = 1024 /*alignment*/ + FL_GUARD + 256 /*barriers*/ + 3 * bn_tile * 4;
-    int stages = (FL_SMEM_MAX - fixed - b_all) / fp.stage_bytes;
+    const int fixed = 1024 /*alignment*/ + FL_GUARD + 8 * FL_STG_BYTES + 256 /*barriers*/ + 3 * bn_tile * 4;
+    int spr = (FL_SMEM_MAX - fixed - b_all) / (2 * fp.stage_bytes);
     {
         static int cap = -1;
-        if (cap < 0) { const char *e = getenv("VECVAD_FLAT_STAGES"); cap = e ? atoi(e) : 3; }
-        if (cap >= 2 && stages > cap) stages = cap;
+        if (cap < 0) { const char *e = getenv("VECVAD_FLAT_STAGES"); cap = e ? atoi(e) : 2; }
+        if (cap >= 1 && spr > cap) spr = cap;
     }
-    if (stages > 8) stages = 8;
-    VV_REQUIRE(stages >= 2, "igemm_flat: tile does not fit in shared memory");
-    fp.stages = stages;
-    const int smem = fixed + b_all + stages * fp.stage_bytes;
+    if (spr > FL_MAX_RING) spr = FL_MAX_RING;
+    VV_REQUIRE(spr >= 1, "igemm_flat: tile does not fit in shared memory");
+    fp.spr = spr;
+    {
+        static int tr = -1;
+        static unsigned long long *buf = nullptr;
+        if (tr < 0) { const char *e = getenv("VECVAD_FLAT_TRACE"); tr = e ? atoi(e) : 0; }
+        if (tr && !buf) VV_CK(cudaMalloc(&buf, 32 * sizeof(unsigned long long)));
+        fp.trace = tr ? buf : nullptr;
+    }
+    const int smem = fixed + b_all + 2 * spr * fp.stage_bytes;
 
     const CUtensorMapDataType dt = tmap_dtype();
     alignas(64) CUtensorMap tmA, tmB;
@@ -344,7 +437,6 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st, int bo_override) {
     if (gx < 1) gx = 1;
     if (gx > fp.m_tiles) gx = fp.m_tiles;
     dim3 grid(gx, n_tiles, p.G);
-    if (bn_tile == 128) return launch_flat<128>(tmA, tmB, fp, grid, smem, st);
     if (bn_tile == 64) return launch_flat<64>(tmA, tmB, fp, grid, smem, st);
     return launch_flat<32>(tmA, tmB, fp, grid, smem, st);
 }
