@@ -1,4 +1,5 @@
-"""Single-op parity: the 3x3 pad-1 convolution tiles (fp32 SIMT and tcgen05 tf32) through the C ABI entry point
+"""Single-op parity: the 3x3 pad-1 convolution tiles (fp32 SIMT and tcgen05 tf32; use_tc 1 = per-tap tiles, 2 = persistent
+per-dx-box tiles, 3 = flattened-sequence tiles) through the C ABI entry point
 vecvad_conv3x3_forward, against torch.nn.functional.conv2d in float64 on the CPU (the same op the reference calls:
 model/unet.py:10,13).  Tolerances: fp32 tiles 1e-5 of the output range; tf32 tiles 2e-3 (10-bit mantissa operands)."""
 import ctypes as C
@@ -47,6 +48,32 @@ def test_conv3x3_forward(shape, use_tc):
     s = stats.cpu().numpy()
     np.testing.assert_allclose(s[:cout], want.sum(dim=(0, 1, 2)).numpy(), rtol=0, atol=tol * want.abs().sum(dim=(0, 1, 2)).max().item())
     np.testing.assert_allclose(s[cout:], (want ** 2).sum(dim=(0, 1, 2)).numpy(), rtol=5 * tol)
+
+
+# flattened-sequence tiles (igemm_flat.cu): any H, W in the tcgen05 tile set with all nine weight tiles resident; ragged batches,
+# images whose positions do not fill the last 128-row tile, one and two 32-channel slabs, 32 and 64 output channels
+FLAT_SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (2, 32, 32, 32, 64), (130, 32, 32, 32, 32), (2, 64, 64, 32, 32), (5, 16, 16, 32, 64),
+               (1, 32, 32, 32, 32), (7, 8, 8, 32, 32), (3, 16, 16, 64, 32), (37, 32, 32, 64, 32)]
+
+
+@pytest.mark.parametrize('shape', FLAT_SHAPES)
+def test_conv3x3_forward_flat(shape):
+    b, h, wd, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + 7)
+    x = torch.randn(b, cin, h, wd, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).contiguous()
+    xn = x.permute(0, 2, 3, 1).contiguous().cuda()
+    got, stats = conv3x3(xn, w.cuda(), bias.cuda(), 3)
+    err = (got.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-3, err
+    s = stats.cpu().numpy()
+    np.testing.assert_allclose(s[:cout], want.sum(dim=(0, 1, 2)).numpy(), rtol=0, atol=2e-3 * want.abs().sum(dim=(0, 1, 2)).max().item())
+    np.testing.assert_allclose(s[cout:], (want ** 2).sum(dim=(0, 1, 2)).numpy(), rtol=1e-2)
+    # same operands, same tf32 rounding, fp32 accumulation in a different order: the two tcgen05 paths agree far below tf32 error
+    ref2, _ = conv3x3(xn, w.cuda(), bias.cuda(), 2)
+    assert (got - ref2).abs().max().item() <= 2e-5 * want.abs().max().item()
 
 
 def test_tf32_error_is_unbiased():
