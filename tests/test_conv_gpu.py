@@ -1,5 +1,5 @@
 """Single-op parity: the 3x3 pad-1 convolution tiles (fp32 SIMT and tcgen05 tf32; use_tc 1 = per-tap tiles, 2 = persistent
-per-dx-box tiles, 3 = flattened-sequence tiles) through the C ABI entry point
+per-dx-box tiles, 3 = flattened-sequence tiles, 4 = pair tiles) through the C ABI entry point
 vecvad_conv3x3_forward, against torch.nn.functional.conv2d in float64 on the CPU (the same op the reference calls:
 model/unet.py:10,13).  Tolerances: fp32 tiles 1e-5 of the output range; tf32 tiles 2e-3 (10-bit mantissa operands)."""
 import ctypes as C
@@ -31,7 +31,7 @@ SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (5, 16, 16, 32, 64), (3, 8, 
           (1, 8, 8, 256, 128), (2, 16, 16, 128, 64)]
 
 
-@pytest.mark.parametrize('use_tc', [0, 1, 2])
+@pytest.mark.parametrize('use_tc', [0, 1, 2, 4])
 @pytest.mark.parametrize('shape', SHAPES + [(130, 32, 32, 32, 32), (70, 16, 16, 64, 64), (150, 4, 4, 256, 256)])
 def test_conv3x3_forward(shape, use_tc):
     b, h, wd, cin, cout = shape

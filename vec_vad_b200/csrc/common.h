@@ -90,6 +90,9 @@ int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st);
 bool vv_igemm_flat_shape_ok(const VvIGemm &p);
 bool vv_igemm_flat_supported(const VvIGemm &p);
 int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st);
+// pair variant of the persistent tiles (igemm_tc3.cu): two pixel tiles share every weight tile, two MMA warps, two epilogue sets
+bool vv_igemm_tc3_supported(const VvIGemm &p);
+int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st);
 bool vv_wgrad_tc_supported(const VvWGrad &p);
 // tap-reuse variant (wgrad_tc2.cu)
 bool vv_wgrad_tc2_supported(const VvWGrad &p);

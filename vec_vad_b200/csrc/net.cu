@@ -144,6 +144,7 @@ int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st, int k_real
     const bool tc = n->cfg.use_tensor_cores && vv_igemm_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_igemm_flat_supported(p)) return vv_launch_igemm_flat(p, st);
+    if (tc && vv_igemm_tc3_supported(p)) return vv_launch_igemm_tc3(p, st);
     if (tc) return vv_igemm_tc2_supported(p) ? vv_launch_igemm_tc2(p, st) : vv_launch_igemm_tc(p, st);
     return vv_launch_igemm_simt(p, st);
 }
@@ -633,6 +634,10 @@ extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w
     p.O = out; p.ldo = cout; p.bias = bias; p.stats = stats; p.G = 1;
     if (use_tc) {
         VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_forward: shape not supported by the tcgen05 path");
+        if (use_tc == 4) {       // pair tiles
+            VV_REQUIRE(vv_igemm_tc3_supported(p), "conv3x3_forward: shape not supported by the pair tcgen05 path");
+            return vv_launch_igemm_tc3(p, st);
+        }
         if (use_tc == 3) {       // flattened-sequence tiles
             VV_REQUIRE(vv_igemm_flat_shape_ok(p), "conv3x3_forward: shape not supported by the flattened tcgen05 path");
             return vv_launch_igemm_flat(p, st);
