@@ -88,8 +88,13 @@ def test_tf32_error_is_unbiased():
     assert abs(rel.mean().item()) < 1e-4, rel.mean().item()
 
 
-@pytest.mark.parametrize('use_tc', [0, 1, 2])
-@pytest.mark.parametrize('shape', SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32), (130, 32, 32, 32, 32), (3, 8, 8, 32, 64)])
+# flattened-sequence weight-gradient tiles (wgrad_flat.cu, use_tc 3): all nine taps from one MMA per K-step
+WGRAD_FLAT_SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (130, 32, 32, 32, 32), (2, 32, 32, 32, 64), (2, 64, 64, 32, 32), (5, 16, 16, 32, 32),
+                     (1, 32, 32, 32, 32), (37, 8, 8, 64, 32)]
+
+
+@pytest.mark.parametrize('use_tc,shape', [(t, s) for t in (0, 1, 2) for s in SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32), (130, 32, 32, 32, 32),
+                                                                                     (3, 8, 8, 32, 64)]] + [(3, s) for s in WGRAD_FLAT_SHAPES])
 def test_conv3x3_wgrad(shape, use_tc):
     """dW of the convolution = autograd of conv2d (what loss.backward() computes in train.py:401)."""
     b, h, wd, cin, cout = shape

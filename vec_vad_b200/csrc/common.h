@@ -94,6 +94,10 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st);
 bool vv_igemm_tc3_supported(const VvIGemm &p);
 int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st);
 bool vv_wgrad_tc_supported(const VvWGrad &p);
+// flattened-sequence weight-gradient tiles (wgrad_flat.cu): one MMA per K-step covers all nine taps
+bool vv_wgrad_flat_shape_ok(const VvWGrad &p);
+bool vv_wgrad_flat_supported(const VvWGrad &p);
+int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st);
 // tap-reuse variant (wgrad_tc2.cu)
 bool vv_wgrad_tc2_supported(const VvWGrad &p);
 int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st);

@@ -151,6 +151,7 @@ int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st, int k_real
 int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
     const bool tc = n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
+    if (tc && vv_wgrad_flat_supported(p)) return vv_launch_wgrad_flat(p, st);
     if (tc) return vv_wgrad_tc2_supported(p) ? vv_launch_wgrad_tc2(p, st) : vv_launch_wgrad_tc(p, st);
     return vv_launch_wgrad_simt(p, st);
 }
@@ -666,7 +667,8 @@ extern "C" int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *gra
     if (use_tc) {
         VV_REQUIRE(vv_wgrad_tc_supported(w), "conv3x3_wgrad: shape not supported by the tcgen05 path");
         if (use_tc == 2) VV_REQUIRE(vv_wgrad_tc2_supported(w), "conv3x3_wgrad: shape not supported by the tap-reuse tcgen05 path");
-        r = use_tc == 2 ? vv_launch_wgrad_tc2(w, st) : vv_launch_wgrad_tc(w, st);
+        if (use_tc == 3) VV_REQUIRE(vv_wgrad_flat_shape_ok(w), "conv3x3_wgrad: shape not supported by the flattened tcgen05 path");
+        r = use_tc == 3 ? vv_launch_wgrad_flat(w, st) : (use_tc == 2 ? vv_launch_wgrad_tc2(w, st) : vv_launch_wgrad_tc(w, st));
     } else {
         r = vv_launch_wgrad_simt(w, st);
     }
