@@ -330,10 +330,21 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
             if (r) return r;
         }
     }
+    // transposed-conv weights are first needed a third of the way into the forward: re-lay them out on the side stream meanwhile
+    cudaStream_t sP = n->use_side ? n->wg_stream : st;
+    cudaEvent_t ct_ready = nullptr;
+    if (n->use_side) {
+        VV_CK(cudaEventRecord(n->ev[VV_NEV - 1], st));
+        VV_CK(cudaStreamWaitEvent(sP, n->ev[VV_NEV - 1], 0));
+    }
     for (int k = 0; k < NT; k++) {
         int r = vv_prep_ct_w(n->params, n->slot, c.slot_param_stride, c.up_w[k], c.up_b[k], n->tCi[k], n->tCo[k], n->tWf[k],
-                             16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->tvec[k], n->tCo[k], G, st);
+                             16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->tvec[k], n->tCo[k], G, sP);
         if (r) return r;
+    }
+    if (n->use_side) {
+        ct_ready = n->ev[VV_NEV - 2];
+        VV_CK(cudaEventRecord(ct_ready, sP));
     }
     if (training) VV_CK(cudaMemsetAsync(n->zero_fwd, 0, n->zero_fwd_bytes, st));
     // 2. the erased-frame inputs of every UNet
@@ -387,6 +398,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     int r;
     for (int u = 0; u < 8; u++) if ((r = conv_unit(u))) return r;
     for (int k = 0; k < 3; k++) {
+        if (k == 0 && ct_ready) VV_CK(cudaStreamWaitEvent(st, ct_ready, 0));
         if ((r = convT(k))) return r;
         if ((r = conv_unit(8 + 2 * k))) return r;
         if ((r = conv_unit(9 + 2 * k))) return r;
@@ -440,8 +452,10 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     for (int g = 0; g < G; g++)
         VV_CK(cudaMemsetAsync(n->grads + n->slot.v[g] * c.slot_param_stride, 0, c.slot_param_stride * sizeof(float), st));
 
-    // ---- output conv
-    {
+    // ---- output conv.  With the loss gradient staged by the forward (no external gradients) its backward is folded into the BatchNorm
+    // backward of the last conv unit (VvBnBwd::dout): dU is never written or read.
+    const bool fuse_out = !ext;
+    if (!fuse_out) {
         VvOutBwd q;
         memset(&q, 0, sizeof(q));
         q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F;
@@ -500,6 +514,9 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         q.save = n->save[u]; q.save_gs = 4LL * N;
         q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
         q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.gamma_off = c.bn_w[u]; q.beta_off = c.bn_b[u];
+        if (fuse_out && u == NU - 1) {
+            q.dout = n->DOUT; q.params = n->params; q.ow_off = c.out_w; q.ob_off = c.out_b; q.out_channels = n->outc;
+        }
         int rr;
         if ((rr = before_write(dz_buf))) return rr;
         {

@@ -243,7 +243,22 @@ __global__ void k_bn_apply(const VvBnApply p) {
         for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
             const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c4 * 4);
             const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c4 * 4);
-            for (int m = blockIdx.x * blockDim.y + threadIdx.y; m < p.M; m += gridDim.x * blockDim.y) {
+            // four independent 16-byte loads in flight per thread: these passes are HBM-bound
+            const int stride = gridDim.x * blockDim.y;
+            int m = blockIdx.x * blockDim.y + threadIdx.y;
+            for (; m + 3 * stride < p.M; m += 4 * stride) {
+                float4 z[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float4 y;
+                    y.x = fmaxf(fmaf(z[u].x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z[u].y, sc.y, sh.y), 0.f);
+                    y.z = fmaxf(fmaf(z[u].z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z[u].w, sc.w, sh.w), 0.f);
+                    *reinterpret_cast<float4 *>(Y + (long long)(m + u * stride) * p.ldy + p.y_coff + c4 * 4) = y;
+                }
+            }
+            for (; m < p.M; m += stride) {
                 float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
                 float4 y;
                 y.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
@@ -294,9 +309,7 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
         const float4 mu = *reinterpret_cast<const float4 *>(sv + 2 * p.C + c4 * 4);
         const float4 is = *reinterpret_cast<const float4 *>(sv + 3 * p.C + c4 * 4);
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        for (int m = blockIdx.x * blockDim.y + threadIdx.y; m < p.M; m += gridDim.x * blockDim.y) {
-            float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-            float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
+        auto acc = [&](const float4 &z, const float4 &d) {
             float dx = fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
             float dy = fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
             float dz = fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
@@ -304,6 +317,71 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
             s.x += dx; s.y += dy; s.z += dz; s.w += dw;
             q.x += dx * (z.x - mu.x) * is.x; q.y += dy * (z.y - mu.y) * is.y;
             q.z += dz * (z.z - mu.z) * is.z; q.w += dw * (z.w - mu.w) * is.w;
+        };
+        const int stride = gridDim.x * blockDim.y;
+        int m = blockIdx.x * blockDim.y + threadIdx.y;
+        if (!p.dout) {
+            for (; m + 3 * stride < p.M; m += 4 * stride) {      // eight independent 16-byte loads in flight per thread
+                float4 z[4], d[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                    d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) acc(z[u], d[u]);
+            }
+            for (; m < p.M; m += stride) {
+                float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
+                float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
+                acc(z, d);
+            }
+        } else {
+            // fused 1x1 output conv backward: dY from the staged loss gradient; dW_out[j][c] += dout[m][j] * relu(bn(z))[m][c]
+            const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
+            const int oc = p.out_channels.v[g];
+            float4 w[3], a[3];
+            float db[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                w[j] = j < oc ? *reinterpret_cast<const float4 *>(P + p.ow_off + j * p.C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+                a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            const float4 *DO = reinterpret_cast<const float4 *>(p.dout) + (long long)g * p.M;
+            auto one = [&](const float4 &z, const float4 &dd) {
+                const float dj[3] = {dd.x, dd.y, dd.z};
+                float4 d, u;
+                d.x = dd.x * w[0].x + dd.y * w[1].x + dd.z * w[2].x; d.y = dd.x * w[0].y + dd.y * w[1].y + dd.z * w[2].y;
+                d.z = dd.x * w[0].z + dd.y * w[1].z + dd.z * w[2].z; d.w = dd.x * w[0].w + dd.y * w[1].w + dd.z * w[2].w;
+                u.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); u.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+                u.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); u.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+#pragma unroll
+                for (int j = 0; j < 3; j++) {
+                    a[j].x = fmaf(dj[j], u.x, a[j].x); a[j].y = fmaf(dj[j], u.y, a[j].y);
+                    a[j].z = fmaf(dj[j], u.z, a[j].z); a[j].w = fmaf(dj[j], u.w, a[j].w);
+                    db[j] += dj[j];
+                }
+                acc(z, d);
+            };
+            for (; m + 3 * stride < p.M; m += 4 * stride) {
+                float4 z[4], dd[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                    dd[u] = DO[m + u * stride];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) one(z[u], dd[u]);
+            }
+            for (; m < p.M; m += stride) {
+                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
+                one(z, DO[m]);
+            }
+            // block-level reduction of the 1x1 conv's gradients: [3][rows][C] + [rows][4] behind the two BN partial arrays
+            float *pw = sm + 2 * blockDim.y * p.C, *pb = pw + 3 * blockDim.y * p.C;
+#pragma unroll
+            for (int j = 0; j < 3; j++) *reinterpret_cast<float4 *>(pw + (j * blockDim.y + threadIdx.y) * p.C + c4 * 4) = a[j];
+            if (c4 == 0) { pb[threadIdx.y * 4 + 0] = db[0]; pb[threadIdx.y * 4 + 1] = db[1]; pb[threadIdx.y * 4 + 2] = db[2]; }
         }
         *reinterpret_cast<float4 *>(ps + threadIdx.y * p.C + c4 * 4) = s;
         *reinterpret_cast<float4 *>(pq + threadIdx.y * p.C + c4 * 4) = q;
@@ -311,6 +389,22 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
     __syncthreads();
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthr = blockDim.x * blockDim.y;
+    if (p.dout) {
+        const int oc = p.out_channels.v[g];
+        float *Gp = p.grads + p.slot.v[g] * p.slot_param_stride;
+        const float *pw = sm + 2 * blockDim.y * p.C, *pb = pw + 3 * blockDim.y * p.C;
+        for (int i = tid; i < oc * p.C; i += nthr) {
+            const int j = i / p.C, c = i - j * p.C;
+            float a = 0.f;
+            for (int r = 0; r < blockDim.y; r++) a += pw[(j * blockDim.y + r) * p.C + c];
+            atomicAdd(Gp + p.ow_off + i, a);
+        }
+        if (tid < oc) {
+            float a = 0.f;
+            for (int r = 0; r < blockDim.y; r++) a += pb[r * 4 + tid];
+            atomicAdd(Gp + p.ob_off + tid, a);
+        }
+    }
     double *sums = p.sums + g * p.sums_gs;
     for (int c = tid; c < p.C; c += nthr) {
         float a = 0.f, b = 0.f;
@@ -351,15 +445,59 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         const float4 is = *reinterpret_cast<const float4 *>(sv + 3 * p.C + c4 * 4);
         const float4 a1 = *reinterpret_cast<const float4 *>(k1 + c4 * 4);
         const float4 a2 = *reinterpret_cast<const float4 *>(k2 + c4 * 4);
-        for (int m = blockIdx.x * blockDim.y + threadIdx.y; m < p.M; m += gridDim.x * blockDim.y) {
-            float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-            float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
+        auto dz_of = [&](const float4 &z, const float4 &d) {
             float4 o;
             o.x = sc.x * ((fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f) - a1.x - (z.x - mu.x) * is.x * a2.x);
             o.y = sc.y * ((fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f) - a1.y - (z.y - mu.y) * is.y * a2.y);
             o.z = sc.z * ((fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f) - a1.z - (z.z - mu.z) * is.z * a2.z);
             o.w = sc.w * ((fmaf(z.w, sc.w, sh.w) > 0.f ? d.w : 0.f) - a1.w - (z.w - mu.w) * is.w * a2.w);
-            *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = o;
+            return o;
+        };
+        const int stride = gridDim.x * blockDim.y;
+        int m = blockIdx.x * blockDim.y + threadIdx.y;
+        if (p.dout) {                                        // fused 1x1 output conv backward: dY formed from the staged loss gradient
+            const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
+            const int oc = p.out_channels.v[g];
+            float4 w[3];
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+                w[j] = j < oc ? *reinterpret_cast<const float4 *>(P + p.ow_off + j * p.C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 *DO = reinterpret_cast<const float4 *>(p.dout) + (long long)g * p.M;
+            auto dy_of = [&](const float4 &dd) {
+                float4 d;
+                d.x = dd.x * w[0].x + dd.y * w[1].x + dd.z * w[2].x; d.y = dd.x * w[0].y + dd.y * w[1].y + dd.z * w[2].y;
+                d.z = dd.x * w[0].z + dd.y * w[1].z + dd.z * w[2].z; d.w = dd.x * w[0].w + dd.y * w[1].w + dd.z * w[2].w;
+                return d;
+            };
+            for (; m + 3 * stride < p.M; m += 4 * stride) {
+                float4 z[4], dd[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                    dd[u] = DO[m + u * stride];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], dy_of(dd[u]));
+            }
+            for (; m < p.M; m += stride) {
+                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
+                *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = dz_of(z, dy_of(DO[m]));
+            }
+        }
+        for (; m + stride < p.M; m += 2 * stride) {          // four independent 16-byte loads in flight per thread
+            float4 z[2], d[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], d[u]);
+        }
+        for (; m < p.M; m += stride) {
+            float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
+            float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
+            *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = dz_of(z, d);
         }
     }
 }
@@ -413,7 +551,16 @@ __global__ void k_colsum(const float *__restrict__ D, long long d_gs, int ld, in
     const int cq = C >> 2;
     for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
         float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int m = blockIdx.x * blockDim.y + threadIdx.y; m < M; m += gridDim.x * blockDim.y) {
+        const int stride = gridDim.x * blockDim.y;
+        int m = blockIdx.x * blockDim.y + threadIdx.y;
+        for (; m + 3 * stride < M; m += 4 * stride) {
+            float4 d[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) d[u] = *reinterpret_cast<const float4 *>(D + g * d_gs + (long long)(m + u * stride) * ld + coff + c4 * 4);
+#pragma unroll
+            for (int u = 0; u < 4; u++) { s.x += d[u].x; s.y += d[u].y; s.z += d[u].z; s.w += d[u].w; }
+        }
+        for (; m < M; m += stride) {
             float4 d = *reinterpret_cast<const float4 *>(D + g * d_gs + (long long)m * ld + coff + c4 * 4);
             s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
         }
@@ -772,7 +919,8 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     int gx = vv_cdiv(p.M, rows * 8);
     if (gx > 148 * 4) gx = 148 * 4;
     if (gx < 1) gx = 1;
-    k_bn_bwd_reduce<<<dim3(gx, G), blk, 2 * rows * p.C * sizeof(float), st>>>(p);
+    if (p.dout) VV_REQUIRE(p.C % 4 == 0 && p.params && p.grads, "bn_bwd: fused output-conv backward needs params / grads");
+    k_bn_bwd_reduce<<<dim3(gx, G), blk, ((p.dout ? 5 : 2) * rows * p.C + (p.dout ? 4 * rows : 0)) * sizeof(float), st>>>(p);
     VV_CKL();
     int gx2 = vv_cdiv(p.M, rows * 4);
     if (gx2 > 148 * 8) gx2 = 148 * 8;

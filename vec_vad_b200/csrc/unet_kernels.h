@@ -29,6 +29,9 @@ struct VvBnBwd {
     const float *save;   long long save_gs;
     double *sums;        long long sums_gs;               // [G][2][C], pre-zeroed
     float *grads;        VvIntG slot;  long long slot_param_stride, gamma_off, beta_off;
+    // fused 1x1 output conv backward (last unit of the UNet, C == features_root): dY[m][c] = sum_j dout[m][j] * w_out[j][c] is formed on
+    // the fly from the staged loss gradient instead of being read, and the 1x1 conv's own weight / bias gradients are reduced here
+    const float *dout;   const float *params;  long long ow_off, ob_off;  VvIntG out_channels;      // dout [G][M][4]; NULL = plain mode
 };
 
 struct VvOutFwd {
