@@ -25,8 +25,9 @@ if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
 # DRAM traffic of the contraction kernel classes over ONE train step (batch 128, 5raw1of), from the ncu pass whose raw output is
-# committed as profiles/r01_tc_v3_step_metrics.csv (dram__bytes_read.sum + dram__bytes_write.sum summed over the class's launches)
-NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': (1.879e9 + 0.591e9, 33), 'wgrad_tcgen05': (1.920e9 + 0.002e9, 17)}
+# committed as profiles/r01_v5_step_metrics.csv, tabulated in profiles/r01_v5_step.txt (dram__bytes_read.sum + dram__bytes_write.sum
+# summed over the class's launches: k_igemm_flat + k_igemm_tc3, k_wgrad_flat + k_wgrad_tc2)
+NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': (1.876e9 + 0.604e9, 33), 'wgrad_tcgen05': (1.924e9 + 0.002e9, 17)}
 
 # algorithmic FLOPs of one train step per STC (fwd + dgrad + wgrad of every conv; SURVEY.md section 8a / BASELINE.md section 2)
 FLOPS_PER_STC = {'net4': 5.524e9, 'full': 9.206e9, 'noflow': 4.604e9}
@@ -221,7 +222,7 @@ def run_ours(args):
                 'roofline': {'bound': 'tensor', 'kernel': dom, 'achieved': dom_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dom_tf / peak,
                              'traffic': (NCU_DRAM_BYTES_PER_STEP[dom][0] / NCU_DRAM_BYTES_PER_STEP[dom][1]
                                          if (dom in NCU_DRAM_BYTES_PER_STEP and args.net == 'net4' and B == 128) else None),
-                             'traffic_note': 'mean DRAM bytes per launch of this kernel class (ncu, profiles/r01_tc_v3_step_metrics.csv)',
+                             'traffic_note': 'mean DRAM bytes per launch of this kernel class (ncu, profiles/r01_v5_step_metrics.csv)',
                              'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / ms_dev,
                              'peak_tf32': peak / 2 if tf32 else None, 'frac_of_tf32_peak': dom_tf / (peak / 2) if tf32 else None,
                              'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak,

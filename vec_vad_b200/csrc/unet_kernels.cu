@@ -295,6 +295,7 @@ __global__ void k_bn_apply(const VvBnApply p) {
 
 // ---- BatchNorm backward through ReLU.  dzhat = dy * [z*scale+shift > 0];  xhat = (z-mean)*invstd
 //      pass 1: sums[g][0][c] = sum dzhat, sums[g][1][c] = sum dzhat*xhat  (double atomics)
+template <bool FUSED>
 __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
     extern __shared__ float sm[];   // [2][blockDim.y][C] partials
     const int g = blockIdx.y;
@@ -320,7 +321,7 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
         };
         const int stride = gridDim.x * blockDim.y;
         int m = blockIdx.x * blockDim.y + threadIdx.y;
-        if (!p.dout) {
+        if (!FUSED) {
             for (; m + 3 * stride < p.M; m += 4 * stride) {      // eight independent 16-byte loads in flight per thread
                 float4 z[4], d[4];
 #pragma unroll
@@ -363,15 +364,15 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
                 }
                 acc(z, d);
             };
-            for (; m + 3 * stride < p.M; m += 4 * stride) {
-                float4 z[4], dd[4];
+            for (; m + stride < p.M; m += 2 * stride) {
+                float4 z[2], dd[2];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 2; u++) {
                     z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
                     dd[u] = DO[m + u * stride];
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) one(z[u], dd[u]);
+                for (int u = 0; u < 2; u++) one(z[u], dd[u]);
             }
             for (; m < p.M; m += stride) {
                 const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
@@ -389,7 +390,7 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
     __syncthreads();
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthr = blockDim.x * blockDim.y;
-    if (p.dout) {
+    if (FUSED) {
         const int oc = p.out_channels.v[g];
         float *Gp = p.grads + p.slot.v[g] * p.slot_param_stride;
         const float *pw = sm + 2 * blockDim.y * p.C, *pb = pw + 3 * blockDim.y * p.C;
@@ -415,6 +416,7 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
 }
 
 //      pass 2: dz = scale * (dzhat - mean(dzhat) - xhat * mean(dzhat*xhat));  d gamma = sum dzhat*xhat, d beta = sum dzhat
+template <bool FUSED>
 __global__ void k_bn_bwd_apply(const VvBnBwd p) {
     extern __shared__ float sm[];   // k1[C], k2[C]
     const int g = blockIdx.y;
@@ -455,7 +457,7 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         };
         const int stride = gridDim.x * blockDim.y;
         int m = blockIdx.x * blockDim.y + threadIdx.y;
-        if (p.dout) {                                        // fused 1x1 output conv backward: dY formed from the staged loss gradient
+        if (FUSED) {                                         // fused 1x1 output conv backward: dY formed from the staged loss gradient
             const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
             const int oc = p.out_channels.v[g];
             float4 w[3];
@@ -469,30 +471,20 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
                 d.z = dd.x * w[0].z + dd.y * w[1].z + dd.z * w[2].z; d.w = dd.x * w[0].w + dd.y * w[1].w + dd.z * w[2].w;
                 return d;
             };
-            for (; m + 3 * stride < p.M; m += 4 * stride) {
-                float4 z[4], dd[4];
+            for (; m + stride < p.M; m += 2 * stride) {
+                float4 z[2], dd[2];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < 2; u++) {
                     z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
                     dd[u] = DO[m + u * stride];
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], dy_of(dd[u]));
+                for (int u = 0; u < 2; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], dy_of(dd[u]));
             }
             for (; m < p.M; m += stride) {
                 const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
                 *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = dz_of(z, dy_of(DO[m]));
             }
-        }
-        for (; m + stride < p.M; m += 2 * stride) {          // four independent 16-byte loads in flight per thread
-            float4 z[2], d[2];
-#pragma unroll
-            for (int u = 0; u < 2; u++) {
-                z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
-                d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
-            }
-#pragma unroll
-            for (int u = 0; u < 2; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], d[u]);
         }
         for (; m < p.M; m += stride) {
             float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
@@ -920,12 +912,14 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     if (gx > 148 * 4) gx = 148 * 4;
     if (gx < 1) gx = 1;
     if (p.dout) VV_REQUIRE(p.C % 4 == 0 && p.params && p.grads, "bn_bwd: fused output-conv backward needs params / grads");
-    k_bn_bwd_reduce<<<dim3(gx, G), blk, ((p.dout ? 5 : 2) * rows * p.C + (p.dout ? 4 * rows : 0)) * sizeof(float), st>>>(p);
+    if (p.dout) k_bn_bwd_reduce<true><<<dim3(gx, G), blk, (5 * rows * p.C + 4 * rows) * sizeof(float), st>>>(p);
+    else k_bn_bwd_reduce<false><<<dim3(gx, G), blk, 2 * rows * p.C * sizeof(float), st>>>(p);
     VV_CKL();
     int gx2 = vv_cdiv(p.M, rows * 4);
     if (gx2 > 148 * 8) gx2 = 148 * 8;
     if (gx2 < 1) gx2 = 1;
-    k_bn_bwd_apply<<<dim3(gx2, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    if (p.dout) k_bn_bwd_apply<true><<<dim3(gx2, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    else k_bn_bwd_apply<false><<<dim3(gx2, G), blk, 2 * p.C * sizeof(float), st>>>(p);
     VV_CKL();
     return 0;
 }
