@@ -186,12 +186,14 @@ int vecvad_net_debug_read(vecvad_net *net, int kind, int index, float *dst, int6
 /* 3x3 pad-1 convolution as implicit GEMM.  in [B,H,W,cin] (row stride ld_in), w [cout,cin,3,3] PyTorch layout,
  * out [B,H,W,cout] raw (pre-BN) values; stats[2*cout] (double) receives per-channel sum and sum of squares
  * (may be NULL).  scratch: >= 9*cout*cin floats. use_tc: 0 fp32 SIMT tiles, 1 tcgen05 per-tap tiles,
- * 2 tcgen05 persistent tap-reuse tiles (the one the net uses when the shape allows). */
+ * 2 tcgen05 persistent tap-reuse tiles, 3 flattened-sequence tiles (the net's choice at >= 32 pixels per row, needs the nine
+ * weight tiles of an output tile within 72 KB), 4 pair tiles (the net's choice below that). */
 int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
                            float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream);
 
 /* weight gradient of the same convolution: dw [cout,cin,3,3] (PyTorch layout, overwritten) from in [B,H,W,cin] and
- * grad_out [B,H,W,cout] (NHWC, dense).  scratch: >= 9*cout*cin floats. */
+ * grad_out [B,H,W,cout] (NHWC, dense).  scratch: >= 9*cout*cin floats.  use_tc: 0 fp32 SIMT tiles, 1 tcgen05 per-tap tiles,
+ * 2 tcgen05 tap-reuse tiles, 3 flattened-sequence tiles (one MMA per K-step covers all nine taps; cout a multiple of 32). */
 int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
                          int cin, int cout, int use_tc, vecvad_stream stream);
 
