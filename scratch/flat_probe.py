@@ -1,6 +1,7 @@
-"""Device probe for the flattened-sequence conv tiles (igemm_flat.cu): which descriptor base-offset convention reads a
-SWIZZLE_128B box correctly when the operand starts on a 128-byte (not 1024-byte) boundary.  use_tc 3 = base offset set,
-4 = base offset 0.  Prints per-tap errors (single-tap weights isolate one descriptor start each)."""
+"""Device probe for the flattened-sequence conv tiles (igemm_flat.cu, use_tc 3): per-shape and per-tap errors against conv2d
+(single-tap weights isolate one descriptor start each).  The first version of the kernel could set the descriptor's base-offset
+field to the start row's swizzle phase or leave it 0; the run kept as profiles/r01_flat_probe.txt shows that only 0 reads a
+SWIZZLE_128B box correctly from a 128-byte-aligned (not 1024-byte-aligned) start, which is what the kernel now does."""
 import sys
 
 import torch
