@@ -76,6 +76,30 @@ def test_conv3x3_forward_flat(shape):
     assert (got - ref2).abs().max().item() <= 2e-5 * want.abs().max().item()
 
 
+@pytest.mark.parametrize('shape', [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (2, 32, 32, 32, 64), (37, 32, 32, 32, 32), (5, 16, 16, 32, 64)])
+def test_conv3x3_forward_flat_fp16_operands(shape):
+    """use_tc 5: the flattened-sequence tiles with fp16 operands (kind::f16, fp32 accumulation; DESIGN.md section 8).  fp16 carries
+    tf32's 10-bit mantissa, so the bound is the tf32 one; operands are converted inside the call (larger scratch)."""
+    b, h, wd, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + 11)
+    x = torch.randn(b, cin, h, wd, generator=g)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    bias = torch.randn(cout, generator=g)
+    want = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).contiguous()
+    xn, wc, bc = x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), bias.cuda()      # keep the device tensors alive across the call
+    out = torch.empty((b, h, wd, cout), device='cuda')
+    stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
+    scratch = torch.empty(9 * cout * cin + (9 * cout * cin) // 2 + 64 + (b * h * wd * cin) // 2 + 64, device='cuda')
+    rc = _lib.lib().vecvad_conv3x3_forward(_lib.ptr(xn), cin, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(out), _lib.ptr(stats),
+                                           _lib.ptr(scratch), b, h, wd, cin, cout, 5, _lib.cur_stream())
+    _lib.check(rc, 'conv3x3_forward')
+    torch.cuda.synchronize()
+    err = (out.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 2e-3, err
+    np.testing.assert_allclose(stats.cpu().numpy()[:cout], want.sum(dim=(0, 1, 2)).numpy(), rtol=0,
+                               atol=2e-3 * want.abs().sum(dim=(0, 1, 2)).max().item())
+
+
 def test_tf32_error_is_unbiased():
     """Operands are rounded (not truncated) to tf32 on their way into shared memory: the mean signed error of a
     positive-operand convolution stays far below the truncation bias (~1e-3 relative)."""

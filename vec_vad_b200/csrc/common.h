@@ -52,6 +52,7 @@ struct VvIGemm {
     const float *bias;  long long bias_gs;                         // nullable; indexed by n (or co when o_d2s)
     double *stats;      long long stats_gs;                        // nullable; [2][N] column sum / sum of squares
     int G;
+    int ab_f16;                                                    // A and Wt hold fp16 (lda / a_coff / Kt in elements); flattened tiles only
 };
 
 // dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]

@@ -57,10 +57,14 @@ constexpr int FL_STG_LD = 36;       // floats per staging row: 16-byte aligned, 
 constexpr int FL_STG_BYTES = 32 * FL_STG_LD * 4;
 constexpr int FL_MAX_RING = 4;
 
-template <int BN>
+// F16: operands are fp16 in HBM and shared memory (64-byte pixel rows, SWIZZLE_64B, kind::f16 with K = 16 per MMA): the same
+// bytes per MMA carry twice the K, so half the MMAs, half the TMA bytes.  Accumulation and outputs stay fp32.
+template <int BN, bool F16>
 __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                               const FlatParams p) {
-    constexpr int B_TAP = BN * KS * 4;                       // one (tap, slab) weight tile
+    constexpr int ROWB = F16 ? KS * 2 : KS * 4;              // bytes of one pixel row of a 32-channel slab
+    constexpr int KSTEPS = F16 ? KS / 16 : KS / 8;           // MMAs per (tap, slab)
+    constexpr int B_TAP = BN * ROWB;                         // one (tap, slab) weight tile
     extern __shared__ uint8_t smem_raw[];
     uint8_t *stage0 = (uint8_t *)(((uintptr_t)smem_raw + FL_GUARD + 1023) & ~(uintptr_t)1023);   // >= FL_GUARD bytes of ours in front
                                                              // stage (ring r, slot j) at stage0 + (r * spr + j) * stage_bytes
@@ -148,10 +152,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
         // ---------------- MMA issuers: warp 1 takes this CTA's even tiles (accumulator 0, ring 0), warp 2 the odd ones.
         // The loop is warp-uniform and free of divisions per MMA; one elected lane issues.
         const int mw = warp - 1;
-        const uint32_t idesc = idesc_tf32(BN);
+        const uint32_t idesc = F16 ? idesc_f16(BN) : idesc_tf32(BN);
         const uint32_t ring0 = smem_u32(stage0) + mw * p.spr * p.stage_bytes;
         const uint32_t b_lo0 = (smem_u32(b_stat) & 0x3FFFF) >> 4;
-        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+        // 8-row groups 8 * ROWB bytes apart, version 1, SWIZZLE_128B (layout 2) / SWIZZLE_64B (layout 4)
+        const uint32_t desc_hi = (uint32_t)((8 * ROWB) >> 4) | (1u << 14) | ((F16 ? 4u : 2u) << 29);
         const uint32_t d_tmem = tmem + mw * BN;
         uint64_t *rfull = full + mw * FL_MAX_RING, *rempty = empty + mw * FL_MAX_RING;
         long long t_wacc = 0, t_wfull = 0, t_wb;
@@ -177,21 +182,24 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
                     t_wfull += clock64() - t0;
                 }
                 tc_fence_after();
-                // descriptor low words (address >> 4); rows are 128 B = 8 units; row offset >= -1: the guard / the previous stage's slack
-                const uint32_t a_lo0 = (((ring0 + s * p.stage_bytes) & 0x3FFFF) >> 4) + (uint32_t)((q0 - p.P - 1) * 8);
+                // descriptor low words (address >> 4); rows are ROWB / 16 units; row offset >= -1: the guard / the previous stage's slack
+                const uint32_t a_lo0 = (((ring0 + s * p.stage_bytes) & 0x3FFFF) >> 4) + (uint32_t)((q0 - p.P - 1) * (ROWB / 16));
                 const uint32_t b_lok = b_lo0 + (uint32_t)(kc * (B_TAP >> 4));
                 if (!(p.dbg & 4)) {
 #pragma unroll
                     for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
                         for (int dxi = 0; dxi < 3; dxi++) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)((dyi * p.P + dxi) * 8);
+                            const uint32_t a_lo = a_lo0 + (uint32_t)((dyi * p.P + dxi) * (ROWB / 16));
                             const uint32_t b_lo = b_lok + (uint32_t)(p.tap[dyi][dxi] * p.kchunks * (B_TAP >> 4));
 #pragma unroll
-                            for (int k = 0; k < KS / 8; k++) {
+                            for (int k = 0; k < KSTEPS; k++) {       // 32 bytes of K per MMA in either format
                                 const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2 * k | (1u << 16));
                                 const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * k | (1u << 16));
-                                if (elect_one()) tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
+                                if (elect_one()) {
+                                    if (F16) tc_mma_f16(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
+                                    else tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
+                                }
                             }
                         }
                     }
@@ -336,14 +344,14 @@ int flat_mode() {
     return v;
 }
 
-template <int BN>
+template <int BN, bool F16>
 int launch_flat(const CUtensorMap &tmA, const CUtensorMap &tmB, const FlatParams &fp, dim3 grid, int smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        VV_CK(cudaFuncSetAttribute(k_igemm_flat<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM_MAX));
+        VV_CK(cudaFuncSetAttribute(k_igemm_flat<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM_MAX));
         attr = true;
     }
-    k_igemm_flat<BN><<<grid, FL_THREADS, smem, st>>>(tmA, tmB, fp);
+    k_igemm_flat<BN, F16><<<grid, FL_THREADS, smem, st>>>(tmA, tmB, fp);
     VV_CKL();
     if (fp.trace) {      // debugging aid: synchronous
         unsigned long long h[18];
@@ -363,7 +371,8 @@ bool vv_igemm_flat_shape_ok(const VvIGemm &p) {
     FlatParams fp;
     if (!vv_igemm_tc_supported(p) || p.a_s2d || p.o_d2s || !analyse_3x3(p.taps, fp)) return false;
     if (p.W + 1 > 256 || p.W < 8) return false;
-    const int b_all = 9 * (p.Kt / KS) * flat_bn_tile(p.N) * KS * 4;
+    if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8)) return false;           // 16-byte aligned pixel rows
+    const int b_all = 9 * (p.Kt / KS) * flat_bn_tile(p.N) * KS * (p.ab_f16 ? 2 : 4);
     return b_all <= 72 * 1024;
 }
 
@@ -385,19 +394,23 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     fp.P = p.W + 1; fp.L = p.H * fp.P; fp.tpi = (fp.L + BM - 1) / BM; fp.m_tiles = fp.tpi * p.B;
     fp.mP = (unsigned)((0x100000000ULL + fp.P - 1) / fp.P); fp.mtpi = (unsigned)((0x100000000ULL + fp.tpi - 1) / fp.tpi);
     fp.rows = (BM - 1) / fp.P + 4;                    // rows holding 128 consecutive positions (<= 127/P + 2) + one halo row either side
+    const int esz = p.ab_f16 ? 2 : 4;                  // operand element size
     fp.kchunks = p.Kt / KS;
-    fp.a_bytes = fp.rows * fp.P * KS * 4;
-    fp.stage_bytes = (fp.a_bytes + KS * 4 + 1023) / 1024 * 1024;      // >= one zero pixel-row of slack: the next stage's leading guard
+    fp.a_bytes = fp.rows * fp.P * KS * esz;
+    fp.stage_bytes = (fp.a_bytes + KS * esz + 1023) / 1024 * 1024;    // >= one zero pixel-row of slack: the next stage's leading guard
     fp.N = p.N; fp.O = p.O; fp.o_gs = p.o_gs; fp.ldo = p.ldo; fp.o_coff = p.o_coff;
     fp.bias = p.bias; fp.bias_gs = p.bias_gs; fp.stats = p.stats; fp.stats_gs = p.stats_gs;
     const int bn_tile = flat_bn_tile(p.N);
-    const int b_all = 9 * fp.kchunks * bn_tile * KS * 4;
+    const int b_all = 9 * fp.kchunks * bn_tile * KS * esz;
     const int fixed = 1024 /*alignment*/ + FL_GUARD + 8 * FL_STG_BYTES + 256 /*barriers*/ + 3 * bn_tile * 4;
     int spr = (FL_SMEM_MAX - fixed - b_all) / (2 * fp.stage_bytes);
     {
+        // tf32: the MMA warps are the limiter, deeper rings change nothing (measured); fp16: half the MMA time per box, so two
+        // stages per ring no longer cover the TMA latency (52.9 -> 39.1 us at four, profiles/r01_flat16_probe.txt)
         static int cap = -1;
-        if (cap < 0) { const char *e = getenv("VECVAD_FLAT_STAGES"); cap = e ? atoi(e) : 2; }
-        if (cap >= 1 && spr > cap) spr = cap;
+        if (cap < 0) { const char *e = getenv("VECVAD_FLAT_STAGES"); cap = e ? atoi(e) : 0; }
+        const int c = cap > 0 ? cap : (p.ab_f16 ? 4 : 2);
+        if (spr > c) spr = c;
     }
     if (spr > FL_MAX_RING) spr = FL_MAX_RING;
     VV_REQUIRE(spr >= 1, "igemm_flat: tile does not fit in shared memory");
@@ -411,24 +424,26 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     }
     const int smem = fixed + b_all + 2 * spr * fp.stage_bytes;
 
-    const CUtensorMapDataType dt = tmap_dtype();
+    const CUtensorMapDataType dt = p.ab_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : tmap_dtype();
+    const CUtensorMapSwizzle sw = p.ab_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;      // 32 channels = 64 / 128 bytes
+    const char *abase = (const char *)p.A + (long long)p.a_coff * esz;
     alignas(64) CUtensorMap tmA, tmB;
     {
         // (channel, x, y, image); the box is P = W + 1 wide and starts at x = 0: column W is out of range = the zero separator
         cuuint64_t dims[4] = {(cuuint64_t)p.Kt, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.G * p.B};
-        cuuint64_t strides[3] = {(cuuint64_t)p.lda * 4, (cuuint64_t)p.W * p.lda * 4, (cuuint64_t)p.H * p.W * p.lda * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)p.lda * esz, (cuuint64_t)p.W * p.lda * esz, (cuuint64_t)p.H * p.W * p.lda * esz};
         cuuint32_t box[4] = {KS, (cuuint32_t)fp.P, (cuuint32_t)fp.rows, 1};
         cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&tmA, dt, 4, (void *)(p.A + p.a_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(&tmA, dt, 4, (void *)abase, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "igemm_flat: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)p.Kt, (cuuint64_t)p.N, (cuuint64_t)9 * p.G};
-        cuuint64_t strides[2] = {(cuuint64_t)p.Kt * 4, (cuuint64_t)p.N * p.Kt * 4};
+        cuuint64_t strides[2] = {(cuuint64_t)p.Kt * esz, (cuuint64_t)p.N * p.Kt * esz};
         cuuint32_t box[3] = {KS, (cuuint32_t)bn_tile, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmB, dt, 3, (void *)p.Wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CUresult r = enc(&tmB, dt, 3, (void *)p.Wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "igemm_flat: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
@@ -437,6 +452,7 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     if (gx < 1) gx = 1;
     if (gx > fp.m_tiles) gx = fp.m_tiles;
     dim3 grid(gx, n_tiles, p.G);
-    if (bn_tile == 64) return launch_flat<64>(tmA, tmB, fp, grid, smem, st);
-    return launch_flat<32>(tmA, tmB, fp, grid, smem, st);
+    if (p.ab_f16) return bn_tile == 64 ? launch_flat<64, true>(tmA, tmB, fp, grid, smem, st) : launch_flat<32, true>(tmA, tmB, fp, grid, smem, st);
+    if (bn_tile == 64) return launch_flat<64, false>(tmA, tmB, fp, grid, smem, st);
+    return launch_flat<32, false>(tmA, tmB, fp, grid, smem, st);
 }

@@ -5,6 +5,8 @@
 //
 // Reference semantics restated (reference file:line in each kernel's comment); PyTorch layer
 // definitions at model/unet.py:9-16 (conv+BN+ReLU), :38 (MaxPool2d(2)), :54 (ConvTranspose2d), :66 (1x1 conv).
+#include <cuda_fp16.h>
+
 #include "unet_kernels.h"
 
 namespace {
@@ -1018,3 +1020,32 @@ extern "C" int vecvad_cubes_to_tensors(const uint8_t *raw, const float *flow, fl
     VV_CKL();
     return 0;
 }
+
+namespace {
+__global__ void k_f32_to_f16(const float *__restrict__ src, int ld, int cols, long long rows, __half *__restrict__ dst) {
+    const int cq = cols >> 2;
+    const long long total = rows * cq;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / cq;
+        const int c4 = (int)(i - r * cq);
+        const float4 v = *reinterpret_cast<const float4 *>(src + r * ld + c4 * 4);
+        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<unsigned *>(&lo);
+        o.y = *reinterpret_cast<unsigned *>(&hi);
+        *reinterpret_cast<uint2 *>(dst + r * cols + c4 * 4) = o;
+    }
+}
+}  // namespace
+
+int vv_f32_to_f16(const float *src, int ld, int cols, long long rows, void *dst, cudaStream_t st) {
+    VV_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "f32_to_f16: cols / ld must be multiples of 4");
+    long long total = rows * (cols / 4);
+    int gx = vv_cdiv(total, 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    if (gx < 1) gx = 1;
+    k_f32_to_f16<<<gx, 256, 0, st>>>(src, ld, cols, rows, (__half *)dst);
+    VV_CKL();
+    return 0;
+}
+

@@ -93,3 +93,7 @@ int vv_scatter_conv_wgrad(const float *dWf, long long gs, int N, int C, int Cp, 
 int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float *grads, const VvIntG &slot, long long slot_stride,
                         long long w_off, int G, cudaStream_t st);
 int vv_losses(const float *sse, int G, int B, const VvIntG &is_flow, float inv_raw, float inv_of, float *out, cudaStream_t st);
+
+// fp32 [rows][ld] (first `cols` of each row) -> dense fp16 [rows][cols], round to nearest (operand staging of the fp16 tile experiments)
+int vv_f32_to_f16(const float *src, int ld, int cols, long long rows, void *dst, cudaStream_t st);
+
