@@ -9,8 +9,8 @@
 // padding of row y + 1.  In that flattened sequence every tap (dy, dx) of every pixel is the constant offset dy * P + dx, so
 // the A operand of a tap is the SAME box read through a UMMA descriptor that starts (dy * P + dx) * 128 bytes further in --
 // 9 taps from one load.  A tile is 128 consecutive sequence positions of one image (positions on the separator column or past
-// the image are computed and discarded: 86 % useful rows at 32x32); its box is the 7 image rows those positions and their
-// halo touch: 1.8 x the activation bytes instead of 4.5 x.
+// the image are computed and discarded: 89 % useful rows at 32x32); its box is the 7 image rows those positions and their
+// halo touch: 2.0 x the activation bytes instead of 4.5 x.
 //   Descriptor starts are 128-byte but not 1024-byte aligned.  Measured on the device (scratch/flat_probe.py): the UMMA applies
 //   the 128B swizzle to the absolute shared-memory address, so such a start reads the TMA-written box correctly with the
 //   descriptor's base-offset field left at 0 (setting it to the start row's phase gives wrong operands).
