@@ -188,8 +188,9 @@ int vecvad_net_debug_read(vecvad_net *net, int kind, int index, float *dst, int6
  * (may be NULL).  scratch: >= 9*cout*cin floats. use_tc: 0 fp32 SIMT tiles, 1 tcgen05 per-tap tiles,
  * 2 tcgen05 persistent tap-reuse tiles, 3 flattened-sequence tiles (the net's choice at >= 32 pixels per row, needs the nine
  * weight tiles of an output tile within 72 KB), 4 pair tiles (the net's choice below that), 5 flattened-sequence tiles with fp16
- * operands and fp32 accumulation (experiment: input and weights are converted inside the call and scratch must hold
- * 9*cout*cin floats + 9*cout*cin halfs (rounded up to 256 bytes) + batch*h*wd*cin halfs). */
+ * operands and fp32 accumulation, 6 the same for the pair tiles (experiments: input and weights are converted inside the call and
+ * scratch must hold 9*cout*cin floats + 9*cout*cin halfs (rounded up to 256 bytes) + batch*h*wd*cin halfs; 6 has not run on a
+ * device yet). */
 int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
                            float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream);
 

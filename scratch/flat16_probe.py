@@ -39,6 +39,16 @@ def run(shape, mode, tap=None, seed=0):
 
 
 if __name__ == '__main__':
+    if os.environ.get('VV_TC3'):
+        # round-2 starting point: the fp16 variant of the pair tiles (use_tc 6, never run on a device in round 1) next to tf32 (4)
+        for shape in [(5, 16, 16, 32, 64), (3, 16, 16, 64, 64), (3, 8, 8, 64, 128), (5, 4, 4, 128, 256), (9, 4, 4, 256, 256), (70, 16, 16, 64, 64)]:
+            for mode in (4, 6):
+                try:
+                    err, d = run(shape, mode)
+                    print('mode %d shape %s err %.3e %s' % (mode, shape, err, 'OK' if err < 2e-3 else 'BAD'), flush=True)
+                except Exception as e:  # noqa: BLE001
+                    print('mode', mode, shape, 'EXC', e, flush=True)
+        sys.exit(0)
     if os.environ.get('VV_TIME'):
         for cfg in [(768, 32, 32, 32, 32), (768, 32, 32, 64, 32), (768, 32, 32, 32, 64)]:
             for mode in (3, 5):

@@ -53,10 +53,14 @@ constexpr int T3_MAX_STAGES = 4;
 // float index of 16-byte chunk c4 (0..7) of staging row r
 __device__ __forceinline__ int stg_idx(int r, int c4) { return r * 32 + ((c4 ^ (r & 7)) << 2); }
 
-template <int BN>
+// F16: operands are fp16 in HBM and shared memory (64-byte pixel rows, SWIZZLE_64B, kind::f16 with K = 16 per MMA), accumulation and
+// outputs fp32 -- the variant measured on the flattened tile; not yet validated on the device for this kernel.
+template <int BN, bool F16>
 __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const Tc3Params p) {
-    constexpr int B_TAP = BN * KS * 4;                       // one (tap, slab) weight tile
+    constexpr int ROWB = F16 ? KS * 2 : KS * 4;              // bytes of one pixel row of a 32-channel slab
+    constexpr int KSTEPS = F16 ? KS / 16 : KS / 8;           // MMAs per (tap, slab): 32 bytes of K each
+    constexpr int B_TAP = BN * ROWB;                         // one (tap, slab) weight tile
     constexpr int NBUF = (4 * BN <= 512 && BN < 128) ? 2 : 1; // accumulator double-buffering across pairs while TMEM allows it
     constexpr int TMEM_COLS = 2 * NBUF * BN < 32 ? 32 : 2 * NBUF * BN;
     extern __shared__ uint8_t smem_raw[];
@@ -153,10 +157,11 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
     } else if (warp <= 2) {
         // ---------------- MMA issuers: warp 1 computes tile 0 of every pair, warp 2 tile 1; same stages, same order.
         const int mw = warp - 1;
-        const uint32_t idesc = idesc_tf32(BN);
+        const uint32_t idesc = F16 ? idesc_f16(BN) : idesc_tf32(BN);
         const uint32_t smem_base = smem_u32(smem);
         const uint32_t bstat_lo = (smem_u32(b_stat) & 0x3FFFF) >> 4;
-        const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);     // SBO 1024 B, version 1, SWIZZLE_128B
+        // 8-row groups 8 * ROWB bytes apart, version 1, SWIZZLE_128B (layout 2) / SWIZZLE_64B (layout 4)
+        const uint32_t desc_hi = (uint32_t)((8 * ROWB) >> 4) | (1u << 14) | ((F16 ? 4u : 2u) << 29);
         long long t_wacc = 0, t_wfull = 0;
         const long long t_begin = clock64();
         if (p.stationary) mbar_wait(bfull, 0);
@@ -188,10 +193,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
                             const uint32_t b_lo = p.stationary ? bstat_lo + (uint32_t)(((p.tap[dyi][dxi] * p.kchunks + kc) * B_TAP) >> 4)
                                                                : st_lo + (uint32_t)((dyi * B_TAP) >> 4);
 #pragma unroll
-                            for (int k = 0; k < KS / 8; k++) {
+                            for (int k = 0; k < KSTEPS; k++) {
                                 const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2 * k | (1u << 16));
                                 const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * k | (1u << 16));
-                                if (elect_one()) tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)k) ? 1u : 0u);
+                                if (elect_one()) {
+                                    if (F16) tc_mma_f16(d_tmem, da, db, idesc, (acc | (uint32_t)k) ? 1u : 0u);
+                                    else tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)k) ? 1u : 0u);
+                                }
                             }
                             acc = 1;
                         }
@@ -343,6 +351,8 @@ inline int tc3_bn_tile(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 
 // fills the geometry / shared-memory plan; false when a pair stage does not fit twice
 bool plan3(const VvIGemm &p, Tc3Params &tp, int &smem_bytes) {
     if (!analyse_taps3(p.taps, tp)) return false;
+    const int esz = p.ab_f16 ? 2 : 4;                  // operand element size
+    if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8 || p.a_s2d)) return false;
     tp.B = p.B; tp.H = p.H; tp.W = p.W; tp.G = p.G;
     if (!tile_geometry_n(p.H, p.W, BM, tp.bw, tp.bh, tp.bn)) return false;
     tp.tiles_x = p.W / tp.bw; tp.tiles_y = p.H / tp.bh; tp.tiles_n = (p.B + tp.bn - 1) / tp.bn;
@@ -350,10 +360,11 @@ bool plan3(const VvIGemm &p, Tc3Params &tp, int &smem_bytes) {
     tp.pairs = (tp.m_tiles + 1) / 2;
     tp.kchunks = p.Kt / KS; tp.cq = p.a_s2d ? p.Kt / 4 : 0;
     const int rows = tp.bh + tp.ndy - 1;
-    tp.row_shift = tp.bn * tp.bw * KS * 4;
+    tp.row_shift = tp.bn * tp.bw * KS * esz;
+    if (tp.row_shift % 1024) return false;             // a dy step must keep the swizzle phase (and the stage layout 1024-byte aligned)
     tp.a_bytes = rows * tp.row_shift;
     const int bn_tile = tc3_bn_tile(p.N);
-    const int b_tap = bn_tile * KS * 4;
+    const int b_tap = bn_tile * KS * esz;
     const int b_all = tp.ntaps * tp.kchunks * b_tap;
     const int fixed = 1024 /*alignment*/ + 8 * T3_STG_BYTES + 256 /*barriers*/ + 3 * bn_tile * 4;
     tp.stationary = b_all <= 72 * 1024;
@@ -371,14 +382,14 @@ bool plan3(const VvIGemm &p, Tc3Params &tp, int &smem_bytes) {
 
 bool g_tc3_disabled = false;      // set when the permuted-dimension tensor map is refused by the driver
 
-template <int BN>
+template <int BN, bool F16>
 int launch3(const CUtensorMap &tmA, const CUtensorMap &tmB, const Tc3Params &tp, dim3 grid, int smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        VV_CK(cudaFuncSetAttribute(k_igemm_tc3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_MAX));
+        VV_CK(cudaFuncSetAttribute(k_igemm_tc3<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_MAX));
         attr = true;
     }
-    k_igemm_tc3<BN><<<grid, T3_THREADS, smem, st>>>(tmA, tmB, tp);
+    k_igemm_tc3<BN, F16><<<grid, T3_THREADS, smem, st>>>(tmA, tmB, tp);
     VV_CKL();
     if (tp.trace) {      // debugging aid: synchronous
         unsigned long long h[12];
@@ -423,18 +434,20 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
     }
     const int rows = tp.bh + tp.ndy - 1;
     const int bn_tile = tc3_bn_tile(p.N);
-    const CUtensorMapDataType dt = tmap_dtype();
+    const int esz = p.ab_f16 ? 2 : 4;
+    const CUtensorMapDataType dt = p.ab_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : tmap_dtype();
+    const CUtensorMapSwizzle sw = p.ab_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B;      // 32 channels = 64 / 128 bytes
     alignas(64) CUtensorMap tmA, tmB;
     {
         // dimensions ordered (channel, x, image, y): the box lands in shared memory as [row][image][x][32 ch]
         const int sc = p.a_s2d ? 2 : 1;
         const cuuint64_t C = p.a_s2d ? p.Kt / 4 : p.Kt;
         cuuint64_t dims[4] = {C, (cuuint64_t)sc * p.W, (cuuint64_t)p.G * p.B, (cuuint64_t)sc * p.H};
-        cuuint64_t strides[3] = {(cuuint64_t)p.lda * 4, (cuuint64_t)sc * p.H * sc * p.W * p.lda * 4, (cuuint64_t)sc * p.W * p.lda * 4};
+        cuuint64_t strides[3] = {(cuuint64_t)p.lda * esz, (cuuint64_t)sc * p.H * sc * p.W * p.lda * esz, (cuuint64_t)sc * p.W * p.lda * esz};
         cuuint32_t box[4] = {KS, (cuuint32_t)(sc * tp.bw), (cuuint32_t)tp.bn, (cuuint32_t)(sc * rows)};
         cuuint32_t estr[4] = {1, (cuuint32_t)sc, 1, (cuuint32_t)sc};
-        CUresult r = enc(&tmA, dt, 4, (void *)(p.A + p.a_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(&tmA, dt, 4, (void *)((const char *)p.A + (long long)p.a_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             g_tc3_disabled = true;                // the per-tap kernel from now on
             return vv_launch_igemm_tc(p, st);
@@ -442,10 +455,10 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)p.Kt, (cuuint64_t)p.N, (cuuint64_t)p.taps.n * p.G};
-        cuuint64_t strides[2] = {(cuuint64_t)p.Kt * 4, (cuuint64_t)p.N * p.Kt * 4};
+        cuuint64_t strides[2] = {(cuuint64_t)p.Kt * esz, (cuuint64_t)p.N * p.Kt * esz};
         cuuint32_t box[3] = {KS, (cuuint32_t)bn_tile, 1};
         cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = enc(&tmB, dt, 3, (void *)p.Wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CUresult r = enc(&tmB, dt, 3, (void *)p.Wt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "igemm_tc3: cuTensorMapEncodeTiled(W) failed with %d", (int)r);
     }
@@ -454,7 +467,12 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
     if (gx < 1) gx = 1;
     if (gx > tp.pairs) gx = tp.pairs;
     dim3 grid(gx, n_tiles, p.G);
-    if (bn_tile == 128) return launch3<128>(tmA, tmB, tp, grid, smem, st);
-    if (bn_tile == 64) return launch3<64>(tmA, tmB, tp, grid, smem, st);
-    return launch3<32>(tmA, tmB, tp, grid, smem, st);
+    if (p.ab_f16) {
+        if (bn_tile == 128) return launch3<128, true>(tmA, tmB, tp, grid, smem, st);
+        if (bn_tile == 64) return launch3<64, true>(tmA, tmB, tp, grid, smem, st);
+        return launch3<32, true>(tmA, tmB, tp, grid, smem, st);
+    }
+    if (bn_tile == 128) return launch3<128, false>(tmA, tmB, tp, grid, smem, st);
+    if (bn_tile == 64) return launch3<64, false>(tmA, tmB, tp, grid, smem, st);
+    return launch3<32, false>(tmA, tmB, tp, grid, smem, st);
 }

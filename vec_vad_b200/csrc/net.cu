@@ -652,13 +652,18 @@ extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w
     p.O = out; p.ldo = cout; p.bias = bias; p.stats = stats; p.G = 1;
     if (use_tc) {
         VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_forward: shape not supported by the tcgen05 path");
-        if (use_tc == 5) {       // flattened-sequence tiles with fp16 operands (experiment): operands are converted
-                                 // here; scratch holds [9*cout*cin fp32 weights][9*cout*cin fp16 weights][batch*h*wd*cin fp16 input]
+        if (use_tc == 5 || use_tc == 6) {   // fp16 operands (experiment): 5 = flattened-sequence tiles, 6 = pair tiles.
+                                            // Operands are converted here; scratch holds [9*cout*cin fp32 weights][9*cout*cin fp16
+                                            // weights][batch*h*wd*cin fp16 input]
             char *w16 = (char *)(scratch + 9LL * cout * cin);
             char *in16 = w16 + (((9LL * cout * cin * 2) + 255) / 256) * 256;
             if ((r = vv_f32_to_f16(scratch, cin, cin, 9LL * cout, w16, st))) return r;
             if ((r = vv_f32_to_f16(in, ld_in, cin, (long long)batch * h * wd, in16, st))) return r;
             p.A = (const float *)in16; p.lda = cin; p.Wt = (const float *)w16; p.ab_f16 = 1;
+            if (use_tc == 6) {
+                VV_REQUIRE(vv_igemm_tc3_supported(p), "conv3x3_forward: shape not supported by the fp16 pair tcgen05 path");
+                return vv_launch_igemm_tc3(p, st);
+            }
             VV_REQUIRE(vv_igemm_flat_shape_ok(p), "conv3x3_forward: shape not supported by the flattened fp16 tcgen05 path");
             return vv_launch_igemm_flat(p, st);
         }
