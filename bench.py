@@ -29,6 +29,8 @@ if REPO not in sys.path:
 # summed over the class's launches: k_igemm_flat + k_igemm_tc3, k_wgrad_flat + k_wgrad_tc2)
 NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': (1.876e9 + 0.604e9, 33), 'wgrad_tcgen05': (1.924e9 + 0.002e9, 17)}
 
+METRIC = 'STCs/sec (train step, device-timed)'       # BASELINE.json's metric; both arms print the same string
+
 # algorithmic FLOPs of one train step per STC (fwd + dgrad + wgrad of every conv; SURVEY.md section 8a / BASELINE.md section 2)
 FLOPS_PER_STC = {'net4': 5.524e9, 'full': 9.206e9, 'noflow': 4.604e9}
 NET_KW = {
@@ -110,10 +112,11 @@ def run_reference(args):
     threads = os.cpu_count() or 1
     batch = args.batch
     v, dt = cpu_reference_steps(args.net, batch, args.steps, args.warmup, threads)
-    line = {'impl': 'reference', 'metric': 'STCs/sec (train step)', 'value': v, 'unit': 'STC/s', 'n_gpus': args.gpus, 'steps': args.steps,
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'STC/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_step': batch},
+            'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': batch, 'global_batch': batch,
+                       'timing': 'host wall clock on rank 0 only (the CPU arm has no device): each step is one batch of the same workload'},
             'cpu_baseline': {'value': v, 'unit': 'STC/s', 'cores': threads, 'kind': 'port',
                              'sample': '%d train steps of batch %d (oracle port of model/unet.py + train.py:383-402, torch CPU fp32)' % (args.steps, batch)},
             'e2e': {'value': v, 'unit': 'STC/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
@@ -209,7 +212,7 @@ def run_ours(args):
         dom_ms, dom_fl, dom_n = prof[dom]
         dom_tf = dom_fl / (dom_ms * 1e-3) / 1e12
         tf32 = not args.simt
-        line = {'metric': 'STCs/sec (train step, device-timed)', 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
+        line = {'metric': METRIC, 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
                 'dtype': 'tf32' if tf32 else 'f32', 'data': 'synthetic',
                 'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': B, 'global_batch': world * B,
