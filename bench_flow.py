@@ -53,6 +53,21 @@ def main():
         ('resample2d_forward', lambda: warp(img1, flow), B * (3 + 2 + 3) * 436 * 1024 * 4, 0.0),
         ('warp_diff_norm_fused', lambda: ops.warp_diff_norm(img0, img1, flow), B * (3 + 3 + 2 + 3 + 3 + 1) * 436 * 1024 * 4, 0.0),
     ]
+    # the stated bar of SURVEY.md section 2.2: the reference's own kernels, recompiled unmodified for sm_100a (oracle/_ref,
+    # test infrastructure -- timed here as the baseline beside ours, never part of the product path)
+    try:
+        from oracle import ref_ops
+        have_ref = ref_ops.available()
+    except ImportError:
+        have_ref = False
+    if have_ref:
+        scratch = torch.empty(ref_ops.lib().ref_correlation_scratch_floats(B, 256, 55, 128, 20), device=dev)
+        rows += [
+            ('reference_correlation_forward', lambda: ref_ops.correlation_forward(f1, f2, 20, 1, 20, 1, 2, 1, scratch=scratch), rows[0][2], rows[0][3]),
+            ('reference_resample2d_forward', lambda: ref_ops.resample2d_forward(img1, flow), rows[1][2], 0.0),
+            ('reference_warp_diff_norm_chain', lambda: ref_ops.channelnorm_forward((img0 - ref_ops.resample2d_forward(img1, flow)).contiguous()),
+             rows[2][2], 0.0),
+        ]
     for name, fn, nbytes, flops in rows:
         t = timed(fn)
         line = {'op': name, 'batch': B, 'us': t * 1e6, 'pairs_per_s': B / t, 'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / t / 1e9,

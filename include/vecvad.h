@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 3
+#define VECVAD_ABI_VERSION 4
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -199,6 +199,24 @@ int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const flo
  * 2 tcgen05 tap-reuse tiles, 3 flattened-sequence tiles (one MMA per K-step covers all nine taps; cout a multiple of 32). */
 int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
                          int cin, int cout, int use_tc, vecvad_stream stream);
+
+/* input gradient of the same convolution (what the engine's backward launches for every unit but the first): grad_out
+ * [B,H,W,cout] dense NHWC, w [cout,cin,3,3] -> grad_in [B,H,W,cin].  scratch: >= 18*cout*cin floats.  use_tc: 0 fp32 SIMT tiles,
+ * nonzero: the tcgen05 tile the engine picks for this shape (flattened-sequence tiles at >= 32 pixels per row, pair tiles below). */
+int vecvad_conv3x3_dgrad(const float *grad_out, const float *w, float *grad_in, float *scratch, int batch, int h, int wd, int cin,
+                         int cout, int use_tc, vecvad_stream stream);
+
+/* ConvTranspose2d(ci -> co, kernel 3, stride 2, padding 1, output_padding 1) (model/unet.py:54) exactly as the engine runs it:
+ * the four sub-pixel phases as one 2x2-tap contraction over 4*co columns, pixel-shuffled by the epilogue into
+ * out [B,2H,2W,ld_out] at channel offset out_coff (the second half of the concat buffer, model/unet.py:59).
+ * in [B,H,W,ci] dense NHWC, w [ci,co,3,3] PyTorch layout, bias [co].  scratch: >= 32*co*ci + co floats (wgrad: 48*co*ci + co).
+ * _dgrad: grad_out [B,2H,2W,ld] (channels coff .. coff+co) -> grad_in [B,H,W,ci];  _wgrad: -> dw [ci,co,3,3] (overwritten). */
+int vecvad_convt3x3s2_forward(const float *in, const float *w, const float *bias, float *out, int ld_out, int out_coff,
+                              float *scratch, int batch, int h, int wd, int ci, int co, int use_tc, vecvad_stream stream);
+int vecvad_convt3x3s2_dgrad(const float *grad_out, int ld, int coff, const float *w, float *grad_in, float *scratch, int batch,
+                            int h, int wd, int ci, int co, int use_tc, vecvad_stream stream);
+int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int coff, float *dw, float *scratch, int batch, int h,
+                            int wd, int ci, int co, int use_tc, vecvad_stream stream);
 
 /* cube staging: uint8 cubes [N,T,S,S,3] (+ float flow [N,T_of,S,S,2]) -> x [N,3T,S,S] float /255, x_of [N,2*T_of,S,S]
  * == cube_to_train_dataset + ToTensor + collate (vad_datasets.py:130-168). */

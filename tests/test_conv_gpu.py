@@ -136,3 +136,95 @@ def test_conv3x3_wgrad(shape, use_tc):
     _lib.check(rc, 'conv3x3_wgrad')
     err = (dw.cpu().double() - want).abs().max().item() / want.abs().max().item()
     assert err < (3e-3 if use_tc else 2e-5), err
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Input-gradient (flipped taps) and transposed-conv tiles, one op at a time through the C ABI, against float64 autograd of the
+# PyTorch ops the reference calls (conv2d: model/unet.py:10,13; ConvTranspose2d(k3, s2, p1, output_padding 1): model/unet.py:54).
+# use_tc 1 = the tcgen05 tile the engine picks for the shape, 0 = fp32 SIMT tiles.  Shapes: the net's own layers (ragged batches).
+# ---------------------------------------------------------------------------------------------------------------------------
+DGRAD_SHAPES = [(3, 32, 32, 32, 32), (2, 32, 32, 32, 64), (5, 16, 16, 64, 64), (3, 16, 16, 32, 64), (7, 8, 8, 128, 128), (5, 8, 8, 64, 128),
+                (9, 4, 4, 256, 256), (37, 4, 4, 128, 256), (130, 32, 32, 32, 32), (3, 8, 8, 256, 128), (2, 16, 16, 128, 64)]
+
+
+def _tol(use_tc):
+    return 3e-3 if use_tc else 2e-5
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('shape', DGRAD_SHAPES)
+def test_conv3x3_dgrad(shape, use_tc):
+    b, h, wd, cin, cout = shape
+    g = torch.Generator().manual_seed(sum(shape) + 3)
+    w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
+    go = torch.randn(b, cout, h, wd, generator=g)
+    x = torch.zeros(b, cin, h, wd, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w.double(), None, padding=1).backward(go.double())
+    want = x.grad.permute(0, 2, 3, 1).contiguous()
+    gn, wc = go.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda()
+    gi = torch.empty((b, h, wd, cin), device='cuda')
+    scratch = torch.empty(18 * cout * cin, device='cuda')
+    _lib.check(_lib.lib().vecvad_conv3x3_dgrad(_lib.ptr(gn), _lib.ptr(wc), _lib.ptr(gi), _lib.ptr(scratch), b, h, wd, cin, cout, use_tc,
+                                               _lib.cur_stream()), 'conv3x3_dgrad')
+    torch.cuda.synchronize()
+    err = (gi.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    assert err < _tol(use_tc), err
+
+
+CT_SHAPES = [(3, 4, 4, 256, 128), (37, 4, 4, 256, 128), (5, 8, 8, 128, 64), (2, 16, 16, 64, 32), (130, 16, 16, 64, 32), (1, 8, 8, 128, 64)]
+
+
+def _ct_reference(shape, seed):
+    b, h, wd, ci, co = shape
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(b, ci, h, wd, generator=g)
+    w = torch.randn(ci, co, 3, 3, generator=g) / (1.5 * ci ** 0.5)
+    bias = torch.randn(co, generator=g)
+    go = torch.randn(b, co, 2 * h, 2 * wd, generator=g)
+    xd, wdd = x.double().requires_grad_(), w.double().requires_grad_()
+    out = F.conv_transpose2d(xd, wdd, bias.double(), stride=2, padding=1, output_padding=1)
+    out.backward(go.double())
+    return x, w, bias, go, out.detach(), xd.grad, wdd.grad
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('shape', CT_SHAPES)
+def test_conv_transpose_forward_into_concat_half(shape, use_tc):
+    """Output lands pixel-shuffled in channels [co, 2co) of a [B,2H,2W,2co] concat buffer (torch.cat([skip, up]), model/unet.py:59);
+    the first half must stay untouched."""
+    b, h, wd, ci, co = shape
+    x, w, bias, go, want, _, _ = _ct_reference(shape, sum(shape) + 5)
+    xn, wc, bc = x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), bias.cuda()
+    cat = torch.full((b, 2 * h, 2 * wd, 2 * co), 7.0, device='cuda')
+    scratch = torch.empty(32 * co * ci + co, device='cuda')
+    _lib.check(_lib.lib().vecvad_convt3x3s2_forward(_lib.ptr(xn), _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(cat), 2 * co, co, _lib.ptr(scratch), b, h,
+                                                    wd, ci, co, use_tc, _lib.cur_stream()), 'convt_forward')
+    torch.cuda.synchronize()
+    got = cat[..., co:].cpu().double()
+    want = want.permute(0, 2, 3, 1)
+    assert (got - want).abs().max().item() / want.abs().max().item() < _tol(use_tc)
+    assert torch.all(cat[..., :co] == 7.0)
+
+
+@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('shape', CT_SHAPES)
+def test_conv_transpose_input_and_weight_gradients(shape, use_tc):
+    b, h, wd, ci, co = shape
+    x, w, bias, go, _, want_gx, want_gw = _ct_reference(shape, sum(shape) + 6)
+    xn, wc = x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda()
+    # the gradient arrives in the second half of the concat-shaped gradient buffer (net.cu: dCAT), first half holds the skip gradient
+    dcat = torch.randn((b, 2 * h, 2 * wd, 2 * co), generator=torch.Generator().manual_seed(1)).cuda()
+    dcat[..., co:] = go.permute(0, 2, 3, 1).cuda()
+    gi = torch.empty((b, h, wd, ci), device='cuda')
+    scratch = torch.empty(48 * co * ci + co, device='cuda')
+    L = _lib.lib()
+    _lib.check(L.vecvad_convt3x3s2_dgrad(_lib.ptr(dcat), 2 * co, co, _lib.ptr(wc), _lib.ptr(gi), _lib.ptr(scratch), b, h, wd, ci, co, use_tc,
+                                         _lib.cur_stream()), 'convt_dgrad')
+    torch.cuda.synchronize()
+    want = want_gx.permute(0, 2, 3, 1)
+    assert (gi.cpu().double() - want).abs().max().item() / want.abs().max().item() < _tol(use_tc)
+    dw = torch.empty((ci, co, 3, 3), device='cuda')
+    _lib.check(L.vecvad_convt3x3s2_wgrad(_lib.ptr(xn), _lib.ptr(dcat), 2 * co, co, _lib.ptr(dw), _lib.ptr(scratch), b, h, wd, ci, co, use_tc,
+                                         _lib.cur_stream()), 'convt_wgrad')
+    torch.cuda.synchronize()
+    assert (dw.cpu().double() - want_gw).abs().max().item() / want_gw.abs().max().item() < _tol(use_tc)

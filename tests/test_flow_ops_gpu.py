@@ -127,3 +127,92 @@ def test_warp_diff_norm_fused():
 def test_rejects_cpu_tensors():
     with pytest.raises(RuntimeError, match='CUDA'):
         ops.ChannelNorm()(torch.zeros(1, 2, 3, 3))
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Against OUTPUTS OF THE REFERENCE'S OWN KERNELS (tests/golden/flow_ops.npz, written on a B200 by
+# tests/golden/make_flow_golden.py from oracle/_ref/libref_ops.so = the reference .cu files recompiled unmodified).
+# ---------------------------------------------------------------------------------------------------------------------------
+import os
+
+from tests import _flow_cases as fc
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'flow_ops.npz')
+
+
+@pytest.fixture(scope='module')
+def gold():
+    assert os.path.exists(_GOLD), 'tests/golden/flow_ops.npz missing'
+    with np.load(_GOLD, allow_pickle=False) as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize('case', fc.CORR_FWD)
+def test_correlation_forward_equals_reference_kernel(case, gold):
+    a, b = fc.corr_inputs(case)
+    got = ops.Correlation(*case[4:], 1)(_t(a), _t(b)).cpu().numpy()
+    fc.compare(gold, fc.key('corr_fwd', case), got, rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('case', fc.CORR_BWD)
+def test_correlation_backward_equals_reference_kernel(case, gold):
+    a, b = fc.corr_inputs(case)
+    ta, tb = _t(a).requires_grad_(), _t(b).requires_grad_()
+    out = ops.Correlation(*case[4:], 1)(ta, tb)
+    out.backward(_t(fc.corr_grad_out(case, tuple(out.shape))))
+    fc.compare(gold, fc.key('corr_bwd1', case), ta.grad.cpu().numpy(), rtol=2e-4, atol=2e-5)
+    fc.compare(gold, fc.key('corr_bwd2', case), tb.grad.cpu().numpy(), rtol=2e-4, atol=2e-5)
+
+
+@pytest.mark.parametrize('case', fc.WARP_FWD)
+def test_resample2d_forward_equals_reference_kernel(case, gold):
+    img, flow, _ = fc.warp_inputs(case)
+    fc.compare(gold, fc.key('warp_fwd', case), ops.Resample2d()(_t(img), _t(flow)).cpu().numpy(), rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('case', fc.WARP_BWD)
+def test_resample2d_backward_equals_reference_kernel(case, gold):
+    img, flow, go = fc.warp_inputs(case)
+    ti, tf = _t(img).requires_grad_(), _t(flow).requires_grad_()
+    ops.Resample2d()(ti, tf).backward(_t(go))
+    fc.compare(gold, fc.key('warp_bwd_img', case), ti.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+    fc.compare(gold, fc.key('warp_bwd_flow', case), tf.grad.cpu().numpy(), rtol=1e-4, atol=1e-5)
+
+
+@pytest.mark.parametrize('case', fc.NORM)
+def test_channelnorm_equals_reference_kernel(case, gold):
+    x, go = fc.norm_inputs(case)
+    t = _t(x).requires_grad_()
+    out = ops.ChannelNorm()(t)
+    fc.compare(gold, fc.key('norm_fwd', case), out.detach().cpu().numpy(), rtol=1e-6, atol=1e-7)
+    out.backward(_t(go))
+    fc.compare(gold, fc.key('norm_bwd', case), t.grad.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize('case', fc.WARP_FWD[:2])
+def test_fused_warp_diff_norm_equals_reference_kernel_chain(case, gold):
+    img, flow, _ = fc.warp_inputs(case)
+    img0 = np.random.RandomState(5000 + sum(int(v) for v in case[:4])).rand(*img.shape).astype(np.float32)
+    _, _, norm = ops.warp_diff_norm(_t(img0), _t(img), _t(flow))
+    fc.compare(gold, fc.key('chain_norm', case), norm.cpu().numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_live_against_recompiled_reference_kernels_at_configs4_size():
+    """BASELINE.json configs[4] at full size, element for element, against the reference kernels run live next to ours (the
+    recompiled reference library travels to the GPU box inside oracle/_ref; skipped only where it was never built)."""
+    from oracle import ref_ops
+    if not ref_ops.available():
+        pytest.skip('oracle/_ref/libref_ops.so not built (needs /root/reference at build time)')
+    g = torch.Generator().manual_seed(12)
+    f1, f2 = torch.randn(2, 256, 55, 128, generator=g).cuda(), torch.randn(2, 256, 55, 128, generator=g).cuda()
+    got = ops.Correlation(20, 1, 20, 1, 2, 1)(f1, f2)
+    want = ref_ops.correlation_forward(f1, f2, 20, 1, 20, 1, 2)
+    torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-5)
+    img0, img1 = torch.rand(2, 3, 436, 1024, generator=g).cuda(), torch.rand(2, 3, 436, 1024, generator=g).cuda()
+    flow = (torch.randn(2, 2, 436, 1024, generator=g) * 4).cuda()
+    w_ref = ref_ops.resample2d_forward(img1, flow)
+    torch.testing.assert_close(ops.Resample2d()(img1, flow), w_ref, rtol=1e-6, atol=1e-7)
+    n_ref = ref_ops.channelnorm_forward((img0 - w_ref).contiguous())
+    warped, diff, norm = ops.warp_diff_norm(img0, img1, flow)
+    torch.testing.assert_close(warped, w_ref, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(norm, n_ref, rtol=1e-5, atol=1e-6)

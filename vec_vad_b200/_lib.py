@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -23,7 +23,8 @@ SYMBOLS = [
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
     'vecvad_net_create', 'vecvad_net_destroy', 'vecvad_net_workspace_bytes', 'vecvad_net_bind',
     'vecvad_net_forward', 'vecvad_net_backward', 'vecvad_net_losses', 'vecvad_adam_step',
-    'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_cubes_to_tensors',
+    'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
+    'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
 ]
 
 
@@ -81,6 +82,10 @@ def lib():
     L.vecvad_net_debug_read.argtypes = [p, i, i, p, i64, C.POINTER(i64), p]
     L.vecvad_conv3x3_forward.argtypes = [p, i, p, p, p, p, p, i, i, i, i, i, i, p]
     L.vecvad_conv3x3_wgrad.argtypes = [p, i, p, p, p, i, i, i, i, i, i, p]
+    L.vecvad_conv3x3_dgrad.argtypes = [p, p, p, p, i, i, i, i, i, i, p]
+    L.vecvad_convt3x3s2_forward.argtypes = [p, p, p, p, i, i, p, i, i, i, i, i, i, p]
+    L.vecvad_convt3x3s2_dgrad.argtypes = [p, i, i, p, p, p, i, i, i, i, i, i, p]
+    L.vecvad_convt3x3s2_wgrad.argtypes = [p, p, i, i, p, p, i, i, i, i, i, i, p]
     L.vecvad_cubes_to_tensors.argtypes = [p, p, p, p, i, i, i, i, p]
     if L.vecvad_abi_version() != ABI_VERSION:
         raise RuntimeError('vec_vad_b200: libvecvad.so ABI %d != binding ABI %d -- rebuild' % (L.vecvad_abi_version(), ABI_VERSION))

@@ -140,16 +140,16 @@ VvTaps taps2x2(int sign) {
 // algorithmic FLOPs of one contraction launch: 2 * pixels * N * K * taps over all groups
 double igemm_flops(int B, int H, int W, int N, int K, int taps, int G) { return 2.0 * B * H * W * (double)N * K * taps * G; }
 
-int run_igemm(const vecvad_net *n, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
-    const bool tc = n->cfg.use_tensor_cores && vv_igemm_tc_supported(p);
+int run_igemm(bool want_tc, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
+    const bool tc = want_tc && vv_igemm_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_igemm_flat_supported(p)) return vv_launch_igemm_flat(p, st);
     if (tc && vv_igemm_tc3_supported(p)) return vv_launch_igemm_tc3(p, st);
     if (tc) return vv_igemm_tc2_supported(p) ? vv_launch_igemm_tc2(p, st) : vv_launch_igemm_tc(p, st);
     return vv_launch_igemm_simt(p, st);
 }
-int run_wgrad(const vecvad_net *n, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
-    const bool tc = n->cfg.use_tensor_cores && vv_wgrad_tc_supported(p);
+int run_wgrad(bool want_tc, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
+    const bool tc = want_tc && vv_wgrad_tc_supported(p);
     VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_wgrad_flat_supported(p)) return vv_launch_wgrad_flat(p, st);
     if (tc) return vv_wgrad_tc2_supported(p) ? vv_launch_wgrad_tc2(p, st) : vv_launch_wgrad_tc(p, st);
@@ -366,7 +366,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         p.bias = n->vec[u]; p.bias_gs = 3LL * N;
         p.stats = training ? n->stats[u] : nullptr; p.stats_gs = 2LL * N;
         p.G = G;
-        int r = run_igemm(n, p, st, n->uC[u]);
+        int r = run_igemm(n->cfg.use_tensor_cores != 0, p, st, n->uC[u]);
         if (r) return r;
         VvProfScope ps(VV_PROF_BN, 0, st);
         VvBnApply q;
@@ -393,7 +393,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         p.O = o.p; p.o_gs = o.gs; p.ldo = o.ld; p.o_coff = o.coff; p.o_d2s = 1;
         p.bias = n->tvec[k]; p.bias_gs = n->tCo[k];
         p.stats = nullptr; p.G = G;
-        return run_igemm(n, p, st);
+        return run_igemm(n->cfg.use_tensor_cores != 0, p, st);
     };
     int r;
     for (int u = 0; u < 8; u++) if ((r = conv_unit(u))) return r;
@@ -533,7 +533,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
         w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
         if ((rr = fork())) return rr;
-        if ((rr = run_wgrad(n, w, sB, n->uC[u]))) return rr;
+        if ((rr = run_wgrad(n->cfg.use_tensor_cores != 0, w, sB, n->uC[u]))) return rr;
         if (!batched_scatter &&
             (rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, sB)))
             return rr;
@@ -549,7 +549,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             p.O = din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
             p.bias = nullptr; p.stats = nullptr; p.G = G;
             if ((rr = before_write(din->p))) return rr;
-            if ((rr = run_igemm(n, p, st))) return rr;
+            if ((rr = run_igemm(n->cfg.use_tensor_cores != 0, p, st))) return rr;
         }
         return 0;
     };
@@ -568,7 +568,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.Gd = dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
         w.taps = t2f; w.dW = n->tdW[k]; w.dw_gs = 16LL * Co * Ci; w.G = G;
         if ((rr = fork())) return rr;
-        if ((rr = run_wgrad(n, w, sB))) return rr;
+        if ((rr = run_wgrad(n->cfg.use_tensor_cores != 0, w, sB))) return rr;
         if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, sB))) return rr;
         if ((rr = mark(nullptr))) return rr;
         VvIGemm p;
@@ -579,7 +579,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         p.O = ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
         p.bias = nullptr; p.stats = nullptr; p.G = G;
         if ((rr = before_write(ddeep.p))) return rr;
-        return run_igemm(n, p, st);
+        return run_igemm(n->cfg.use_tensor_cores != 0, p, st);
     };
 
     // ---- decoder, deepest last.  GA holds dU3 now.
@@ -708,6 +708,91 @@ extern "C" int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *gra
     VvIntG slot;
     memset(&slot, 0, sizeof(slot));
     return vv_scatter_conv_wgrad(scratch, 0, cout, cin, cin, dw, slot, 0, 0, 1, st);
+}
+
+// ---- single-op export: input gradient of the 3x3 pad-1 convolution (the engine's dgrad launch: flipped taps, Wd operand)
+extern "C" int vecvad_conv3x3_dgrad(const float *grad_out, const float *w, float *grad_in, float *scratch, int batch, int h, int wd, int cin,
+                                    int cout, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(grad_out && w && grad_in && scratch, "conv3x3_dgrad: null argument");
+    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "conv3x3_dgrad: cin/cout must be multiples of 16");
+    cudaStream_t st = (cudaStream_t)stream;
+    VvIntG slot;
+    memset(&slot, 0, sizeof(slot));
+    float *Wf = scratch, *Wd = scratch + 9LL * cout * cin;
+    int r = vv_prep_conv_w(w, slot, 0, 0, 0, 0, 0, cout, cin, cin, Wf, 0, Wd, 0, nullptr, 0, 1, st);
+    if (r) return r;
+    VvIGemm p;
+    memset(&p, 0, sizeof(p));
+    p.A = grad_out; p.lda = cout; p.Kt = cout; p.B = batch; p.H = h; p.W = wd;
+    p.Wt = Wd; p.taps = taps3x3(-1); p.N = cin;
+    p.O = grad_in; p.ldo = cin; p.G = 1;
+    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_dgrad: shape not supported by the tcgen05 path");
+    return run_igemm(use_tc != 0, p, st);
+}
+
+// ---- single-op exports: ConvTranspose2d(k3, s2, p1, output_padding 1) as the engine runs it (model/unet.py:54): four sub-pixel
+// phases = a 2x2-tap conv over N = 4*Co columns whose epilogue pixel-shuffles into a [B,2H,2W,ld_out] tensor at channel out_coff.
+// scratch: 32*Co*Ci + Co floats (forward / dgrad) or 48*Co*Ci + Co (wgrad).
+static int ct_prep(const float *w, const float *bias, int ci, int co, float *scratch, cudaStream_t st, float **Wf, float **Wd, float **vec) {
+    VvIntG slot;
+    memset(&slot, 0, sizeof(slot));
+    *Wf = scratch; *Wd = scratch + 16LL * co * ci; *vec = scratch + 32LL * co * ci;
+    // vv_prep_ct_w reads weight and bias at offsets of one base pointer
+    return vv_prep_ct_w(w, slot, 0, 0, bias ? (long long)(bias - w) : 0, ci, co, *Wf, 0, *Wd, 0, *vec, 0, 1, st);
+}
+
+extern "C" int vecvad_convt3x3s2_forward(const float *in, const float *w, const float *bias, float *out, int ld_out, int out_coff,
+                                         float *scratch, int batch, int h, int wd, int ci, int co, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(in && w && bias && out && scratch, "convt_forward: null argument");
+    VV_REQUIRE(ci % 32 == 0 && co % 16 == 0 && ld_out >= out_coff + co, "convt_forward: bad channel counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *Wf, *Wd, *vec;
+    int r = ct_prep(w, bias, ci, co, scratch, st, &Wf, &Wd, &vec);
+    if (r) return r;
+    VvIGemm p;
+    memset(&p, 0, sizeof(p));
+    p.A = in; p.lda = ci; p.Kt = ci; p.B = batch; p.H = h; p.W = wd;
+    p.Wt = Wf; p.taps = taps2x2(+1); p.N = 4 * co;
+    p.O = out; p.ldo = ld_out; p.o_coff = out_coff; p.o_d2s = 1;
+    p.bias = vec; p.G = 1;
+    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "convt_forward: shape not supported by the tcgen05 path");
+    return run_igemm(use_tc != 0, p, st);
+}
+
+extern "C" int vecvad_convt3x3s2_dgrad(const float *grad_out, int ld, int coff, const float *w, float *grad_in, float *scratch, int batch,
+                                       int h, int wd, int ci, int co, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(grad_out && w && grad_in && scratch, "convt_dgrad: null argument");
+    VV_REQUIRE(ci % 32 == 0 && co % 32 == 0 && ld >= coff + co, "convt_dgrad: bad channel counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    float *Wf, *Wd, *vec;
+    int r = ct_prep(w, nullptr, ci, co, scratch, st, &Wf, &Wd, &vec);
+    if (r) return r;
+    VvIGemm p;
+    memset(&p, 0, sizeof(p));
+    p.A = grad_out; p.lda = ld; p.a_coff = coff; p.a_s2d = 1; p.Kt = 4 * co; p.B = batch; p.H = h; p.W = wd;
+    p.Wt = Wd; p.taps = taps2x2(-1); p.N = ci;
+    p.O = grad_in; p.ldo = ci; p.G = 1;
+    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "convt_dgrad: shape not supported by the tcgen05 path");
+    return run_igemm(use_tc != 0, p, st);
+}
+
+extern "C" int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int coff, float *dw, float *scratch, int batch, int h,
+                                       int wd, int ci, int co, int use_tc, vecvad_stream stream) {
+    VV_REQUIRE(in && grad_out && dw && scratch, "convt_wgrad: null argument");
+    VV_REQUIRE(ci % 32 == 0 && co % 32 == 0 && ld >= coff + co, "convt_wgrad: bad channel counts");
+    cudaStream_t st = (cudaStream_t)stream;
+    VV_CK(cudaMemsetAsync(scratch, 0, 16LL * co * ci * sizeof(float), st));
+    VvWGrad w;
+    memset(&w, 0, sizeof(w));
+    w.A = in; w.lda = ci; w.Kt = ci; w.B = batch; w.H = h; w.W = wd;
+    w.Gd = grad_out; w.ldg = ld; w.g_coff = coff; w.g_s2d = 1; w.N = 4 * co;
+    w.taps = taps2x2(+1); w.dW = scratch; w.G = 1;
+    if (use_tc) VV_REQUIRE(vv_wgrad_tc_supported(w), "convt_wgrad: shape not supported by the tcgen05 path");
+    int r = run_wgrad(use_tc != 0, w, st);
+    if (r) return r;
+    VvIntG slot;
+    memset(&slot, 0, sizeof(slot));
+    return vv_scatter_ct_wgrad(scratch, 0, ci, co, dw, slot, 0, 0, 1, st);
 }
 
 extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
