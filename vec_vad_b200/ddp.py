@@ -15,11 +15,44 @@ import torch.distributed as dist
 
 
 def shard_bounds(n, rank, world):
-    """[begin, end) of rank's contiguous shard of n cubes; shard sizes differ by at most one (DataParallel's scatter
-    gives the first chunks ceil(n/world) items; the same rule is used here)."""
+    """[begin, end) of rank's contiguous shard of n items, chunks of ceil(n/world) like DataParallel's scatter
+    (torch.chunk): the LAST shards may be shorter or EMPTY (n=9, world=4 -> 3,3,3,0)."""
     chunk = (n + world - 1) // world
     b = min(n, rank * chunk)
     return b, min(n, b + chunk)
+
+
+def rank_batch_plan(n, batch_size, rank, world, seed=None, shuffle=True):
+    """This rank's share of every GLOBAL batch of one epoch over n cubes: [(index tensor (may be empty), global batch size)].
+
+    One permutation per epoch from a seed every rank shares (``shared_seed``), cut into global batches of ``batch_size``
+    (the last one ragged, like ``DataLoader(shuffle=True)``, train.py:373), each split over the ranks with ``shard_bounds``
+    exactly as ``nn.DataParallel`` scatters a batch (train.py:375).  Every rank therefore runs the SAME number of steps
+    (ceil(n / batch_size)) whatever n is, so the per-step gradient all-reduces always pair up; a rank whose share of a ragged
+    last batch is empty still takes part with a zero gradient."""
+    if shuffle:
+        g = torch.Generator().manual_seed(int(seed))
+        order = torch.randperm(n, generator=g)
+    else:
+        order = torch.arange(n)
+    plan = []
+    for i in range(0, n, batch_size):
+        glob = order[i:i + batch_size]
+        b, e = shard_bounds(glob.numel(), rank, world)
+        plan.append((glob[b:e], int(glob.numel())))
+    return plan
+
+
+def shared_seed(group=None):
+    """A fresh shuffle seed drawn on rank 0 (RandomSampler's own seeding) and broadcast, so all ranks cut the same batches."""
+    seed = torch.empty((), dtype=torch.int64).random_()
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = seed.reshape(1)
+        if dist.get_backend(group) == 'nccl':
+            t = t.cuda()
+        dist.broadcast(t, src=0, group=group)
+        seed = t.cpu()[0]
+    return int(seed.item())
 
 
 def init_from_env(backend=None):
@@ -46,10 +79,24 @@ class GradReducer:
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = bucket_bytes // 4
+        self.pre_weight = None
+
+    def set_batch(self, local_n, global_n):
+        """Tell the reducer how this step's global batch was split.  The global-batch mean gradient is
+        sum_r (local_n_r / global_n) * grad_r (each rank's loss is a mean over ITS cubes): with equal shares that is the plain
+        sum times 1/world (folded into Adam); with a ragged split every rank weights its gradient before the sum."""
+        self.pre_weight = None if global_n % self.world == 0 else float(local_n) / float(global_n)
 
     def __call__(self, flat):
         if self.world == 1:
             return 1.0
+        pre = self.pre_weight
+        if pre is not None:
+            flat.mul_(pre)
+        scale = 1.0 / self.world if pre is None else 1.0
+        return self._sum(flat, scale)
+
+    def _sum(self, flat, scale):
         if self.bucket_elems and flat.numel() > self.bucket_elems:
             # bucketed: lets NCCL pipeline the buckets; each is contiguous in the flat buffer
             works = [dist.all_reduce(flat[o:o + self.bucket_elems], group=self.group, async_op=True)
@@ -58,7 +105,7 @@ class GradReducer:
                 w.wait()
         else:
             dist.all_reduce(flat, group=self.group)
-        return 1.0 / self.world
+        return scale
 
 
 def broadcast_state(model, src=0, group=None):

@@ -265,16 +265,23 @@ def load_block_state(net, sd):
 
 
 def train_block(net, cube_batches, cfg, reducer, meters, tag):
-    """One model on one block: the hot loop of train.py:378-408.  ``cube_batches(epoch)`` yields device (x, x_of) batches."""
+    """One model on one block: the hot loop of train.py:378-408.  ``cube_batches(epoch)`` yields ``(x, x_of, local_n, global_n)``
+    for every GLOBAL batch (``DeviceCubeStore.rank_batches``); with several ranks every rank sees the same number of steps and
+    ``x`` is None where its share of a ragged last batch is empty."""
     net.train()
     net.init_adam(lr=1e-3, betas=(0.9, 0.999), eps=1e-7, weight_decay=0.0)       # optim.Adam(eps=1e-7, weight_decay=0.0), train.py:376
     raw_losses, of_losses = meters
     pending = []                                                                   # (device losses, batch size) since the last print
     for epoch in range(cfg.epochs):
         n_batches = 0
-        for idx, (x, x_of) in enumerate(cube_batches(epoch)):
-            losses = net.train_step(x, x_of, cfg.lambda_raw, cfg.lambda_of, reduce_grads=reducer)
-            pending.append((losses, x.shape[0]))
+        for idx, (x, x_of, local_n, global_n) in enumerate(cube_batches(epoch)):
+            if reducer is not None:
+                reducer.set_batch(local_n, global_n)
+            if x is None:
+                losses = net.train_step_empty(reducer)
+            else:
+                losses = net.train_step(x, x_of, cfg.lambda_raw, cfg.lambda_of, reduce_grads=reducer)
+            pending.append((losses, local_n))
             n_batches += 1
             if idx % 5 == 0:
                 for l, n in pending:
@@ -290,8 +297,9 @@ def train_block(net, cube_batches, cfg, reducer, meters, tag):
 
 
 @torch.no_grad()
-def score_block(net, store, batch_size):
-    """Per-cube sum of squared error over a cube store in order (train.py:412-431)."""
+def score_block(net, store, batch_size, useFlow=True):
+    """Per-cube sum of squared error over a cube store in order (train.py:412-431).  An empty store (a ShanghaiTech disk segment
+    without cubes for this block) yields empty score vectors instead of failing the concatenate."""
     net.eval()
     raw, of = [], []
     for x, x_of in store.batches(batch_size, shuffle=False):
@@ -299,12 +307,14 @@ def score_block(net, store, batch_size):
         raw.append(r.cpu().numpy())
         if o is not None:
             of.append(o.cpu().numpy())
+    if not raw:
+        return np.zeros((0,), dtype=np.float32), (np.zeros((0,), dtype=np.float32) if useFlow else [])
     return np.concatenate(raw, 0), (np.concatenate(of, 0) if of else [])
 
 
-def _rank_store(raw, flow, rank, world, device):
-    b, e = ddp.shard_bounds(len(raw), rank, world)
-    return vd.DeviceCubeStore(raw[b:e], flow[b:e], device=device)
+def _epoch_batches(store, cfg, rank, world):
+    """One epoch of global batches of ``cfg.batch_size`` cubes, this rank's share of each (all ranks: same step count)."""
+    return store.rank_batches(cfg.batch_size, rank, world, seed=ddp.shared_seed(), shuffle=True)
 
 
 def train(cfg_path='config.cfg', use_tensor_cores=True):
@@ -314,14 +324,25 @@ def train(cfg_path='config.cfg', use_tensor_cores=True):
     torch.cuda.set_device(device)
     probe = vd.unified_dataset_interface(cfg.dataset_name, os.path.join(cfg.raw_dataset_dir, cfg.dataset_name), context_frame_num=1,
                                          mode=cfg.mode, border_mode='hard')
-    all_bboxes = load_or_make_bboxes(cfg, probe)
+    # host-side preprocessing (box files, foreground cube extraction: minutes to hours of disk-bound work on real datasets) runs
+    # on rank 0 only; the others wait on a CPU (gloo) barrier with a day-long timeout instead of the NCCL watchdog's default
+    slow_group = None
+    if world > 1:
+        import datetime
+        slow_group = torch.distributed.new_group(backend='gloo', timeout=datetime.timedelta(hours=24))
+    if rank == 0 or cfg.bbox_saved:
+        all_bboxes = load_or_make_bboxes(cfg, probe)
+    if world > 1 and not cfg.bbox_saved:
+        torch.distributed.barrier(group=slow_group)
+        if rank != 0:
+            all_bboxes = np.load(os.path.join(probe.dir, 'bboxes_{}_{}.npy'.format(cfg.mode, cfg.foreground_extraction_mode)), allow_pickle=True)
     sh = cfg.dataset_name == 'ShanghaiTech'
     m = cfg.foreground_extraction_mode
     if not cfg.foreground_saved:
         if rank == 0:
             extract_foreground_train(cfg, all_bboxes)
         if world > 1:
-            torch.distributed.barrier()
+            torch.distributed.barrier(group=slow_group)
     net = build_network(cfg, use_tensor_cores=use_tensor_cores).to(device)     # ONE instance shared by every block, like the reference
     ddp.broadcast_state(net)
     reducer = ddp.GradReducer() if world > 1 else None
@@ -343,19 +364,26 @@ def train(cfg_path='config.cfg', use_tensor_cores=True):
 
                     def batches(epoch, s=s, hh=hh, ww=ww):
                         for si in range(tot_seg):        # segments streamed from disk every epoch (train.py:293-299)
-                            store = _rank_store(seg(si, 'raw')[s][hh][ww], seg(si, 'flow')[s][hh][ww], rank, world, device)
-                            yield from store.batches(max(1, cfg.batch_size // world), shuffle=True)
+                            raw_seg = seg(si, 'raw')[s][hh][ww]
+                            if len(raw_seg) == 0:        # a segment without cubes for this block: nothing to train on
+                                continue
+                            store = vd.DeviceCubeStore(raw_seg, seg(si, 'flow')[s][hh][ww], device=device)
+                            yield from _epoch_batches(store, cfg, rank, world)
                     train_block(net, batches, cfg, reducer, meters, (s, hh, ww))
                     model_set[s][hh][ww].append(_state_dict_for_disk(net))
                     for si in range(tot_seg):
-                        store = vd.DeviceCubeStore(seg(si, 'raw')[s][hh][ww], seg(si, 'flow')[s][hh][ww], device=device)
-                        r, o = score_block(net, store, cfg.batch_size)
+                        raw_seg = seg(si, 'raw')[s][hh][ww]
+                        if len(raw_seg) == 0:            # the reference concatenates only what the segments hold
+                            continue
+                        store = vd.DeviceCubeStore(raw_seg, seg(si, 'flow')[s][hh][ww], device=device)
+                        r, o = score_block(net, store, cfg.batch_size, cfg.useFlow)
                         raw_scores_set[s][hh][ww].append(r)
                         if cfg.useFlow:
                             of_scores_set[s][hh][ww].append(o)
-                    raw_scores_set[s][hh][ww] = np.concatenate(raw_scores_set[s][hh][ww], axis=0)
-                    if cfg.useFlow:
-                        of_scores_set[s][hh][ww] = np.concatenate(of_scores_set[s][hh][ww], axis=0)
+                    if raw_scores_set[s][hh][ww]:
+                        raw_scores_set[s][hh][ww] = np.concatenate(raw_scores_set[s][hh][ww], axis=0)
+                        if cfg.useFlow:
+                            of_scores_set[s][hh][ww] = np.concatenate(of_scores_set[s][hh][ww], axis=0)
     else:
         fs = np.load(cfg.path('foreground_train_{}-raw.npy'.format(m)), allow_pickle=True)
         fs2 = np.load(cfg.path('foreground_train_{}-flow.npy'.format(m)), allow_pickle=True)
@@ -366,12 +394,10 @@ def train(cfg_path='config.cfg', use_tensor_cores=True):
         for hh in range(len(fs)):
             for ww in range(len(fs[hh])):
                 if len(fs[hh][ww]) > 1:                   # "num > 1 for data parallel" (train.py:370)
-                    store = _rank_store(fs[hh][ww], fs2[hh][ww], rank, world, device)
-                    train_block(net, lambda epoch, store=store: store.batches(max(1, cfg.batch_size // world), shuffle=True), cfg, reducer,
-                                meters, (hh, ww))
+                    store = vd.DeviceCubeStore(fs[hh][ww], fs2[hh][ww], device=device)     # the whole block on every rank
+                    train_block(net, lambda epoch, store=store: _epoch_batches(store, cfg, rank, world), cfg, reducer, meters, (hh, ww))
                     model_set[hh][ww].append(_state_dict_for_disk(net))
-                    full = store if world == 1 else vd.DeviceCubeStore(fs[hh][ww], fs2[hh][ww], device=device)
-                    raw_scores_set[hh][ww], of_scores_set[hh][ww] = score_block(net, full, cfg.batch_size)
+                    raw_scores_set[hh][ww], of_scores_set[hh][ww] = score_block(net, store, cfg.batch_size, cfg.useFlow)
     if rank == 0:
         torch.save(raw_scores_set, cfg.path('raw_training_scores_{}.npy'.format(cfg.tag())))
         torch.save(of_scores_set, cfg.path('of_training_scores_{}.npy'.format(cfg.tag())))

@@ -603,6 +603,24 @@ class CompletionNet(nn.Module):
                                       _lib.cur_stream()), 'adam_step')
         return losses
 
+    def train_step_empty(self, reduce_grads):
+        """A data-parallel step for a rank whose share of a ragged last batch is EMPTY: no forward / backward, a zero gradient
+        into the collective, then the same Adam update as every other rank (the replicas must stay identical).  BatchNorm
+        running statistics are not touched (no batch was seen), like a DataParallel replica that received no chunk."""
+        if self._adam is None:
+            self.init_adam()
+        _lib.require_cuda(self._pflat)
+        if self._gflat is None:
+            self._gflat = torch.zeros_like(self._pflat)
+        self._gflat.zero_()
+        scale = float(reduce_grads(self._gflat)) if reduce_grads is not None else 1.0
+        a = self._adam
+        a['step'] += 1
+        _lib.check(_lib.lib().vecvad_adam_step(_lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(a['m']), _lib.ptr(a['v']),
+                                               self._pflat.numel(), a['lr'], a['b1'], a['b2'], a['eps'], a['wd'], a['step'], scale,
+                                               _lib.cur_stream()), 'adam_step')
+        return torch.zeros(2, dtype=torch.float32, device=self._pflat.device)
+
     @property
     def flat_params(self):
         return self._pflat

@@ -401,3 +401,17 @@ class DeviceCubeStore:
             if drop_last and idx.numel() < batch_size:
                 return
             yield cubes_to_device_tensors(self.raw.index_select(0, idx), self.flow.index_select(0, idx))
+
+    def rank_batches(self, batch_size, rank, world, seed=None, shuffle=True):
+        """Multi-process feed: yields ``(x, x_of, local_n, global_n)`` for EVERY global batch of the epoch (``ddp.rank_batch_plan``:
+        one shared permutation, each global batch split over the ranks like DataParallel's scatter).  ``x`` is None when this
+        rank's share of a ragged last batch is empty -- the caller must still take part in that step's gradient reduction.
+        The store holds the whole block on every rank (15 KB + 8..40 KB per STC)."""
+        from . import ddp
+        for idx, global_n in ddp.rank_batch_plan(len(self), batch_size, rank, world, seed=seed, shuffle=shuffle):
+            if idx.numel() == 0:
+                yield None, None, 0, global_n
+                continue
+            idx = idx.to(self.raw.device)
+            x, x_of = cubes_to_device_tensors(self.raw.index_select(0, idx), self.flow.index_select(0, idx))
+            yield x, x_of, int(idx.numel()), global_n
