@@ -138,7 +138,8 @@ def run_ours(args):
     kind, kw, t_of = NET_KW[args.net]
     cls = {'net4': vu.SelfCompleteNet4, 'full': vu.SelfCompleteNetFull}[kind]
     torch.manual_seed(0)
-    model = cls(use_tensor_cores=not args.simt, **kw).cuda().train()
+    prec = 0 if args.simt else {'tf32': 1, 'f16': 2}[args.precision]
+    model = cls(use_tensor_cores=prec, **kw).cuda().train()
     model.init_adam(lr=1e-3, eps=1e-7)
     B, P = args.batch, args.pool
     g = torch.Generator().manual_seed(1234 + rank)
@@ -214,7 +215,7 @@ def run_ours(args):
         tf32 = not args.simt
         line = {'metric': METRIC, 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': 'tf32' if tf32 else 'f32', 'data': 'synthetic',
+                'dtype': (args.precision if tf32 else 'f32'), 'data': 'synthetic',
                 'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': B, 'global_batch': world * B,
                            'parallelism': 'dp%d' % world, 'input_pool_batches': P,
                            'l2': 'per-step working set (activations + gradients, >3 GB at batch 128) exceeds the 126 MB L2; inputs rotate over %d batches' % P,
@@ -254,7 +255,8 @@ def main():
     ap.add_argument('--net', default='net4', choices=sorted(NET_KW))
     ap.add_argument('--batch', type=int, default=128, help='cubes per GPU per step')
     ap.add_argument('--pool', type=int, default=8, help='distinct input batches rotated through')
-    ap.add_argument('--simt', action='store_true', help='fp32 SIMT tiles instead of tcgen05 tf32 tiles')
+    ap.add_argument('--simt', action='store_true', help='fp32 SIMT tiles instead of tcgen05 tiles')
+    ap.add_argument('--precision', default='f16', choices=['tf32', 'f16'], help='operand type of the tcgen05 tiles (fp32 accumulation either way)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':

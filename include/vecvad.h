@@ -129,7 +129,11 @@ typedef struct vecvad_net_config {
     int64_t up_w[VECVAD_N_UPS], up_b[VECVAD_N_UPS];
     int64_t out_w, out_b;
     int64_t run_mean[VECVAD_N_UNITS], run_var[VECVAD_N_UNITS];
-    int use_tensor_cores;                     /* 1: tcgen05 kind::tf32 implicit-GEMM tiles; 0: fp32 SIMT tiles   */
+    int use_tensor_cores;                     /* 0: fp32 SIMT tiles; 1: tcgen05 kind::tf32 implicit-GEMM tiles (fp32 tensors in HBM, operands
+                                               * rounded to tf32 on their way into shared memory); 2: tcgen05 kind::f16 tiles: post-BN
+                                               * activations, dZ gradients and re-laid-out weights are stored as fp16 in HBM (the same 10-bit
+                                               * mantissa, rounded once where they are produced), accumulation, BatchNorm statistics, raw conv
+                                               * outputs, losses and the optimiser stay fp32 */
     /* A UNet set may be split over several nets (one per stream) that share the flat buffers and the output tensors:
      * the loss means and the external gradient tensors then span ALL raw / flow outputs, not only this net's.
      * 0 = this net's own count. */
@@ -166,6 +170,12 @@ int vecvad_net_forward(vecvad_net *net, const float *x, const float *x_of, int x
  * Writes (overwrites) every gradient of the executed UNets into the bound `grads` buffer. */
 int vecvad_net_backward(vecvad_net *net, const float *grad_raw_out, const float *grad_of_out, vecvad_stream stream);
 
+/* fp16-operand mode only: the power-of-two loss scale the backward applies to the dZ operands it stores as fp16 (and removes again
+ * from every parameter gradient it writes).  scale <= 0 (default): derived per step from the MSE-gradient coefficients of the last
+ * forward (2*lambda / elements), which suits gradients of the size the MSE losses of train.py:385-392 produce; pass an explicit
+ * power of two when external output gradients of a very different magnitude are fed to vecvad_net_backward. */
+int vecvad_net_set_loss_scale(vecvad_net *net, float scale);
+
 /* losses[0] = mean raw MSE, losses[1] = mean flow MSE (0 if no flow UNet) from the sse buffer of the last forward. */
 int vecvad_net_losses(vecvad_net *net, const float *sse, int batch, float *losses, vecvad_stream stream);
 
@@ -175,28 +185,28 @@ int vecvad_net_losses(vecvad_net *net, const float *sse, int batch, float *losse
 int vecvad_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, vecvad_stream stream);
 
-/* debug / test facility: copy an internal workspace buffer (device to device) into dst.  kind: 0 X0, 1 Z[u], 2 A[u] (even u),
- * 3 CAT[k], 4 PL[k], 5 X4, 6 UU[k], 7 dCAT[k], 8 GA, 9 GB, 10 DOUT, 11 Wf[u], 12 dWf[u], 13 tWf[k], 14 tdW[k].
- * Buffers are grouped NHWC [G][B*H*W][C] of the last forward; *n_floats receives the element count copied. */
+/* debug / test facility: copy an internal workspace buffer (device to device) into dst as fp32.  kind: 0 X0, 1 Z[u], 2 A[u] (even u),
+ * 3 CAT[k], 4 PL[k], 5 X4, 6 UU[k], 7 dCAT[k], 8 GA, 9 GB, 10 DOUT, 11 Wf[u], 12 dWf[u], 13 tWf[k], 14 tdW[k], 15 dUP[k] and
+ * 16 dZ ring buffer k (fp16 mode only).  Buffers are grouped NHWC [G][B*H*W][C] of the last forward; fp16 buffers of the fp16 mode
+ * are converted; *n_floats receives the element count copied. */
 int vecvad_net_debug_read(vecvad_net *net, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
                           vecvad_stream stream);
 
 /* ---- single ops on NHWC tensors, exported for unit tests and for profiling one kernel at a time ---- */
 
+/* use_tc of every single op: 0 = fp32 SIMT tiles; low four bits 1 = the tcgen05 tile the net engine picks for the shape,
+ * 3 = flattened-sequence tiles (what the engine uses at >= 32 pixels per row), 4 (forward / dgrad) or 2 (wgrad) = pair / tap-reuse
+ * tiles (what it uses below that); + 16 = fp16 operands (kind::f16, fp32 accumulation): inputs are converted to fp16 inside the
+ * call into stream-ordered temporaries, outputs stay fp32. */
+
 /* 3x3 pad-1 convolution as implicit GEMM.  in [B,H,W,cin] (row stride ld_in), w [cout,cin,3,3] PyTorch layout,
  * out [B,H,W,cout] raw (pre-BN) values; stats[2*cout] (double) receives per-channel sum and sum of squares
- * (may be NULL).  scratch: >= 9*cout*cin floats. use_tc: 0 fp32 SIMT tiles, 1 tcgen05 per-tap tiles,
- * 2 tcgen05 persistent tap-reuse tiles, 3 flattened-sequence tiles (the net's choice at >= 32 pixels per row, needs the nine
- * weight tiles of an output tile within 72 KB), 4 pair tiles (the net's choice below that), 5 flattened-sequence tiles with fp16
- * operands and fp32 accumulation, 6 the same for the pair tiles (experiments: input and weights are converted inside the call and
- * scratch must hold 9*cout*cin floats + 9*cout*cin halfs (rounded up to 256 bytes) + batch*h*wd*cin halfs; 6 has not run on a
- * device yet). */
+ * (may be NULL).  scratch: >= 9*cout*cin floats. */
 int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
                            float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream);
 
 /* weight gradient of the same convolution: dw [cout,cin,3,3] (PyTorch layout, overwritten) from in [B,H,W,cin] and
- * grad_out [B,H,W,cout] (NHWC, dense).  scratch: >= 9*cout*cin floats.  use_tc: 0 fp32 SIMT tiles, 1 tcgen05 per-tap tiles,
- * 2 tcgen05 tap-reuse tiles, 3 flattened-sequence tiles (one MMA per K-step covers all nine taps; cout a multiple of 32). */
+ * grad_out [B,H,W,cout] (NHWC, dense).  scratch: >= 9*cout*cin floats. */
 int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
                          int cin, int cout, int use_tc, vecvad_stream stream);
 

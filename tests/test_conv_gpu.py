@@ -1,7 +1,7 @@
-"""Single-op parity: the 3x3 pad-1 convolution tiles (fp32 SIMT and tcgen05 tf32; use_tc 1 = per-tap tiles, 2 = persistent
-per-dx-box tiles, 3 = flattened-sequence tiles, 4 = pair tiles) through the C ABI entry point
-vecvad_conv3x3_forward, against torch.nn.functional.conv2d in float64 on the CPU (the same op the reference calls:
-model/unet.py:10,13).  Tolerances: fp32 tiles 1e-5 of the output range; tf32 tiles 2e-3 (10-bit mantissa operands)."""
+"""Single-op parity: the 3x3 pad-1 convolution tiles through the C ABI entry point vecvad_conv3x3_forward, against
+torch.nn.functional.conv2d in float64 on the CPU (the same op the reference calls: model/unet.py:10,13).
+use_tc: 0 = fp32 SIMT tiles, 1 = the tcgen05 tile the engine picks, 3 = flattened-sequence tiles, 4 = pair tiles, +16 = fp16 operands
+(kind::f16) instead of tf32.  Tolerances: fp32 tiles 1e-5 of the output range; tf32 / fp16 tiles 2e-3 (10-bit mantissa operands)."""
 import ctypes as C
 
 import numpy as np
@@ -31,7 +31,7 @@ SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (5, 16, 16, 32, 64), (3, 8, 
           (1, 8, 8, 256, 128), (2, 16, 16, 128, 64)]
 
 
-@pytest.mark.parametrize('use_tc', [0, 1, 2, 4])
+@pytest.mark.parametrize('use_tc', [0, 1, 4, 17, 20])
 @pytest.mark.parametrize('shape', SHAPES + [(130, 32, 32, 32, 32), (70, 16, 16, 64, 64), (150, 4, 4, 256, 256)])
 def test_conv3x3_forward(shape, use_tc):
     b, h, wd, cin, cout = shape
@@ -72,29 +72,22 @@ def test_conv3x3_forward_flat(shape):
     np.testing.assert_allclose(s[:cout], want.sum(dim=(0, 1, 2)).numpy(), rtol=0, atol=2e-3 * want.abs().sum(dim=(0, 1, 2)).max().item())
     np.testing.assert_allclose(s[cout:], (want ** 2).sum(dim=(0, 1, 2)).numpy(), rtol=1e-2)
     # same operands, same tf32 rounding, fp32 accumulation in a different order: the two tcgen05 paths agree far below tf32 error
-    ref2, _ = conv3x3(xn, w.cuda(), bias.cuda(), 2)
+    ref2, _ = conv3x3(xn, w.cuda(), bias.cuda(), 4)
     assert (got - ref2).abs().max().item() <= 2e-5 * want.abs().max().item()
 
 
 @pytest.mark.parametrize('shape', [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (2, 32, 32, 32, 64), (37, 32, 32, 32, 32), (5, 16, 16, 32, 64)])
 def test_conv3x3_forward_flat_fp16_operands(shape):
-    """use_tc 5: the flattened-sequence tiles with fp16 operands (kind::f16, fp32 accumulation; DESIGN.md section 8).  fp16 carries
-    tf32's 10-bit mantissa, so the bound is the tf32 one; operands are converted inside the call (larger scratch)."""
+    """use_tc 16+3: the flattened-sequence tiles with fp16 operands (kind::f16, fp32 accumulation).  fp16 carries tf32's 10-bit
+    mantissa, so the bound is the tf32 one."""
     b, h, wd, cin, cout = shape
     g = torch.Generator().manual_seed(sum(shape) + 11)
     x = torch.randn(b, cin, h, wd, generator=g)
     w = torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)
     bias = torch.randn(cout, generator=g)
     want = F.conv2d(x.double(), w.double(), bias.double(), padding=1).permute(0, 2, 3, 1).contiguous()
-    xn, wc, bc = x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), bias.cuda()      # keep the device tensors alive across the call
-    out = torch.empty((b, h, wd, cout), device='cuda')
-    stats = torch.zeros(2 * cout, dtype=torch.float64, device='cuda')
-    scratch = torch.empty(9 * cout * cin + (9 * cout * cin) // 2 + 64 + (b * h * wd * cin) // 2 + 64, device='cuda')
-    rc = _lib.lib().vecvad_conv3x3_forward(_lib.ptr(xn), cin, _lib.ptr(wc), _lib.ptr(bc), _lib.ptr(out), _lib.ptr(stats),
-                                           _lib.ptr(scratch), b, h, wd, cin, cout, 5, _lib.cur_stream())
-    _lib.check(rc, 'conv3x3_forward')
-    torch.cuda.synchronize()
-    err = (out.cpu().double() - want).abs().max().item() / want.abs().max().item()
+    got, stats = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), bias.cuda(), 19)
+    err = (got.cpu().double() - want).abs().max().item() / want.abs().max().item()
     assert err < 2e-3, err
     np.testing.assert_allclose(stats.cpu().numpy()[:cout], want.sum(dim=(0, 1, 2)).numpy(), rtol=0,
                                atol=2e-3 * want.abs().sum(dim=(0, 1, 2)).max().item())
@@ -107,7 +100,7 @@ def test_tf32_error_is_unbiased():
     x = torch.rand(4, 64, 16, 16, generator=g) + 0.5
     w = torch.rand(64, 64, 3, 3, generator=g) + 0.5
     want = F.conv2d(x.double(), w.double(), None, padding=1).permute(0, 2, 3, 1)
-    got, _ = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, 2, want_stats=False)
+    got, _ = conv3x3(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), None, 4, want_stats=False)
     rel = ((got.cpu().double() - want) / want)
     assert abs(rel.mean().item()) < 1e-4, rel.mean().item()
 
@@ -117,8 +110,8 @@ WGRAD_FLAT_SHAPES = [(2, 32, 32, 32, 32), (3, 32, 32, 64, 32), (130, 32, 32, 32,
                      (1, 32, 32, 32, 32), (37, 8, 8, 64, 32)]
 
 
-@pytest.mark.parametrize('use_tc,shape', [(t, s) for t in (0, 1, 2) for s in SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32), (130, 32, 32, 32, 32),
-                                                                                     (3, 8, 8, 32, 64)]] + [(3, s) for s in WGRAD_FLAT_SHAPES])
+@pytest.mark.parametrize('use_tc,shape', [(t, s) for t in (0, 1, 2, 17, 18) for s in SHAPES + [(7, 4, 4, 128, 256), (37, 4, 4, 32, 32), (130, 32, 32, 32, 32),
+                                                                                           (3, 8, 8, 32, 64)]] + [(t, s) for t in (3, 19) for s in WGRAD_FLAT_SHAPES])
 def test_conv3x3_wgrad(shape, use_tc):
     """dW of the convolution = autograd of conv2d (what loss.backward() computes in train.py:401)."""
     b, h, wd, cin, cout = shape
@@ -141,7 +134,7 @@ def test_conv3x3_wgrad(shape, use_tc):
 # ---------------------------------------------------------------------------------------------------------------------------
 # Input-gradient (flipped taps) and transposed-conv tiles, one op at a time through the C ABI, against float64 autograd of the
 # PyTorch ops the reference calls (conv2d: model/unet.py:10,13; ConvTranspose2d(k3, s2, p1, output_padding 1): model/unet.py:54).
-# use_tc 1 = the tcgen05 tile the engine picks for the shape, 0 = fp32 SIMT tiles.  Shapes: the net's own layers (ragged batches).
+# use_tc 1 = the tcgen05 tile the engine picks for the shape (17: with fp16 operands), 0 = fp32 SIMT tiles.  Shapes: the net's own layers (ragged batches).
 # ---------------------------------------------------------------------------------------------------------------------------
 DGRAD_SHAPES = [(3, 32, 32, 32, 32), (2, 32, 32, 32, 64), (5, 16, 16, 64, 64), (3, 16, 16, 32, 64), (7, 8, 8, 128, 128), (5, 8, 8, 64, 128),
                 (9, 4, 4, 256, 256), (37, 4, 4, 128, 256), (130, 32, 32, 32, 32), (3, 8, 8, 256, 128), (2, 16, 16, 128, 64)]
@@ -151,7 +144,7 @@ def _tol(use_tc):
     return 3e-3 if use_tc else 2e-5
 
 
-@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('use_tc', [0, 1, 17])
 @pytest.mark.parametrize('shape', DGRAD_SHAPES)
 def test_conv3x3_dgrad(shape, use_tc):
     b, h, wd, cin, cout = shape
@@ -187,7 +180,7 @@ def _ct_reference(shape, seed):
     return x, w, bias, go, out.detach(), xd.grad, wdd.grad
 
 
-@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('use_tc', [0, 1, 17])
 @pytest.mark.parametrize('shape', CT_SHAPES)
 def test_conv_transpose_forward_into_concat_half(shape, use_tc):
     """Output lands pixel-shuffled in channels [co, 2co) of a [B,2H,2W,2co] concat buffer (torch.cat([skip, up]), model/unet.py:59);
@@ -206,7 +199,7 @@ def test_conv_transpose_forward_into_concat_half(shape, use_tc):
     assert torch.all(cat[..., :co] == 7.0)
 
 
-@pytest.mark.parametrize('use_tc', [0, 1])
+@pytest.mark.parametrize('use_tc', [0, 1, 17])
 @pytest.mark.parametrize('shape', CT_SHAPES)
 def test_conv_transpose_input_and_weight_gradients(shape, use_tc):
     b, h, wd, ci, co = shape

@@ -93,3 +93,77 @@ def test_two_rank_gradient_equals_global_batch_gradient():
     np.testing.assert_allclose(ret['grad'], g, rtol=1e-4, atol=1e-7)
     want = ((raw_t - raw_o.detach()) ** 2).sum(dim=(1, 2, 3)).numpy()
     np.testing.assert_allclose(ret['scores'], want, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# Global batch plan: n not divisible by world * batch.  Every rank must run the same number of steps, the
+# ranks' shares of every global batch must partition it, and the weighted gradient sum must equal the global-batch gradient.
+# ---------------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('n,batch,world', [(9, 4, 4), (10001, 128, 8), (129, 128, 2), (7, 4, 2), (5, 4, 4), (1, 4, 2), (256, 128, 2)])
+def test_rank_batch_plan_same_steps_and_partition(n, batch, world):
+    plans = [ddp.rank_batch_plan(n, batch, r, world, seed=1234, shuffle=True) for r in range(world)]
+    steps = {len(p) for p in plans}
+    assert steps == {(n + batch - 1) // batch}                       # identical step count on every rank
+    g = torch.Generator().manual_seed(1234)
+    order = torch.randperm(n, generator=g)
+    seen = []
+    for s in range(len(plans[0])):
+        glob = order[s * batch:(s + 1) * batch]
+        parts = [plans[r][s][0] for r in range(world)]
+        assert all(plans[r][s][1] == glob.numel() for r in range(world))
+        assert torch.equal(torch.cat(parts), glob)                   # the shares partition the global batch, in order
+        seen.append(glob)
+    assert sorted(torch.cat(seen).tolist()) == list(range(n))        # one epoch = every cube exactly once
+
+
+def _worker_ragged(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    torch.set_num_threads(1)
+    ddp.init_from_env('gloo')
+    from oracle import unet_oracle as orc
+    kw = dict(features_root=16, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
+    torch.manual_seed(100)
+    m = orc.CompletionNetOracle('net4', **kw).eval()
+    raw_u8, flow = orc.synthetic_cubes(5, t_of=1, seed=6)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    seed = ddp.shared_seed()
+    reducer = ddp.GradReducer()
+    mse = torch.nn.MSELoss()
+    out = []
+    for idx, global_n in ddp.rank_batch_plan(5, 4, rank, world, seed=seed, shuffle=True):   # global batches of 4 and 1: rank 1's last share is empty
+        reducer.set_batch(idx.numel(), global_n)
+        m.zero_grad()
+        if idx.numel():
+            of_o, raw_o, of_t, raw_t = m(x[idx], x_of[idx])
+            (mse(raw_t, raw_o) + mse(of_t, of_o)).backward()
+            g = torch.cat([p.grad.reshape(-1) for p in m.parameters()])
+        else:
+            g = torch.zeros(sum(p.numel() for p in m.parameters()))
+        out.append((g * reducer(g)).numpy().copy())
+    if rank == 0:
+        ret['seed'] = seed
+        ret['grads'] = out
+    dist.destroy_process_group()
+
+
+def test_ragged_global_batches_weighted_gradient_equals_global_batch_gradient():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker_ragged, args=(world, port, ret), nprocs=world, join=True)
+    from oracle import unet_oracle as orc
+    kw = dict(features_root=16, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
+    torch.manual_seed(100)
+    torch.set_num_threads(1)
+    m = orc.CompletionNetOracle('net4', **kw).eval()
+    raw_u8, flow = orc.synthetic_cubes(5, t_of=1, seed=6)
+    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
+    mse = torch.nn.MSELoss()
+    plan = ddp.rank_batch_plan(5, 4, 0, 1, seed=ret['seed'], shuffle=True)      # world 1 = the global batches themselves
+    assert len(plan) == len(ret['grads']) == 2
+    for (idx, _), got in zip(plan, ret['grads']):
+        m.zero_grad()
+        of_o, raw_o, of_t, raw_t = m(x[idx], x_of[idx])
+        (mse(raw_t, raw_o) + mse(of_t, of_o)).backward()
+        want = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).numpy()
+        np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-7)

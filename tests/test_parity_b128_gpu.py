@@ -90,13 +90,14 @@ def _report(tag, rows, extra=None):
     return worst
 
 
+@pytest.mark.parametrize('prec', [1, 2])                               # 1 = tf32 operands, 2 = fp16 operands
 @pytest.mark.parametrize('name', ['net4_flow_b2', 'full_b2'])          # the configurations (batch comes from this file)
-def test_tc_path_matches_oracle_at_benchmark_batch(name):
+def test_tc_path_matches_oracle_at_benchmark_batch(name, prec):
     kind, kw = CONFIGS[name]
     t_of = kw['tot_of_num']
     torch.manual_seed(17)
     ref = orc.CompletionNetOracle(kind, **kw)
-    m = KIND_CLS[kind](use_tensor_cores=True, **kw)
+    m = KIND_CLS[kind](use_tensor_cores=prec, **kw)
     m.load_state_dict(ref.state_dict())
     m = m.cuda().train()
     raw_u8, flow = orc.synthetic_cubes(B, t_of=t_of, seed=4321)
@@ -104,7 +105,7 @@ def test_tc_path_matches_oracle_at_benchmark_batch(name):
     lr_, lo_, want = _oracle_grads(ref, x, x_of)
     gr, go, got = _engine_grads(m, x.cuda(), x_of.cuda())
     rows = _compare(got, want)
-    w = _report('tc_vs_oracle_' + name, rows, {'loss_raw': [gr, lr_], 'loss_of': [go, lo_]})
+    w = _report('tc%d_vs_oracle_%s' % (prec, name), rows, {'loss_raw': [gr, lr_], 'loss_of': [go, lo_]})
     assert abs(gr - lr_) <= 1e-4 * abs(lr_), (gr, lr_)
     assert abs(go - lo_) <= 1e-4 * abs(lo_), (go, lo_)
     assert w['min_cos'][1] >= 0.9999, w
@@ -114,20 +115,21 @@ def test_tc_path_matches_oracle_at_benchmark_batch(name):
             assert float(got[k].abs().max()) == 0.0
 
 
+@pytest.mark.parametrize('prec', [1, 2])
 @pytest.mark.parametrize('name', ['net4_flow_b2', 'full_b2'])
-def test_tc_path_matches_fp32_simt_path_on_device(name):
+def test_tc_path_matches_fp32_simt_path_on_device(name, prec):
     kind, kw = CONFIGS[name]
     raw_u8, flow = orc.synthetic_cubes(B, t_of=kw['tot_of_num'], seed=77)
     x, x_of = orc.cubes_to_tensors(raw_u8, flow)
     x, x_of = x.cuda(), x_of.cuda()
     res = {}
-    for tc in (False, True):
+    for tc in (False, prec):
         torch.manual_seed(23)
         m = KIND_CLS[kind](use_tensor_cores=tc, **kw).cuda().train()
         res[tc] = _engine_grads(m, x, x_of)
         del m
-    rows = _compare(res[True][2], res[False][2])
-    w = _report('tc_vs_simt_' + name, rows, {'loss_raw': [res[True][0], res[False][0]], 'bound': TC_VS_FP32_BOUND})
-    assert abs(res[True][0] - res[False][0]) <= 1e-4 * abs(res[False][0])
-    assert abs(res[True][1] - res[False][1]) <= 1e-4 * abs(res[False][1])
+    rows = _compare(res[prec][2], res[False][2])
+    w = _report('tc%d_vs_simt_%s' % (prec, name), rows, {'loss_raw': [res[prec][0], res[False][0]], 'bound': TC_VS_FP32_BOUND})
+    assert abs(res[prec][0] - res[False][0]) <= 1e-4 * abs(res[False][0])
+    assert abs(res[prec][1] - res[False][1]) <= 1e-4 * abs(res[False][1])
     assert w['max_rel_dist'][1] <= TC_VS_FP32_BOUND, w

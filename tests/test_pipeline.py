@@ -87,3 +87,13 @@ def test_batched_frame_scoring_equals_frame_by_frame(tmp_path, monkeypatch):
     assert len(a) == len(b) == 10
     for ma, mb in zip(a, b):
         assert np.array_equal(ma, mb) and ma.max() > -100000
+    # bounded workspace: sub-batches of 7 cubes through a workspace shared with a second model give the same masks
+    pool = pl.vu.WorkspacePool()
+    torch.manual_seed(1)
+    other = pl.build_network(cfg).cuda().eval().share_workspace(pool)
+    net.share_workspace(pool)
+    other.score(torch.rand(3, 15, 32, 32, device='cuda'), torch.randn(3, 2, 32, 32, device='cuda'))      # overwrites the shared bytes
+    c = pl.score_frames(cfg, lambda s, h, w: net, lambda s, h, w: ((3.0, 2.0), (1.0, 0.5)), fs, fs2, fb, dev, score_batch=7)
+    for ma, mc in zip(a, c):
+        assert np.array_equal(ma, mc)
+    assert net._ws_batch <= 7 and net._parts[0]['ws'] is pool.buf

@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 KIND_CLS = {'net4': vu.SelfCompleteNet4, 'full': vu.SelfCompleteNetFull, '1raw1of': vu.SelfCompleteNet1raw1of}
 
 # (use_tensor_cores, output rel tol, loss rel tol, grad l2 rel tol)
-PATHS = {'simt': (False, 2e-5, 1e-5, 2e-3), 'tc': (True, 5e-3, 1e-4, 6e-2)}
+PATHS = {'simt': (False, 2e-5, 1e-5, 2e-3), 'tc': (True, 5e-3, 1e-4, 6e-2), 'tc16': (2, 5e-3, 1e-4, 6e-2)}     # tc = tf32 operands, tc16 = fp16 operands
 
 
 def _model(name, g, tc):
@@ -208,7 +208,7 @@ def test_reference_style_loop_with_torch_adam():
         assert abs(loss_raw.item() - lr_) <= tol * lr_ and abs(loss_of.item() - lo_) <= tol * lo_
 
 
-@pytest.mark.parametrize('tc', [False, True])
+@pytest.mark.parametrize('tc', [False, True, 2])
 def test_side_stream_weight_gradients_equal_single_stream(tc, monkeypatch):
     """The weight-gradient tiles run on a side stream with event-tracked buffer hazards (net.cu).  Same weights, same cubes:
     the flat gradient buffer must equal the single-stream schedule's up to the run-dependent order of the split fp32
@@ -239,7 +239,7 @@ def test_side_stream_weight_gradients_equal_single_stream(tc, monkeypatch):
             assert (g_ - ref).abs().max().item() <= (5e-3 if tc else 1e-3) * scale, side
 
 
-@pytest.mark.parametrize('tc', [False, True])
+@pytest.mark.parametrize('tc', [False, True, 2])
 def test_full_batch_properties(tc):
     """BASELINE.json batch (128 cubes, 5raw1of): properties that need no oracle run.
     (a) the two losses of the fused train step are the means of the per-cube SSE it reports;

@@ -22,7 +22,7 @@ SYMBOLS = [
     'vecvad_resample2d_forward', 'vecvad_resample2d_backward',
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
     'vecvad_net_create', 'vecvad_net_destroy', 'vecvad_net_workspace_bytes', 'vecvad_net_bind',
-    'vecvad_net_forward', 'vecvad_net_backward', 'vecvad_net_losses', 'vecvad_adam_step',
+    'vecvad_net_forward', 'vecvad_net_backward', 'vecvad_net_losses', 'vecvad_net_set_loss_scale', 'vecvad_adam_step',
     'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
     'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
 ]
@@ -78,6 +78,7 @@ def lib():
     L.vecvad_net_forward.argtypes = [p, p, p, i, i, i, p, i, p, i, p, f, f, p]
     L.vecvad_net_backward.argtypes = [p, p, p, p]
     L.vecvad_net_losses.argtypes = [p, p, i, p, p]
+    L.vecvad_net_set_loss_scale.argtypes = [p, f]
     L.vecvad_adam_step.argtypes = [p, p, p, p, i64, f, f, f, f, f, i, f, p]
     L.vecvad_net_debug_read.argtypes = [p, i, i, p, i64, C.POINTER(i64), p]
     L.vecvad_conv3x3_forward.argtypes = [p, i, p, p, p, p, p, i, i, i, i, i, i, p]

@@ -52,7 +52,12 @@ struct VvIGemm {
     const float *bias;  long long bias_gs;                         // nullable; indexed by n (or co when o_d2s)
     double *stats;      long long stats_gs;                        // nullable; [2][N] column sum / sum of squares
     int G;
-    int ab_f16;                                                    // A and Wt hold fp16 (lda / a_coff / Kt in elements); flattened tiles only
+    int ab_f16;                                                    // A and Wt hold fp16 (lda / a_coff / a_gs / w_gs / Kt in elements); tcgen05 tiles only
+    int o_f16;                                                     // O holds fp16 (ldo / o_coff / o_gs in elements): the transposed conv writing the concat half
+    // split output (input gradient of the first conv of an up-block): columns >= o_split go, as fp16, to O2 (the transposed
+    // conv's output gradient) instead of O; 0 = no split
+    int o_split;
+    void *O2;           long long o2_gs; int ldo2;
 };
 
 // dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]
@@ -65,6 +70,7 @@ struct VvWGrad {
     VvTaps taps;
     float *dW;          long long dw_gs;                           // [ntaps][N][Kt], pre-zeroed, atomically accumulated
     int G;
+    int ab_f16;                                                    // A and Gd hold fp16 (strides / offsets in elements); tcgen05 tiles only
 };
 
 // ---- per-kernel-class event timing (prof.cu)
@@ -79,26 +85,21 @@ struct VvProfScope {
 
 int vv_launch_igemm_simt(const VvIGemm &p, cudaStream_t st);
 int vv_launch_wgrad_simt(const VvWGrad &p, cudaStream_t st);
-// tcgen05 (kind::tf32) tiles; return -3 if the shape is not supported by the tensor-core path.
-int vv_launch_igemm_tc(const VvIGemm &p, cudaStream_t st);
-int vv_launch_wgrad_tc(const VvWGrad &p, cudaStream_t st);
+// tcgen05 tiles (kind::tf32, or kind::f16 when ab_f16): which problems they accept at all (tc_support.cu) ...
 bool vv_igemm_tc_supported(const VvIGemm &p);
-// persistent tap-reuse variant (igemm_tc2.cu); falls back to vv_launch_igemm_tc when the driver refuses its tensor map
-bool vv_igemm_tc2_supported(const VvIGemm &p);
-int vv_launch_igemm_tc2(const VvIGemm &p, cudaStream_t st);
-// flattened-sequence 3x3 tiles (igemm_flat.cu): one activation box serves all nine taps.  _shape_ok: what the kernel can run;
-// _supported: where the net engine prefers it (full-width rows, VECVAD_FLAT != 0)
+bool vv_wgrad_tc_supported(const VvWGrad &p);
+// ... flattened-sequence 3x3 conv tiles (igemm_flat.cu): one activation box serves all nine taps.  _shape_ok: what the kernel can
+// run; _supported: where the net engine prefers it (full-width rows, VECVAD_FLAT != 0)
 bool vv_igemm_flat_shape_ok(const VvIGemm &p);
 bool vv_igemm_flat_supported(const VvIGemm &p);
 int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st);
-// pair variant of the persistent tiles (igemm_tc3.cu): two pixel tiles share every weight tile, two MMA warps, two epilogue sets
+// ... pair tiles (igemm_tc3.cu): two pixel tiles share every weight tile, two MMA warps, two epilogue sets
 bool vv_igemm_tc3_supported(const VvIGemm &p);
 int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st);
-bool vv_wgrad_tc_supported(const VvWGrad &p);
-// flattened-sequence weight-gradient tiles (wgrad_flat.cu): one MMA per K-step covers all nine taps
+// ... flattened-sequence weight-gradient tiles (wgrad_flat.cu): one MMA per K-step covers all nine taps
 bool vv_wgrad_flat_shape_ok(const VvWGrad &p);
 bool vv_wgrad_flat_supported(const VvWGrad &p);
 int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st);
-// tap-reuse variant (wgrad_tc2.cu)
+// ... tap-reuse weight-gradient tiles (wgrad_tc2.cu)
 bool vv_wgrad_tc2_supported(const VvWGrad &p);
 int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st);

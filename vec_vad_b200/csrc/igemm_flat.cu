@@ -2,7 +2,7 @@
 //
 //   out[m, n] = bias[n] + sum_t sum_k A[shift(m, t), k] * Wt[t][n][k]          (VvIGemm, common.h; 3x3 taps of either sign)
 //
-// k_igemm_tc2 (igemm_tc2.cu) loads one box per distinct dx because a dx step inside a [rows][W] box wraps around the image
+// The pair tiles (igemm_tc3.cu) load one box per distinct dx because a dx step inside a [rows][W] box wraps around the image
 // edge: at 32x32 resolution that is 3 boxes of 6 rows per 4 output rows = 4.5 x the activation bytes through L2 -> shared
 // memory.  Here the box is (W + 1) pixels wide: TMA zero-fills the out-of-range column x = W, so in shared memory image rows
 // sit P = W + 1 pixel-rows apart with ONE zero pixel between them, which is both the right padding of row y and the left
@@ -38,7 +38,6 @@ struct FlatParams {
     int kchunks, spr;               // 32-channel slabs per tile; TMA stages per ring (two rings, one per MMA warp)
     int tap[3][3];                  // [dy+1][dx+1] -> tap index of the weight tensor
     int a_bytes, stage_bytes;
-    int dbg;                        // VECVAD_DBG_TC2 bits (timing experiments only): 1 skip stores, 2 skip statistics, 4 skip MMAs
     unsigned long long *trace;      // VECVAD_FLAT_TRACE: cycle counters of CTA (0,0,0), see launch_flat
     int N;
     float *O;
@@ -48,6 +47,10 @@ struct FlatParams {
     long long bias_gs;
     double *stats;
     long long stats_gs;
+    int o_split;                    // columns >= o_split go to O2 as fp16 (VvIGemm::o_split); 0 = none
+    __half *O2;
+    long long o2_gs;
+    int ldo2;
 };
 
 constexpr int FL_THREADS = 352;
@@ -185,21 +188,19 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
                 // descriptor low words (address >> 4); rows are ROWB / 16 units; row offset >= -1: the guard / the previous stage's slack
                 const uint32_t a_lo0 = (((ring0 + s * p.stage_bytes) & 0x3FFFF) >> 4) + (uint32_t)((q0 - p.P - 1) * (ROWB / 16));
                 const uint32_t b_lok = b_lo0 + (uint32_t)(kc * (B_TAP >> 4));
-                if (!(p.dbg & 4)) {
 #pragma unroll
-                    for (int dyi = 0; dyi < 3; dyi++) {
+                for (int dyi = 0; dyi < 3; dyi++) {
 #pragma unroll
-                        for (int dxi = 0; dxi < 3; dxi++) {
-                            const uint32_t a_lo = a_lo0 + (uint32_t)((dyi * p.P + dxi) * (ROWB / 16));
-                            const uint32_t b_lo = b_lok + (uint32_t)(p.tap[dyi][dxi] * p.kchunks * (B_TAP >> 4));
+                    for (int dxi = 0; dxi < 3; dxi++) {
+                        const uint32_t a_lo = a_lo0 + (uint32_t)((dyi * p.P + dxi) * (ROWB / 16));
+                        const uint32_t b_lo = b_lok + (uint32_t)(p.tap[dyi][dxi] * p.kchunks * (B_TAP >> 4));
 #pragma unroll
-                            for (int k = 0; k < KSTEPS; k++) {       // 32 bytes of K per MMA in either format
-                                const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2 * k | (1u << 16));
-                                const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * k | (1u << 16));
-                                if (elect_one()) {
-                                    if (F16) tc_mma_f16(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
-                                    else tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
-                                }
+                        for (int k = 0; k < KSTEPS; k++) {       // 32 bytes of K per MMA in either format
+                            const uint64_t da = ((uint64_t)desc_hi << 32) | (a_lo + 2 * k | (1u << 16));
+                            const uint64_t db = ((uint64_t)desc_hi << 32) | (b_lo + 2 * k | (1u << 16));
+                            if (elect_one()) {
+                                if (F16) tc_mma_f16(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
+                                else tc_mma_tf32(d_tmem, da, db, idesc, (acc | (uint32_t)(dyi | dxi | k)) ? 1u : 0u);
                             }
                         }
                     }
@@ -268,7 +269,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
                 }
                 __syncwarp();
                 { const long long t2 = clock64(); t_stage += t2 - t1; t1 = t2; }
-                if (p.stats && !(p.dbg & 2)) {          // lane j sums column c0 + j over the 32 rows
+                if (p.stats) {          // lane j sums column c0 + j over the 32 rows
                     float s = 0.f, sq = 0.f;
 #pragma unroll
                     for (int r = 0; r < 32; r++) {
@@ -280,7 +281,16 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
                     c_sq[c0 / 32] += sq;
                 }
                 { const long long t2 = clock64(); t_stat += t2 - t1; t1 = t2; }
-                if (!(p.dbg & 1)) {                      // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
+                if (p.o_split && n0 + c0 >= p.o_split) {       // this 32-column block belongs to the fp16 side output
+                    __half *O2 = p.O2 + g * p.o2_gs + (n0 + c0 - p.o_split) + 4 * (lane & 7);
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {
+                        const int r = 4 * i + (lane >> 3);
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + r * FL_STG_LD + 4 * (lane & 7));
+                        const int rp = __shfl_sync(0xffffffffu, pix, r);
+                        if ((vmask >> r) & 1) *reinterpret_cast<uint2 *>(O2 + (long long)rp * p.ldo2) = pack_half4(o);
+                    }
+                } else {                                  // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = 4 * i + (lane >> 3);
@@ -334,7 +344,7 @@ bool analyse_3x3(const VvTaps &t, FlatParams &fp) {
 
 inline int flat_bn_tile(int N) { return N % 64 == 0 ? 64 : 32; }
 
-// VECVAD_FLAT=0 keeps the net engine on the per-dx-box tiles (igemm_tc2.cu)
+// VECVAD_FLAT=0 keeps the net engine on the per-dx-box pair tiles (igemm_tc3.cu)
 int flat_mode() {
     static int v = -1;
     if (v < 0) {
@@ -369,7 +379,7 @@ int launch_flat(const CUtensorMap &tmA, const CUtensorMap &tmB, const FlatParams
 // shapes the flattened-sequence tiles take: 3x3 taps, plain NHWC in/out, all nine weight tiles resident (<= 72 KB)
 bool vv_igemm_flat_shape_ok(const VvIGemm &p) {
     FlatParams fp;
-    if (!vv_igemm_tc_supported(p) || p.a_s2d || p.o_d2s || !analyse_3x3(p.taps, fp)) return false;
+    if (!vv_igemm_tc_supported(p) || p.a_s2d || p.o_d2s || p.o_f16 || !analyse_3x3(p.taps, fp)) return false;
     if (p.W + 1 > 256 || p.W < 8) return false;
     if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8)) return false;           // 16-byte aligned pixel rows
     const int b_all = 9 * (p.Kt / KS) * flat_bn_tile(p.N) * KS * (p.ab_f16 ? 2 : 4);
@@ -385,11 +395,6 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     memset(&fp, 0, sizeof(fp));
     VV_REQUIRE(enc && vv_igemm_flat_shape_ok(p) && analyse_3x3(p.taps, fp), "igemm_flat: unsupported shape (Kt=%d N=%d H=%d W=%d)", p.Kt, p.N,
                p.H, p.W);
-    {
-        static int dbg = -1;
-        if (dbg < 0) { const char *e = getenv("VECVAD_DBG_TC2"); dbg = e ? atoi(e) : 0; }
-        fp.dbg = dbg;
-    }
     fp.B = p.B; fp.H = p.H; fp.W = p.W; fp.G = p.G;
     fp.P = p.W + 1; fp.L = p.H * fp.P; fp.tpi = (fp.L + BM - 1) / BM; fp.m_tiles = fp.tpi * p.B;
     fp.mP = (unsigned)((0x100000000ULL + fp.P - 1) / fp.P); fp.mtpi = (unsigned)((0x100000000ULL + fp.tpi - 1) / fp.tpi);
@@ -400,6 +405,7 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     fp.stage_bytes = (fp.a_bytes + KS * esz + 1023) / 1024 * 1024;    // >= one zero pixel-row of slack: the next stage's leading guard
     fp.N = p.N; fp.O = p.O; fp.o_gs = p.o_gs; fp.ldo = p.ldo; fp.o_coff = p.o_coff;
     fp.bias = p.bias; fp.bias_gs = p.bias_gs; fp.stats = p.stats; fp.stats_gs = p.stats_gs;
+    fp.o_split = p.o_split; fp.O2 = (__half *)p.O2; fp.o2_gs = p.o2_gs; fp.ldo2 = p.ldo2;
     const int bn_tile = flat_bn_tile(p.N);
     const int b_all = 9 * fp.kchunks * bn_tile * KS * esz;
     const int fixed = 1024 /*alignment*/ + FL_GUARD + 8 * FL_STG_BYTES + 256 /*barriers*/ + 3 * bn_tile * 4;

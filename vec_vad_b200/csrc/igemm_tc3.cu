@@ -1,9 +1,9 @@
-// Persistent tcgen05 (kind::tf32) implicit-GEMM conv tiles, PAIR variant of k_igemm_tc2 (igemm_tc2.cu): a CTA works on TWO
-// 128-pixel tiles at a time that share every weight tile.
+// Persistent tcgen05 (kind::tf32 / kind::f16) implicit-GEMM conv tiles: a CTA works on a PAIR of 128-pixel tiles at a time
+// that share every weight tile.
 //
 //   out[m, n] = bias[n] + sum_t sum_k A[shift(m, t), k] * Wt[t][n][k]          (VvIGemm, common.h)
 //
-// What the ncu pass over one train step showed for k_igemm_tc2 at 16x16 / 8x8 / 4x4 resolution (profiles/r01_flat_v4_step.txt):
+// What the ncu pass over one train step showed for single-tile CTAs at 16x16 / 8x8 / 4x4 resolution (profiles/r01_flat_v4_step.txt):
 // the launches move 6.6 - 9.3 TB/s from L2 into shared memory, i.e. they sit on the L2 -> SM delivery limit, and 55 - 70 % of
 // those bytes are WEIGHTS: the 9 x K x N weight tensor does not fit next to the activation ring, so it is streamed again for
 // every 128-pixel tile.  And the flattened-sequence kernel (igemm_flat.cu) showed that one warp cannot issue MMAs faster than
@@ -16,7 +16,7 @@
 //   * TWO EPILOGUE SETS of four warps, one per tile of the pair: tcgen05.ld, release the accumulator at once, then bias,
 //     BatchNorm statistics and NHWC stores (or the transposed conv's pixel shuffle) through an XOR-swizzled 4 KB staging tile
 //     per warp: column sums without shuffles, full 128-byte lines per store instruction.
-//   * Tap reuse as in k_igemm_tc2: per slab one box per distinct dx, (bh + ndy - 1) pixel rows tall, laid out [row][image][x];
+//   * Tap reuse: per slab one box per distinct dx, (bh + ndy - 1) pixel rows tall, laid out [row][image][x];
 //     the dy taps are descriptor start offsets into the same box.  Weights resident when all taps x slabs fit in 72 KB.
 // warp 0: TMA producer | warps 1-2: MMA issuers (warp 1 allocates TMEM) | warps 3-6 / 7-10: epilogue of tile 0 / 1 of the pair.
 #include "tc_common.cuh"
@@ -43,6 +43,11 @@ struct Tc3Params {
     long long bias_gs;
     double *stats;
     long long stats_gs;
+    int o_f16;                      // O is fp16 (the transposed conv writing the concat half)
+    int o_split;                    // columns >= o_split go to O2 as fp16 (VvIGemm::o_split); 0 = none
+    __half *O2;
+    long long o2_gs;
+    int ldo2;
 };
 
 constexpr int T3_THREADS = 352;
@@ -53,8 +58,8 @@ constexpr int T3_MAX_STAGES = 4;
 // float index of 16-byte chunk c4 (0..7) of staging row r
 __device__ __forceinline__ int stg_idx(int r, int c4) { return r * 32 + ((c4 ^ (r & 7)) << 2); }
 
-// F16: operands are fp16 in HBM and shared memory (64-byte pixel rows, SWIZZLE_64B, kind::f16 with K = 16 per MMA), accumulation and
-// outputs fp32 -- the variant measured on the flattened tile; not yet validated on the device for this kernel.
+// F16: operands are fp16 in HBM and shared memory (64-byte pixel rows, SWIZZLE_64B, kind::f16 with K = 16 per MMA), accumulation
+// fp32; outputs fp32, or fp16 where the consumer is another contraction (o_f16 / o_split).
 template <int BN, bool F16>
 __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                                                              const Tc3Params p) {
@@ -286,12 +291,25 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
                     col = ncol - phs * Co;
                     pixc = pix + (phs >> 1) * (2 * p.W) + (phs & 1);
                 }
+                if (p.o_f16 || (p.o_split && ncol >= p.o_split)) {      // fp16 destination: 8 bytes per lane, 64-byte pixel rows
+                    __half *Oh = p.o_f16 ? reinterpret_cast<__half *>(p.O) + g * p.o_gs + p.o_coff + col + 4 * (lane & 7)
+                                         : p.O2 + g * p.o2_gs + (ncol - p.o_split) + 4 * (lane & 7);
+                    const int ldh = p.o_f16 ? p.ldo : p.ldo2;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {            // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
-                    const int rr = 4 * i + (lane >> 3);
-                    const float4 o = *reinterpret_cast<const float4 *>(stg + stg_idx(rr, lane & 7));
-                    const int rp = __shfl_sync(0xffffffffu, pixc, rr);
-                    if ((vmask >> rr) & 1) *reinterpret_cast<float4 *>(O + (long long)rp * p.ldo + col + 4 * (lane & 7)) = o;
+                    for (int i = 0; i < 8; i++) {
+                        const int rr = 4 * i + (lane >> 3);
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + stg_idx(rr, lane & 7));
+                        const int rp = __shfl_sync(0xffffffffu, pixc, rr);
+                        if ((vmask >> rr) & 1) *reinterpret_cast<uint2 *>(Oh + (long long)rp * ldh) = pack_half4(o);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) {            // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
+                        const int rr = 4 * i + (lane >> 3);
+                        const float4 o = *reinterpret_cast<const float4 *>(stg + stg_idx(rr, lane & 7));
+                        const int rp = __shfl_sync(0xffffffffu, pixc, rr);
+                        if ((vmask >> rr) & 1) *reinterpret_cast<float4 *>(O + (long long)rp * p.ldo + col + 4 * (lane & 7)) = o;
+                    }
                 }
                 __syncwarp();
             }
@@ -352,7 +370,8 @@ inline int tc3_bn_tile(int N) { return N % 128 == 0 ? 128 : (N % 64 == 0 ? 64 : 
 bool plan3(const VvIGemm &p, Tc3Params &tp, int &smem_bytes) {
     if (!analyse_taps3(p.taps, tp)) return false;
     const int esz = p.ab_f16 ? 2 : 4;                  // operand element size
-    if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8 || p.a_s2d)) return false;
+    if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8)) return false;
+    if (p.o_f16 && (p.ldo % 8 || p.o_coff % 8)) return false;
     tp.B = p.B; tp.H = p.H; tp.W = p.W; tp.G = p.G;
     if (!tile_geometry_n(p.H, p.W, BM, tp.bw, tp.bh, tp.bn)) return false;
     tp.tiles_x = p.W / tp.bw; tp.tiles_y = p.H / tp.bh; tp.tiles_n = (p.B + tp.bn - 1) / tp.bn;
@@ -380,7 +399,6 @@ bool plan3(const VvIGemm &p, Tc3Params &tp, int &smem_bytes) {
     return true;
 }
 
-bool g_tc3_disabled = false;      // set when the permuted-dimension tensor map is refused by the driver
 
 template <int BN, bool F16>
 int launch3(const CUtensorMap &tmA, const CUtensorMap &tmB, const Tc3Params &tp, dim3 grid, int smem, cudaStream_t st) {
@@ -410,7 +428,7 @@ bool vv_igemm_tc3_supported(const VvIGemm &p) {
         const char *e = getenv("VECVAD_NO_TC3");
         off = (e && e[0] == '1') ? 1 : 0;
     }
-    if (off || g_tc3_disabled || !vv_igemm_tc_supported(p)) return false;
+    if (off || !vv_igemm_tc_supported(p)) return false;
     Tc3Params tp;
     int smem;
     memset(&tp, 0, sizeof(tp));
@@ -425,6 +443,7 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
     VV_REQUIRE(enc && plan3(p, tp, smem), "igemm_tc3: unsupported shape (Kt=%d N=%d H=%d W=%d taps=%d)", p.Kt, p.N, p.H, p.W, p.taps.n);
     tp.N = p.N; tp.O = p.O; tp.o_gs = p.o_gs; tp.ldo = p.ldo; tp.o_coff = p.o_coff; tp.o_d2s = p.o_d2s;
     tp.bias = p.bias; tp.bias_gs = p.bias_gs; tp.stats = p.stats; tp.stats_gs = p.stats_gs;
+    tp.o_f16 = p.o_f16; tp.o_split = p.o_split; tp.O2 = (__half *)p.O2; tp.o2_gs = p.o2_gs; tp.ldo2 = p.ldo2;
     {
         static int tr = -1;
         static unsigned long long *buf = nullptr;
@@ -448,10 +467,7 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
         cuuint32_t estr[4] = {1, (cuuint32_t)sc, 1, (cuuint32_t)sc};
         CUresult r = enc(&tmA, dt, 4, (void *)((const char *)p.A + (long long)p.a_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                          sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            g_tc3_disabled = true;                // the per-tap kernel from now on
-            return vv_launch_igemm_tc(p, st);
-        }
+        VV_REQUIRE(r == CUDA_SUCCESS, "igemm_tc3: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     {
         cuuint64_t dims[3] = {(cuuint64_t)p.Kt, (cuuint64_t)p.N, (cuuint64_t)p.taps.n * p.G};

@@ -26,8 +26,8 @@ extern "C" uint64_t vecvad_launch_count(void) { return g_vv_launches; }
 
 namespace {
 
-struct View {           // grouped NHWC view: element (g, m, c) at p + g*gs + m*ld + coff + c
-    float *p;
+struct View {           // grouped NHWC view: element (g, m, c) at p + g*gs + m*ld + coff + c   (element units: fp32, or fp16 for the
+    void *p;            // activation buffers of the fp16-operand mode)
     long long gs;
     int ld, coff, C, H;
 };
@@ -41,6 +41,8 @@ constexpr int NT = VECVAD_N_UPS;
 struct vecvad_net {
     vecvad_net_config cfg;
     int G, F, S, T, cin_real, cinp;
+    int f16;                                 // use_tensor_cores == 2: activations, dZ and re-laid-out weights are fp16 (operands of kind::f16 tiles)
+    float lscale, lscale_user;               // power-of-two loss scale of the fp16 gradient operands (1 in the other modes); user override (<= 0: automatic)
     VvIntG slot, erase, outc, isflow, tidx, oslot;
     int n_raw_out, n_of_out, n_raw_tot, n_of_tot;
     // unit geometry: conv unit u maps C -> N at resolution H
@@ -52,8 +54,11 @@ struct vecvad_net {
     int64_t ws_bytes;
     int maxB;
     // workspace sub-buffers (float offsets resolved to pointers at bind time)
-    float *X0, *Z[NU], *A[NU], *CAT[3], *PL[3], *X4, *UU[3], *dCAT[3], *GA, *GB, *DOUT;
-    float *Wf[NU], *Wd[NU], *vec[NU], *save[NU], *tWf[NT], *tWd[NT], *tvec[NT];
+    void *X0, *A[NU], *CAT[3], *PL[3], *X4, *UU[3];           // activations: fp32, or fp16 in the fp16-operand mode
+    float *Z[NU], *dCAT[3], *GA, *GB, *DOUT;                  // raw conv outputs and output gradients (dY): always fp32
+    void *dUP[3], *HZ[4];                                     // fp16 mode only: transposed-conv output gradients, ring of dZ operand buffers
+    void *Wf[NU], *Wd[NU], *tWf[NT], *tWd[NT];                // re-laid-out weights: fp32 or fp16
+    float *vec[NU], *save[NU], *tvec[NT];
     float *dWf[NU], *tdW[NT];
     double *stats[NU], *bsums[NU];
     char *zero_fwd;  size_t zero_fwd_bytes;   // BN statistics accumulators
@@ -79,33 +84,37 @@ long long layout(vecvad_net *n, int B, char *base) {
         return p;
     };
     const int G = n->G, F = n->F, S = n->S;
+    const long long es = n->f16 ? 2 : 4;                       // bytes per activation / operand element
     auto M = [&](int H) { return (long long)B * H * H; };
     auto fl = [&](long long count) { return (float *)take(count * (long long)sizeof(float)); };
-    n->X0 = fl(G * M(S) * n->cinp);
+    auto act = [&](long long count) { return (void *)take(count * es); };
+    n->X0 = act(G * M(S) * n->cinp);
     for (int u = 0; u < NU; u++) n->Z[u] = fl(G * M(n->uH[u]) * n->uN[u]);
-    for (int u = 0; u < NU; u += 2) n->A[u] = fl(G * M(n->uH[u]) * n->uN[u]);
+    for (int u = 0; u < NU; u += 2) n->A[u] = act(G * M(n->uH[u]) * n->uN[u]);
     // CAT[k]: concat input of up-block k+1:  k=0 @S/4 (8F), k=1 @S/2 (4F), k=2 @S (2F)
     for (int k = 0; k < 3; k++) {
         int H = S >> (2 - k), C = F << (3 - k);
-        n->CAT[k] = fl(G * M(H) * C);
+        n->CAT[k] = act(G * M(H) * C);
         n->dCAT[k] = fl(G * M(H) * C);
+        n->dUP[k] = n->f16 ? take(G * M(H) * (C / 2) * 2) : nullptr;
     }
     // PL[k]: pooled input of down-block k+1: k=0 @S/2 (F), k=1 @S/4 (2F), k=2 @S/8 (4F)
-    for (int k = 0; k < 3; k++) n->PL[k] = fl(G * M(S >> (k + 1)) * (F << k));
-    n->X4 = fl(G * M(S >> 3) * 8 * F);
-    for (int k = 0; k < 3; k++) n->UU[k] = fl(G * M(S >> (2 - k)) * (F << (2 - k)));   // U1 @S/4 4F, U2 @S/2 2F, U3 @S F
+    for (int k = 0; k < 3; k++) n->PL[k] = act(G * M(S >> (k + 1)) * (F << k));
+    n->X4 = act(G * M(S >> 3) * 8 * F);
+    for (int k = 0; k < 3; k++) n->UU[k] = act(G * M(S >> (2 - k)) * (F << (2 - k)));   // U1 @S/4 4F, U2 @S/2 2F, U3 @S F
     n->GA = fl(G * M(S) * F);
     n->GB = fl(G * M(S) * F);
+    for (int i = 0; i < 4; i++) n->HZ[i] = n->f16 ? take(G * M(S) * F * 2) : nullptr;
     n->DOUT = fl(G * M(S) * 4);
     for (int u = 0; u < NU; u++) {
-        n->Wf[u] = fl((long long)G * 9 * n->uN[u] * n->uCp[u]);
-        n->Wd[u] = fl((long long)G * 9 * n->uN[u] * n->uCp[u]);
+        n->Wf[u] = act((long long)G * 9 * n->uN[u] * n->uCp[u]);
+        n->Wd[u] = act((long long)G * 9 * n->uN[u] * n->uCp[u]);
         n->vec[u] = fl((long long)G * 3 * n->uN[u]);
         n->save[u] = fl((long long)G * 4 * n->uN[u]);
     }
     for (int k = 0; k < NT; k++) {
-        n->tWf[k] = fl((long long)G * 16 * n->tCo[k] * n->tCi[k]);
-        n->tWd[k] = fl((long long)G * 16 * n->tCo[k] * n->tCi[k]);
+        n->tWf[k] = act((long long)G * 16 * n->tCo[k] * n->tCi[k]);
+        n->tWd[k] = act((long long)G * 16 * n->tCo[k] * n->tCi[k]);
         n->tvec[k] = fl((long long)G * n->tCo[k]);
     }
     long long z0 = off;
@@ -142,17 +151,20 @@ double igemm_flops(int B, int H, int W, int N, int K, int taps, int G) { return 
 
 int run_igemm(bool want_tc, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
     const bool tc = want_tc && vv_igemm_tc_supported(p);
+    if (p.ab_f16 && !(tc && (vv_igemm_flat_supported(p) || vv_igemm_tc3_supported(p))))
+        return vv_set_err(-3, "fp16-operand contraction %dx%d Kt=%d N=%d is not covered by the tcgen05 tiles (no fp32 fallback reads fp16)", p.H, p.W, p.Kt, p.N);
     VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_igemm_flat_supported(p)) return vv_launch_igemm_flat(p, st);
     if (tc && vv_igemm_tc3_supported(p)) return vv_launch_igemm_tc3(p, st);
-    if (tc) return vv_igemm_tc2_supported(p) ? vv_launch_igemm_tc2(p, st) : vv_launch_igemm_tc(p, st);
     return vv_launch_igemm_simt(p, st);
 }
 int run_wgrad(bool want_tc, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
     const bool tc = want_tc && vv_wgrad_tc_supported(p);
+    if (p.ab_f16 && !(tc && (vv_wgrad_flat_supported(p) || vv_wgrad_tc2_supported(p))))
+        return vv_set_err(-3, "fp16-operand weight gradient %dx%d Kt=%d N=%d is not covered by the tcgen05 tiles", p.H, p.W, p.Kt, p.N);
     VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_wgrad_flat_supported(p)) return vv_launch_wgrad_flat(p, st);
-    if (tc) return vv_wgrad_tc2_supported(p) ? vv_launch_wgrad_tc2(p, st) : vv_launch_wgrad_tc(p, st);
+    if (tc && vv_wgrad_tc2_supported(p)) return vv_launch_wgrad_tc2(p, st);
     return vv_launch_wgrad_simt(p, st);
 }
 
@@ -162,7 +174,7 @@ struct Flow {   // buffer wiring of one forward for batch B
     View tin[NT], tout[NT];
 };
 
-View mk(float *p, int B, int H, int ld, int coff, int C) {
+View mk(void *p, int B, int H, int ld, int coff, int C) {
     View v;
     v.p = p; v.gs = (long long)B * H * H * ld; v.ld = ld; v.coff = coff; v.C = C; v.H = H;
     return v;
@@ -203,6 +215,12 @@ void wire(const vecvad_net *n, int B, Flow &f) {
 
 }  // namespace
 
+// dispatchers shared with single_ops.cu
+int vv_run_igemm(bool want_tc, const VvIGemm &p, cudaStream_t st) { return run_igemm(want_tc, p, st); }
+int vv_run_wgrad(bool want_tc, const VvWGrad &p, cudaStream_t st) { return run_wgrad(want_tc, p, st); }
+VvTaps vv_taps3x3(int sign) { return taps3x3(sign); }
+VvTaps vv_taps2x2(int sign) { return taps2x2(sign); }
+
 extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out) {
     VV_REQUIRE(cfg && out, "net_create: null argument");
     VV_REQUIRE(cfg->n_unets >= 1 && cfg->n_unets <= VECVAD_MAX_UNETS, "net_create: n_unets=%d out of range", cfg->n_unets);
@@ -217,7 +235,9 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
     n->G = cfg->n_unets; n->F = cfg->features_root; n->S = cfg->patch; n->T = cfg->tot_raw_num;
     n->cin_real = 3 * (cfg->padding ? n->T : n->T - 1);
     n->cinp = (n->cin_real + 15) / 16 * 16;
-    if (cfg->use_tensor_cores) n->cinp = (n->cin_real + 31) / 32 * 32;   // tcgen05 tiles use 128-byte (32 x tf32) K slabs
+    if (cfg->use_tensor_cores) n->cinp = (n->cin_real + 31) / 32 * 32;   // tcgen05 tiles use 32-channel K slabs (128 bytes of tf32, 64 of fp16)
+    n->f16 = cfg->use_tensor_cores == 2;
+    n->lscale = 1.f; n->lscale_user = 0.f;
     int max_raw = -1, max_of = -1;
     for (int g = 0; g < n->G; g++) {
         n->slot.v[g] = cfg->param_slot[g]; n->erase.v[g] = cfg->erase_frame[g]; n->outc.v[g] = cfg->out_channels[g];
@@ -320,13 +340,14 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
             pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
             pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
         }
+        all.w_f16 = n->f16;
         int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, st);
         if (r) return r;
     } else {
         for (int u = 0; u < NU; u++) {
             int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
                                    n->uCp[u], n->Wf[u], 9LL * n->uN[u] * n->uCp[u], (training && u > 0) ? n->Wd[u] : nullptr,
-                                   9LL * n->uN[u] * n->uCp[u], n->vec[u], 3LL * n->uN[u], G, st);
+                                   9LL * n->uN[u] * n->uCp[u], n->f16, n->vec[u], 3LL * n->uN[u], G, st);
             if (r) return r;
         }
     }
@@ -339,7 +360,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     }
     for (int k = 0; k < NT; k++) {
         int r = vv_prep_ct_w(n->params, n->slot, c.slot_param_stride, c.up_w[k], c.up_b[k], n->tCi[k], n->tCo[k], n->tWf[k],
-                             16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->tvec[k], n->tCo[k], G, sP);
+                             16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->f16, n->tvec[k], n->tCo[k], G, sP);
         if (r) return r;
     }
     if (n->use_side) {
@@ -349,7 +370,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     if (training) VV_CK(cudaMemsetAsync(n->zero_fwd, 0, n->zero_fwd_bytes, st));
     // 2. the erased-frame inputs of every UNet
     {
-        int r = vv_prep_input(x, n->X0, G, B, n->T, S, n->cinp, c.padding, n->erase, st);
+        int r = vv_prep_input(x, n->X0, n->f16, G, B, n->T, S, n->cinp, c.padding, n->erase, st);
         if (r) return r;
     }
     const VvTaps t3 = taps3x3(+1), t2 = taps2x2(+1);
@@ -359,9 +380,9 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         const int H = n->uH[u], N = n->uN[u];
         VvIGemm p;
         memset(&p, 0, sizeof(p));
-        p.A = in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->uCp[u];
-        p.B = B; p.H = H; p.W = H;
-        p.Wt = n->Wf[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3; p.N = N;
+        p.A = (const float *)in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->uCp[u];
+        p.B = B; p.H = H; p.W = H; p.ab_f16 = n->f16;
+        p.Wt = (const float *)n->Wf[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3; p.N = N;
         p.O = n->Z[u]; p.o_gs = (long long)B * H * H * N; p.ldo = N; p.o_coff = 0; p.o_d2s = 0;
         p.bias = n->vec[u]; p.bias_gs = 3LL * N;
         p.stats = training ? n->stats[u] : nullptr; p.stats_gs = 2LL * N;
@@ -372,7 +393,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         VvBnApply q;
         memset(&q, 0, sizeof(q));
         q.Z = n->Z[u]; q.z_gs = p.o_gs;
-        q.Y = y.p; q.y_gs = y.gs; q.ldy = y.ld; q.y_coff = y.coff;
+        q.Y = y.p; q.y_gs = y.gs; q.ldy = y.ld; q.y_coff = y.coff; q.y_f16 = n->f16;
         q.pool = f.pool[u] >= 0;
         if (q.pool) { q.P = n->PL[f.pool[u]]; q.p_gs = (long long)B * (H / 2) * (H / 2) * N; }
         q.M = B * H * H; q.H = H; q.W = H; q.C = N; q.training = training;
@@ -387,10 +408,10 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         const View &o = f.tout[k];
         VvIGemm p;
         memset(&p, 0, sizeof(p));
-        p.A = in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->tCi[k];
-        p.B = B; p.H = n->tH[k]; p.W = n->tH[k];
-        p.Wt = n->tWf[k]; p.w_gs = 16LL * n->tCo[k] * n->tCi[k]; p.taps = t2; p.N = 4 * n->tCo[k];
-        p.O = o.p; p.o_gs = o.gs; p.ldo = o.ld; p.o_coff = o.coff; p.o_d2s = 1;
+        p.A = (const float *)in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->tCi[k];
+        p.B = B; p.H = n->tH[k]; p.W = n->tH[k]; p.ab_f16 = n->f16;
+        p.Wt = (const float *)n->tWf[k]; p.w_gs = 16LL * n->tCo[k] * n->tCi[k]; p.taps = t2; p.N = 4 * n->tCo[k];
+        p.O = (float *)o.p; p.o_gs = o.gs; p.ldo = o.ld; p.o_coff = o.coff; p.o_d2s = 1; p.o_f16 = n->f16;
         p.bias = n->tvec[k]; p.bias_gs = n->tCo[k];
         p.stats = nullptr; p.G = G;
         return run_igemm(n->cfg.use_tensor_cores != 0, p, st);
@@ -406,7 +427,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     // 3. 1x1 output conv (+ squared error / MSE gradient)
     VvOutFwd q;
     memset(&q, 0, sizeof(q));
-    q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F;
+    q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F; q.u_f16 = n->f16;
     q.params = n->params; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.w_off = c.out_w; q.b_off = c.out_b;
     q.out_channels = n->outc; q.target_is_flow = n->isflow; q.target_index = n->tidx; q.out_slot = n->oslot;
     q.B = B; q.S = S; q.F = F;
@@ -418,6 +439,15 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     q.coef_raw = n->n_raw_tot ? 2.f * lambda_raw / ((float)B * 3.f * n->n_raw_tot * S * S) : 0.f;
     q.coef_of = n->n_of_tot ? 2.f * lambda_of / ((float)B * 2.f * n->n_of_tot * S * S) : 0.f;
     if ((r = vv_outconv_fwd(q, G, st))) return r;
+    // fp16 gradient operands: one power-of-two loss scale for the whole backward, from the largest MSE-gradient coefficient
+    // (|d loss / d out| = coef * |out - tgt|, residuals are O(1)): dZ values land around 2^3, 12 binades under the fp16 maximum
+    // and 17 above its smallest normal.  The scale is applied once (where the last unit's dZ is stored) and removed wherever a
+    // parameter gradient is written, so gradients come out unscaled.
+    n->lscale = 1.f;
+    if (n->f16) {
+        const float cm = q.coef_raw > q.coef_of ? q.coef_raw : q.coef_of;
+        n->lscale = n->lscale_user > 0.f ? n->lscale_user : (cm > 0.f ? exp2f(floorf(log2f(1.f / cm)) + 3.f) : 1.f);
+    }
     n->lastB = B; n->last_training = training; n->have_dout = (sse && training) ? 1 : 0;
     return 0;
 }
@@ -455,10 +485,12 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     // ---- output conv.  With the loss gradient staged by the forward (no external gradients) its backward is folded into the BatchNorm
     // backward of the last conv unit (VvBnBwd::dout): dU is never written or read.
     const bool fuse_out = !ext;
+    const int f16 = n->f16;
+    const float LS = f16 ? n->lscale : 1.f, inv_LS = 1.f / LS;      // loss scale carried by every dY / dZ behind the last unit (fp16 mode)
     if (!fuse_out) {
         VvOutBwd q;
         memset(&q, 0, sizeof(q));
-        q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F;
+        q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F; q.u_f16 = f16;
         q.dU = n->GA; q.du_gs = q.u_gs;
         q.params = n->params; q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.w_off = c.out_w; q.b_off = c.out_b;
         q.out_channels = n->outc; q.target_is_flow = n->isflow; q.out_slot = n->oslot;
@@ -470,13 +502,21 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     }
     const VvTaps t3f = taps3x3(+1), t3b = taps3x3(-1), t2f = taps2x2(+1), t2b = taps2x2(-1);
     // ---- side stream for the weight-gradient tiles.  fork: sB waits for everything issued so far on st, runs the wgrad, and
-    // leaves an event; a kernel on st that overwrites the gradient buffer (GA / GB) the wgrad still reads waits for it first.
+    // leaves an event; a kernel on st that overwrites a buffer the wgrad still reads (fp32 mode: GA / GB, where dZ replaces dY in
+    // place; fp16 mode: the ring of dZ operand buffers) waits for it first.
     cudaStream_t sB = n->use_side ? n->wg_stream : st;
-    cudaEvent_t pend[2] = {nullptr, nullptr}, last_wg = nullptr;
+    constexpr int NPEND = 6;
+    const void *pend_ptr[NPEND] = {n->GA, n->GB, n->HZ[0], n->HZ[1], n->HZ[2], n->HZ[3]};
+    cudaEvent_t pend[NPEND] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, last_wg = nullptr;
     n->ev_next = 0;
     auto next_ev = [&]() { return n->ev[(n->ev_next++) % VV_NEV]; };
-    auto before_write = [&](const float *ptr) -> int {
-        const int i = ptr == n->GA ? 0 : (ptr == n->GB ? 1 : -1);
+    auto pend_slot = [&](const void *ptr) -> int {
+        for (int i = 0; i < NPEND; i++)
+            if (ptr && ptr == pend_ptr[i]) return i;
+        return -1;
+    };
+    auto before_write = [&](const void *ptr) -> int {
+        const int i = pend_slot(ptr);
         if (n->use_side && i >= 0 && pend[i]) {
             VV_CK(cudaStreamWaitEvent(st, pend[i], 0));
             pend[i] = nullptr;
@@ -490,26 +530,33 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         VV_CK(cudaStreamWaitEvent(sB, e, 0));
         return 0;
     };
-    auto mark = [&](const float *reads) -> int {
+    auto mark = [&](const void *reads) -> int {
         if (!n->use_side) return 0;
         cudaEvent_t e = next_ev();
         VV_CK(cudaEventRecord(e, sB));
-        const int i = reads == n->GA ? 0 : (reads == n->GB ? 1 : -1);
+        const int i = pend_slot(reads);
         if (i >= 0) pend[i] = e;
         last_wg = e;
         return 0;
     };
+    int hz_next = 0;
     bool batched_scatter = true;       // conv weight gradients go back to PyTorch's layout in one launch at the end
     for (int u = 0; u < NU; u++) batched_scatter = batched_scatter && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
 
-    // gradient of the post-ReLU output of unit u lives in dyv; produces d(input of unit u) into `din` (if u > 0)
-    auto unit_bwd = [&](int u, const View &dyv, float *dz_buf, const View *din) -> int {
+    // gradient of the post-ReLU output of unit u lives in dyv (fp32); produces d(input of unit u) into `din` (if u > 0).
+    // dz_inplace: where dZ goes in the fp32 modes (it may overwrite dY); the fp16 mode takes the next buffer of its dZ ring.
+    // up_k >= 0: unit u is the first conv of up-block up_k, whose input gradient splits into the skip half (din, fp32) and the
+    // transposed conv's output gradient (fp16 mode: stored as fp16 in dUP[up_k], the operand of the two transposed-conv backward tiles).
+    auto unit_bwd = [&](int u, const View &dyv, float *dz_inplace, const View *din, int up_k) -> int {
         const int H = n->uH[u], N = n->uN[u], M = B * H * H;
+        void *dz_buf = f16 ? n->HZ[(hz_next++) & 3] : (void *)dz_inplace;
         VvBnBwd q;
         memset(&q, 0, sizeof(q));
         q.Z = n->Z[u]; q.z_gs = (long long)M * N;
-        q.dY = dyv.p; q.dy_gs = dyv.gs; q.ldy = dyv.ld; q.dy_coff = dyv.coff;
-        q.dZ = dz_buf; q.dz_gs = (long long)M * N;
+        q.dY = (const float *)dyv.p; q.dy_gs = dyv.gs; q.ldy = dyv.ld; q.dy_coff = dyv.coff;
+        q.dZ = dz_buf; q.dz_gs = (long long)M * N; q.dz_f16 = f16;
+        q.store_scale = (u == NU - 1) ? LS : 1.f;              // the loss scale enters where the last unit's dZ is stored ...
+        q.grad_unscale = (u == NU - 1) ? 1.f : inv_LS;         // ... so every earlier dY carries it: removed from d gamma / d beta
         q.M = M; q.C = N;
         q.save = n->save[u]; q.save_gs = 4LL * N;
         q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
@@ -528,12 +575,12 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         const View &in = f.in[u];
         VvWGrad w;
         memset(&w, 0, sizeof(w));
-        w.A = in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = n->uCp[u];
-        w.B = B; w.H = H; w.W = H;
-        w.Gd = dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
+        w.A = (const float *)in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = n->uCp[u];
+        w.B = B; w.H = H; w.W = H; w.ab_f16 = f16;
+        w.Gd = (const float *)dz_buf; w.g_gs = (long long)M * N; w.ldg = N; w.g_coff = 0; w.g_s2d = 0; w.N = N;
         w.taps = t3f; w.dW = n->dWf[u]; w.dw_gs = 9LL * N * n->uCp[u]; w.G = G;
         if ((rr = fork())) return rr;
-        if ((rr = run_wgrad(n->cfg.use_tensor_cores != 0, w, sB, n->uC[u]))) return rr;
+        if ((rr = run_wgrad(c.use_tensor_cores != 0, w, sB, n->uC[u]))) return rr;
         if (!batched_scatter &&
             (rr = vv_scatter_conv_wgrad(n->dWf[u], w.dw_gs, N, n->uC[u], n->uCp[u], n->grads, n->slot, c.slot_param_stride, c.conv_w[u], G, sB)))
             return rr;
@@ -543,55 +590,59 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         if (din) {
             VvIGemm p;
             memset(&p, 0, sizeof(p));
-            p.A = dz_buf; p.a_gs = (long long)M * N; p.lda = N; p.a_coff = 0; p.a_s2d = 0; p.Kt = N;
+            p.A = (const float *)dz_buf; p.a_gs = (long long)M * N; p.lda = N; p.a_coff = 0; p.a_s2d = 0; p.Kt = N; p.ab_f16 = f16;
             p.B = B; p.H = H; p.W = H;
-            p.Wt = n->Wd[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3b; p.N = n->uC[u];
-            p.O = din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
+            p.Wt = (const float *)n->Wd[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3b; p.N = n->uC[u];
+            p.O = (float *)din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
+            if (f16 && up_k >= 0) {
+                p.o_split = n->uC[u] / 2; p.O2 = n->dUP[up_k]; p.ldo2 = n->uC[u] / 2; p.o2_gs = (long long)M * (n->uC[u] / 2);
+            }
             p.bias = nullptr; p.stats = nullptr; p.G = G;
             if ((rr = before_write(din->p))) return rr;
-            if ((rr = run_igemm(n->cfg.use_tensor_cores != 0, p, st))) return rr;
+            if ((rr = run_igemm(c.use_tensor_cores != 0, p, st))) return rr;
         }
         return 0;
     };
-    // transposed conv k: gradient arrives in the second half of dCAT[k]
+    // transposed conv k: its output gradient is the second half of the concat gradient: fp32 modes: columns [Co, 2Co) of dCAT[k];
+    // fp16 mode: the dense fp16 tensor dUP[k] the split epilogue of the producing tile wrote
     auto convT_bwd = [&](int k, const View &ddeep) -> int {
         const int Hi = n->tH[k], Ci = n->tCi[k], Co = n->tCo[k];
         const int Hc = 2 * Hi, Cc = 2 * Co;                   // concat buffer geometry
-        View dhalf = mk(n->dCAT[k], B, Hc, Cc, Co, Co);
-        int rr = vv_colsum(dhalf.p, dhalf.gs, dhalf.ld, dhalf.coff, B * Hc * Hc, Co, n->grads, n->slot, c.slot_param_stride, c.up_b[k], G, st);
+        View dhalf = f16 ? mk(n->dUP[k], B, Hc, Co, 0, Co) : mk(n->dCAT[k], B, Hc, Cc, Co, Co);
+        int rr = vv_colsum(dhalf.p, f16, dhalf.gs, dhalf.ld, dhalf.coff, B * Hc * Hc, Co, inv_LS, n->grads, n->slot, c.slot_param_stride, c.up_b[k], G, st);
         if (rr) return rr;
         const View &in = f.tin[k];
         VvWGrad w;
         memset(&w, 0, sizeof(w));
-        w.A = in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = Ci;
-        w.B = B; w.H = Hi; w.W = Hi;
-        w.Gd = dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
+        w.A = (const float *)in.p; w.a_gs = in.gs; w.lda = in.ld; w.a_coff = in.coff; w.Kt = Ci;
+        w.B = B; w.H = Hi; w.W = Hi; w.ab_f16 = f16;
+        w.Gd = (const float *)dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
         w.taps = t2f; w.dW = n->tdW[k]; w.dw_gs = 16LL * Co * Ci; w.G = G;
         if ((rr = fork())) return rr;
-        if ((rr = run_wgrad(n->cfg.use_tensor_cores != 0, w, sB))) return rr;
-        if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, sB))) return rr;
+        if ((rr = run_wgrad(c.use_tensor_cores != 0, w, sB))) return rr;
+        if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, inv_LS, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, sB))) return rr;
         if ((rr = mark(nullptr))) return rr;
         VvIGemm p;
         memset(&p, 0, sizeof(p));
-        p.A = dhalf.p; p.a_gs = dhalf.gs; p.lda = dhalf.ld; p.a_coff = dhalf.coff; p.a_s2d = 1; p.Kt = 4 * Co;
+        p.A = (const float *)dhalf.p; p.a_gs = dhalf.gs; p.lda = dhalf.ld; p.a_coff = dhalf.coff; p.a_s2d = 1; p.Kt = 4 * Co; p.ab_f16 = f16;
         p.B = B; p.H = Hi; p.W = Hi;
-        p.Wt = n->tWd[k]; p.w_gs = 16LL * Co * Ci; p.taps = t2b; p.N = Ci;
-        p.O = ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
+        p.Wt = (const float *)n->tWd[k]; p.w_gs = 16LL * Co * Ci; p.taps = t2b; p.N = Ci;
+        p.O = (float *)ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
         p.bias = nullptr; p.stats = nullptr; p.G = G;
         if ((rr = before_write(ddeep.p))) return rr;
-        return run_igemm(n->cfg.use_tensor_cores != 0, p, st);
+        return run_igemm(c.use_tensor_cores != 0, p, st);
     };
 
-    // ---- decoder, deepest last.  GA holds dU3 now.
+    // ---- decoder, deepest last.  GA holds dU3 now (external gradients), or nothing (fused: formed from DOUT on the fly).
     float *ga = n->GA, *gb = n->GB;
     for (int k = 2; k >= 0; k--) {
         const int H = S >> (2 - k), C = F << (3 - k);          // concat geometry of up-block k
         const int u2 = 9 + 2 * k, u1 = 8 + 2 * k;
         View dy2 = mk(ga, B, H, C / 2, 0, C / 2);               // d(output of second conv)
         View dmid = mk(gb, B, H, C / 2, 0, C / 2);
-        if ((r = unit_bwd(u2, dy2, ga, &dmid))) return r;        // dz in place in ga, d(mid) -> gb
+        if ((r = unit_bwd(u2, dy2, ga, &dmid, -1))) return r;    // fp32: dz in place in ga; d(mid) -> gb
         View dcat = mk(n->dCAT[k], B, H, C, 0, C);
-        if ((r = unit_bwd(u1, dmid, gb, &dcat))) return r;       // dz in place in gb, d(concat) -> dCAT[k]
+        if ((r = unit_bwd(u1, dmid, gb, &dcat, k))) return r;    // fp32: dz in place in gb; d(concat) -> dCAT[k] (+ dUP[k])
         View ddeep = mk(ga, B, H / 2, C, 0, C);                  // d(X4 / U1 / U2): [B,(H/2)^2, C]
         if ((r = convT_bwd(k, ddeep))) return r;
     }
@@ -602,20 +653,24 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         View dy2;
         if (k == 3) dy2 = mk(ga, B, H, N, 0, N);
         else dy2 = mk(n->dCAT[2 - k], B, H, 2 * N, 0, N);       // first half of the concat gradient (+ pooled path, added below)
+        // fp32 modes: dZ of the second conv replaces its dY in place (ga), or goes to gb when dY sits in dCAT; d(mid) takes the other
+        // scratch buffer and d(pooled input) the first again.  fp16 mode: dZ lives in the ring, so d(mid) -> gb, d(pooled input) -> ga.
         float *dz2 = (k == 3) ? ga : gb;
-        float *other = (dz2 == ga) ? gb : ga;
+        float *other = f16 ? gb : ((dz2 == ga) ? gb : ga);
+        float *pool_buf = f16 ? ga : dz2;
         View dmid = mk(other, B, H, N, 0, N);
-        if ((r = unit_bwd(u2, dy2, dz2, &dmid))) return r;
+        if ((r = unit_bwd(u2, dy2, dz2, &dmid, -1))) return r;
         if (k == 0) {
-            if ((r = unit_bwd(u1, dmid, other, nullptr))) return r;   // first conv: its input needs no gradient
+            if ((r = unit_bwd(u1, dmid, other, nullptr, -1))) return r;   // first conv: its input needs no gradient
         } else {
-            // d(pooled input) -> the remaining scratch buffer, then routed through the max-pool into dCAT[3-k]
-            View dpool = mk(dz2, B, H, n->uC[u1], 0, n->uC[u1]);
-            if ((r = unit_bwd(u1, dmid, other, &dpool))) return r;
+            // d(pooled input) -> scratch, then routed through the max-pool into the skip half of dCAT[3-k]
+            View dpool = mk(pool_buf, B, H, n->uC[u1], 0, n->uC[u1]);
+            if ((r = unit_bwd(u1, dmid, other, &dpool, -1))) return r;
             const int Hs = 2 * H, Cs = n->uC[u1];                 // skip tensor geometry (x_k) : [B,Hs,Hs,Cs] inside CAT[3-k]
             View ysk = mk(n->CAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
             View dsk = mk(n->dCAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
-            if ((r = vv_maxpool_bwd(ysk.p, ysk.gs, ysk.ld, ysk.coff, dpool.p, dpool.gs, dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B, Hs, Hs, Cs, st)))
+            if ((r = vv_maxpool_bwd(ysk.p, f16, ysk.gs, ysk.ld, ysk.coff, (const float *)dpool.p, dpool.gs, (float *)dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B,
+                                    Hs, Hs, Cs, st)))
                 return r;
         }
     }
@@ -624,6 +679,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         VvPrepAll all;
         memset(&all, 0, sizeof(all));
         all.n = NU;
+        all.scale = inv_LS;
         for (int u = 0; u < NU; u++) {
             VvPrepUnit &pu = all.u[u];
             pu.w_off = c.conv_w[u]; pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
@@ -634,165 +690,14 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     return 0;
 }
 
-// ---- single-op export: 3x3 pad-1 convolution on one NHWC tensor (unit tests, single-kernel profiling)
-extern "C" int vecvad_conv3x3_forward(const float *in, int ld_in, const float *w, const float *bias, float *out, double *stats,
-                                      float *scratch, int batch, int h, int wd, int cin, int cout, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(in && w && out && scratch, "conv3x3_forward: null argument");
-    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && ld_in >= cin && ld_in % 4 == 0, "conv3x3_forward: cin/cout must be multiples of 16");
-    cudaStream_t st = (cudaStream_t)stream;
-    VvIntG slot;
-    memset(&slot, 0, sizeof(slot));
-    int r = vv_prep_conv_w(w, slot, 0, 0, 0, 0, 0, cout, cin, cin, scratch, 0, nullptr, 0, nullptr, 0, 1, st);
-    if (r) return r;
-    if (stats) VV_CK(cudaMemsetAsync(stats, 0, 2 * cout * sizeof(double), st));
-    VvIGemm p;
-    memset(&p, 0, sizeof(p));
-    p.A = in; p.a_gs = 0; p.lda = ld_in; p.Kt = cin; p.B = batch; p.H = h; p.W = wd;
-    p.Wt = scratch; p.taps = taps3x3(+1); p.N = cout;
-    p.O = out; p.ldo = cout; p.bias = bias; p.stats = stats; p.G = 1;
-    if (use_tc) {
-        VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_forward: shape not supported by the tcgen05 path");
-        if (use_tc == 5 || use_tc == 6) {   // fp16 operands (experiment): 5 = flattened-sequence tiles, 6 = pair tiles.
-                                            // Operands are converted here; scratch holds [9*cout*cin fp32 weights][9*cout*cin fp16
-                                            // weights][batch*h*wd*cin fp16 input]
-            char *w16 = (char *)(scratch + 9LL * cout * cin);
-            char *in16 = w16 + (((9LL * cout * cin * 2) + 255) / 256) * 256;
-            if ((r = vv_f32_to_f16(scratch, cin, cin, 9LL * cout, w16, st))) return r;
-            if ((r = vv_f32_to_f16(in, ld_in, cin, (long long)batch * h * wd, in16, st))) return r;
-            p.A = (const float *)in16; p.lda = cin; p.Wt = (const float *)w16; p.ab_f16 = 1;
-            if (use_tc == 6) {
-                VV_REQUIRE(vv_igemm_tc3_supported(p), "conv3x3_forward: shape not supported by the fp16 pair tcgen05 path");
-                return vv_launch_igemm_tc3(p, st);
-            }
-            VV_REQUIRE(vv_igemm_flat_shape_ok(p), "conv3x3_forward: shape not supported by the flattened fp16 tcgen05 path");
-            return vv_launch_igemm_flat(p, st);
-        }
-        if (use_tc == 4) {       // pair tiles
-            VV_REQUIRE(vv_igemm_tc3_supported(p), "conv3x3_forward: shape not supported by the pair tcgen05 path");
-            return vv_launch_igemm_tc3(p, st);
-        }
-        if (use_tc == 3) {       // flattened-sequence tiles
-            VV_REQUIRE(vv_igemm_flat_shape_ok(p), "conv3x3_forward: shape not supported by the flattened tcgen05 path");
-            return vv_launch_igemm_flat(p, st);
-        }
-        if (use_tc == 2) {       // persistent tap-reuse tiles
-            VV_REQUIRE(vv_igemm_tc2_supported(p), "conv3x3_forward: shape not supported by the persistent tcgen05 path");
-            return vv_launch_igemm_tc2(p, st);
-        }
-        return vv_launch_igemm_tc(p, st);
+extern "C" int vecvad_net_set_loss_scale(vecvad_net *n, float scale) {
+    VV_REQUIRE(n, "set_loss_scale: null net");
+    if (scale > 0.f) {
+        int e;
+        VV_REQUIRE(frexpf(scale, &e) == 0.5f, "set_loss_scale: %g is not a power of two", (double)scale);
     }
-    return vv_launch_igemm_simt(p, st);
-}
-
-// ---- single-op export: weight gradient of the 3x3 pad-1 convolution, dw[cout][cin][3][3] = sum_pixels grad_out x shifted in
-extern "C" int vecvad_conv3x3_wgrad(const float *in, int ld_in, const float *grad_out, float *dw, float *scratch, int batch, int h, int wd,
-                                    int cin, int cout, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(in && grad_out && dw && scratch, "conv3x3_wgrad: null argument");
-    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && ld_in >= cin && ld_in % 4 == 0, "conv3x3_wgrad: cin/cout must be multiples of 16");
-    cudaStream_t st = (cudaStream_t)stream;
-    VV_CK(cudaMemsetAsync(scratch, 0, 9LL * cout * cin * sizeof(float), st));
-    VvWGrad w;
-    memset(&w, 0, sizeof(w));
-    w.A = in; w.lda = ld_in; w.Kt = cin; w.B = batch; w.H = h; w.W = wd;
-    w.Gd = grad_out; w.ldg = cout; w.N = cout; w.taps = taps3x3(+1); w.dW = scratch; w.G = 1;
-    int r;
-    if (use_tc) {
-        VV_REQUIRE(vv_wgrad_tc_supported(w), "conv3x3_wgrad: shape not supported by the tcgen05 path");
-        if (use_tc == 2) VV_REQUIRE(vv_wgrad_tc2_supported(w), "conv3x3_wgrad: shape not supported by the tap-reuse tcgen05 path");
-        if (use_tc == 3) VV_REQUIRE(vv_wgrad_flat_shape_ok(w), "conv3x3_wgrad: shape not supported by the flattened tcgen05 path");
-        r = use_tc == 3 ? vv_launch_wgrad_flat(w, st) : (use_tc == 2 ? vv_launch_wgrad_tc2(w, st) : vv_launch_wgrad_tc(w, st));
-    } else {
-        r = vv_launch_wgrad_simt(w, st);
-    }
-    if (r) return r;
-    VvIntG slot;
-    memset(&slot, 0, sizeof(slot));
-    return vv_scatter_conv_wgrad(scratch, 0, cout, cin, cin, dw, slot, 0, 0, 1, st);
-}
-
-// ---- single-op export: input gradient of the 3x3 pad-1 convolution (the engine's dgrad launch: flipped taps, Wd operand)
-extern "C" int vecvad_conv3x3_dgrad(const float *grad_out, const float *w, float *grad_in, float *scratch, int batch, int h, int wd, int cin,
-                                    int cout, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(grad_out && w && grad_in && scratch, "conv3x3_dgrad: null argument");
-    VV_REQUIRE(cin % 16 == 0 && cout % 16 == 0, "conv3x3_dgrad: cin/cout must be multiples of 16");
-    cudaStream_t st = (cudaStream_t)stream;
-    VvIntG slot;
-    memset(&slot, 0, sizeof(slot));
-    float *Wf = scratch, *Wd = scratch + 9LL * cout * cin;
-    int r = vv_prep_conv_w(w, slot, 0, 0, 0, 0, 0, cout, cin, cin, Wf, 0, Wd, 0, nullptr, 0, 1, st);
-    if (r) return r;
-    VvIGemm p;
-    memset(&p, 0, sizeof(p));
-    p.A = grad_out; p.lda = cout; p.Kt = cout; p.B = batch; p.H = h; p.W = wd;
-    p.Wt = Wd; p.taps = taps3x3(-1); p.N = cin;
-    p.O = grad_in; p.ldo = cin; p.G = 1;
-    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "conv3x3_dgrad: shape not supported by the tcgen05 path");
-    return run_igemm(use_tc != 0, p, st);
-}
-
-// ---- single-op exports: ConvTranspose2d(k3, s2, p1, output_padding 1) as the engine runs it (model/unet.py:54): four sub-pixel
-// phases = a 2x2-tap conv over N = 4*Co columns whose epilogue pixel-shuffles into a [B,2H,2W,ld_out] tensor at channel out_coff.
-// scratch: 32*Co*Ci + Co floats (forward / dgrad) or 48*Co*Ci + Co (wgrad).
-static int ct_prep(const float *w, const float *bias, int ci, int co, float *scratch, cudaStream_t st, float **Wf, float **Wd, float **vec) {
-    VvIntG slot;
-    memset(&slot, 0, sizeof(slot));
-    *Wf = scratch; *Wd = scratch + 16LL * co * ci; *vec = scratch + 32LL * co * ci;
-    // vv_prep_ct_w reads weight and bias at offsets of one base pointer
-    return vv_prep_ct_w(w, slot, 0, 0, bias ? (long long)(bias - w) : 0, ci, co, *Wf, 0, *Wd, 0, *vec, 0, 1, st);
-}
-
-extern "C" int vecvad_convt3x3s2_forward(const float *in, const float *w, const float *bias, float *out, int ld_out, int out_coff,
-                                         float *scratch, int batch, int h, int wd, int ci, int co, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(in && w && bias && out && scratch, "convt_forward: null argument");
-    VV_REQUIRE(ci % 32 == 0 && co % 16 == 0 && ld_out >= out_coff + co, "convt_forward: bad channel counts");
-    cudaStream_t st = (cudaStream_t)stream;
-    float *Wf, *Wd, *vec;
-    int r = ct_prep(w, bias, ci, co, scratch, st, &Wf, &Wd, &vec);
-    if (r) return r;
-    VvIGemm p;
-    memset(&p, 0, sizeof(p));
-    p.A = in; p.lda = ci; p.Kt = ci; p.B = batch; p.H = h; p.W = wd;
-    p.Wt = Wf; p.taps = taps2x2(+1); p.N = 4 * co;
-    p.O = out; p.ldo = ld_out; p.o_coff = out_coff; p.o_d2s = 1;
-    p.bias = vec; p.G = 1;
-    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "convt_forward: shape not supported by the tcgen05 path");
-    return run_igemm(use_tc != 0, p, st);
-}
-
-extern "C" int vecvad_convt3x3s2_dgrad(const float *grad_out, int ld, int coff, const float *w, float *grad_in, float *scratch, int batch,
-                                       int h, int wd, int ci, int co, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(grad_out && w && grad_in && scratch, "convt_dgrad: null argument");
-    VV_REQUIRE(ci % 32 == 0 && co % 32 == 0 && ld >= coff + co, "convt_dgrad: bad channel counts");
-    cudaStream_t st = (cudaStream_t)stream;
-    float *Wf, *Wd, *vec;
-    int r = ct_prep(w, nullptr, ci, co, scratch, st, &Wf, &Wd, &vec);
-    if (r) return r;
-    VvIGemm p;
-    memset(&p, 0, sizeof(p));
-    p.A = grad_out; p.lda = ld; p.a_coff = coff; p.a_s2d = 1; p.Kt = 4 * co; p.B = batch; p.H = h; p.W = wd;
-    p.Wt = Wd; p.taps = taps2x2(-1); p.N = ci;
-    p.O = grad_in; p.ldo = ci; p.G = 1;
-    if (use_tc) VV_REQUIRE(vv_igemm_tc_supported(p), "convt_dgrad: shape not supported by the tcgen05 path");
-    return run_igemm(use_tc != 0, p, st);
-}
-
-extern "C" int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int coff, float *dw, float *scratch, int batch, int h,
-                                       int wd, int ci, int co, int use_tc, vecvad_stream stream) {
-    VV_REQUIRE(in && grad_out && dw && scratch, "convt_wgrad: null argument");
-    VV_REQUIRE(ci % 32 == 0 && co % 32 == 0 && ld >= coff + co, "convt_wgrad: bad channel counts");
-    cudaStream_t st = (cudaStream_t)stream;
-    VV_CK(cudaMemsetAsync(scratch, 0, 16LL * co * ci * sizeof(float), st));
-    VvWGrad w;
-    memset(&w, 0, sizeof(w));
-    w.A = in; w.lda = ci; w.Kt = ci; w.B = batch; w.H = h; w.W = wd;
-    w.Gd = grad_out; w.ldg = ld; w.g_coff = coff; w.g_s2d = 1; w.N = 4 * co;
-    w.taps = taps2x2(+1); w.dW = scratch; w.G = 1;
-    if (use_tc) VV_REQUIRE(vv_wgrad_tc_supported(w), "convt_wgrad: shape not supported by the tcgen05 path");
-    int r = run_wgrad(use_tc != 0, w, st);
-    if (r) return r;
-    VvIntG slot;
-    memset(&slot, 0, sizeof(slot));
-    return vv_scatter_ct_wgrad(scratch, 0, ci, co, dw, slot, 0, 0, 1, st);
+    n->lscale_user = scale;
+    return 0;
 }
 
 extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *dst, int64_t max_floats, int64_t *n_floats,
@@ -800,29 +705,34 @@ extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *
     VV_REQUIRE(n && n->ws && dst && n_floats && n->lastB > 0, "debug_read: net not bound / no forward yet");
     const long long G = n->G, B = n->lastB, F = n->F, S = n->S;
     auto M = [&](long long H) { return B * H * H; };
-    const float *src = nullptr;
+    const void *src = nullptr;
     long long cnt = 0;
+    bool half = false;                       // the buffer holds fp16 in the fp16-operand mode: converted on the way out
     const int u = index, k = index;
     switch (kind) {
-        case 0: src = n->X0; cnt = G * M(S) * n->cinp; break;
+        case 0: src = n->X0; cnt = G * M(S) * n->cinp; half = true; break;
         case 1: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Z[u]; cnt = G * M(n->uH[u]) * n->uN[u]; break;
-        case 2: VV_REQUIRE(u >= 0 && u < NU && u % 2 == 0, "debug_read: unit"); src = n->A[u]; cnt = G * M(n->uH[u]) * n->uN[u]; break;
-        case 3: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->CAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); break;
-        case 4: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->PL[k]; cnt = G * M(S >> (k + 1)) * (F << k); break;
-        case 5: src = n->X4; cnt = G * M(S >> 3) * 8 * F; break;
-        case 6: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->UU[k]; cnt = G * M(S >> (2 - k)) * (F << (2 - k)); break;
+        case 2: VV_REQUIRE(u >= 0 && u < NU && u % 2 == 0, "debug_read: unit"); src = n->A[u]; cnt = G * M(n->uH[u]) * n->uN[u]; half = true; break;
+        case 3: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->CAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); half = true; break;
+        case 4: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->PL[k]; cnt = G * M(S >> (k + 1)) * (F << k); half = true; break;
+        case 5: src = n->X4; cnt = G * M(S >> 3) * 8 * F; half = true; break;
+        case 6: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->UU[k]; cnt = G * M(S >> (2 - k)) * (F << (2 - k)); half = true; break;
         case 7: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->dCAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); break;
         case 8: src = n->GA; cnt = G * M(S) * F; break;
         case 9: src = n->GB; cnt = G * M(S) * F; break;
         case 10: src = n->DOUT; cnt = G * M(S) * 4; break;
-        case 11: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Wf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; break;
+        case 11: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Wf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; half = true; break;
         case 12: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->dWf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; break;
-        case 13: VV_REQUIRE(k >= 0 && k < NT, "debug_read: k"); src = n->tWf[k]; cnt = G * 16 * n->tCo[k] * n->tCi[k]; break;
+        case 13: VV_REQUIRE(k >= 0 && k < NT, "debug_read: k"); src = n->tWf[k]; cnt = G * 16 * n->tCo[k] * n->tCi[k]; half = true; break;
         case 14: VV_REQUIRE(k >= 0 && k < NT, "debug_read: k"); src = n->tdW[k]; cnt = G * 16 * n->tCo[k] * n->tCi[k]; break;
+        case 15: VV_REQUIRE(k >= 0 && k < 3 && n->f16, "debug_read: dUP exists in the fp16 mode only"); src = n->dUP[k];
+                 cnt = G * M(S >> (2 - k)) * (F << (2 - k)); half = true; break;
+        case 16: VV_REQUIRE(k >= 0 && k < 4 && n->f16, "debug_read: the dZ ring exists in the fp16 mode only"); src = n->HZ[k]; cnt = G * M(S) * F; half = true; break;
         default: return vv_set_err(-1, "debug_read: unknown kind %d", kind);
     }
     VV_REQUIRE(cnt <= max_floats, "debug_read: destination too small (%lld > %lld)", cnt, (long long)max_floats);
-    VV_CK(cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     *n_floats = cnt;
+    if (half && n->f16) return vv_f16_to_f32(src, cnt, dst, (cudaStream_t)stream);
+    VV_CK(cudaMemcpyAsync(dst, src, cnt * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }

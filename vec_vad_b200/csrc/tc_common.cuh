@@ -1,6 +1,7 @@
 // tcgen05 / TMA / mbarrier PTX wrappers and tensor-map helpers shared by the tensor-core tile kernels (sm_100a).
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.h"
@@ -114,6 +115,17 @@ __device__ __forceinline__ uint32_t idesc_tf32(int n) {
 
 // instruction descriptor: D fp32, A/B fp16, both K-major, M = 128, N = n
 __device__ __forceinline__ uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+
+// four floats -> four fp16 (round to nearest, saturating at the fp16 range instead of producing infinities)
+__device__ __forceinline__ uint2 pack_half4(const float4 &v) {
+    const float m = 65504.f;
+    __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x, -m), m), fminf(fmaxf(v.y, -m), m));
+    __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z, -m), m), fminf(fmaxf(v.w, -m), m));
+    uint2 o;
+    o.x = *reinterpret_cast<unsigned *>(&lo);
+    o.y = *reinterpret_cast<unsigned *>(&hi);
+    return o;
+}
 
 // one lane of a fully active warp; the surrounding loop stays warp-uniform so descriptors live in uniform registers
 __device__ __forceinline__ bool elect_one() {

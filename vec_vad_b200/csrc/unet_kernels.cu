@@ -11,6 +11,36 @@
 
 namespace {
 
+// element-typed 4-wide access: H = fp16 storage (8 bytes), else fp32 (16 bytes); idx in elements
+__device__ __forceinline__ uint2 pack_h4(const float4 &v) {
+    const float m = 65504.f;                     // saturate instead of producing infinities
+    __half2 lo = __floats2half2_rn(fminf(fmaxf(v.x, -m), m), fminf(fmaxf(v.y, -m), m));
+    __half2 hi = __floats2half2_rn(fminf(fmaxf(v.z, -m), m), fminf(fmaxf(v.w, -m), m));
+    uint2 o;
+    o.x = *reinterpret_cast<unsigned *>(&lo);
+    o.y = *reinterpret_cast<unsigned *>(&hi);
+    return o;
+}
+template <bool H>
+__device__ __forceinline__ float4 ld4(const void *base, long long idx) {
+    if (H) {
+        const uint2 r = *reinterpret_cast<const uint2 *>(reinterpret_cast<const __half *>(base) + idx);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x)), b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+        return make_float4(a.x, a.y, b.x, b.y);
+    }
+    return *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + idx);
+}
+template <bool H>
+__device__ __forceinline__ void st4(void *base, long long idx, const float4 &v) {
+    if (H) *reinterpret_cast<uint2 *>(reinterpret_cast<__half *>(base) + idx) = pack_h4(v);
+    else *reinterpret_cast<float4 *>(reinterpret_cast<float *>(base) + idx) = v;
+}
+
+__device__ __forceinline__ void st1(void *base, long long idx, float v, int h) {
+    if (h) reinterpret_cast<__half *>(base)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
+    else reinterpret_cast<float *>(base)[idx] = v;
+}
+
 __device__ __forceinline__ void pix3(int m, int H, int W, int &b, int &y, int &x) {
     x = m % W;
     int t = m / W;
@@ -19,7 +49,8 @@ __device__ __forceinline__ void pix3(int m, int H, int W, int &b, int &y, int &x
 }
 
 // ---- input staging: x NCHW [B, 3*T, S, S] -> X0 [G][B*S*S][cinp] with frame erase[g] dropped or zeroed (model/unet.py:179-183)
-__global__ void k_prep_input(const float *__restrict__ x, float *__restrict__ X0, int B, int T, int S, int cinp, int padding,
+template <bool H>
+__global__ void k_prep_input(const float *__restrict__ x, void *__restrict__ X0, int B, int T, int S, int cinp, int padding,
                              VvIntG erase) {
     const int g = blockIdx.y;
     const int M = B * S * S;
@@ -28,7 +59,7 @@ __global__ void k_prep_input(const float *__restrict__ x, float *__restrict__ X0
     const int pix = m % (S * S), b = m / (S * S);
     const int e = erase.v[g];
     const float *xb = x + (long long)b * 3 * T * S * S + pix;
-    float *dst = X0 + ((long long)g * M + m) * cinp;
+    const long long dst = ((long long)g * M + m) * cinp;
     const int creal = padding ? 3 * T : 3 * (T - 1);
     for (int c4 = 0; c4 < cinp; c4 += 4) {
         float v[4];
@@ -43,15 +74,15 @@ __global__ void k_prep_input(const float *__restrict__ x, float *__restrict__ X0
             }
             v[j] = val;
         }
-        *reinterpret_cast<float4 *>(dst + c4) = make_float4(v[0], v[1], v[2], v[3]);
+        st4<H>(X0, dst + c4, make_float4(v[0], v[1], v[2], v[3]));
     }
 }
 
 // ---- weight re-layout, once per step.  Conv2d weight [N][C][3][3] -> Wf[t][N][Cp] (forward B operand, K contiguous)
 //      and Wd[t][C][N] (dgrad B operand); bias / gamma / beta gathered into a uniform-stride vector block [3][N].
 __global__ void k_prep_conv_w(const float *__restrict__ params, VvIntG slot, long long slot_stride, long long w_off, long long b_off,
-                              long long g_off, long long beta_off, int N, int C, int Cp, float *__restrict__ Wf, long long wf_gs,
-                              float *__restrict__ Wd, long long wd_gs, float *__restrict__ vec, long long vec_gs) {
+                              long long g_off, long long beta_off, int N, int C, int Cp, void *__restrict__ Wf, long long wf_gs,
+                              void *__restrict__ Wd, long long wd_gs, int w_f16, float *__restrict__ vec, long long vec_gs) {
     const int g = blockIdx.y;
     const float *P = params + slot.v[g] * slot_stride;
     const int total = 9 * N * Cp;
@@ -61,8 +92,8 @@ __global__ void k_prep_conv_w(const float *__restrict__ params, VvIntG slot, lon
         int n = (i / Cp) % N;
         int t = i / (Cp * N);
         float v = (c < C) ? P[w_off + ((long long)n * C + c) * 9 + t] : 0.f;
-        Wf[g * wf_gs + i] = v;
-        if (Wd && c < C) Wd[g * wd_gs + ((long long)t * C + c) * N + n] = v;
+        st1(Wf, g * wf_gs + i, v, w_f16);
+        if (Wd && c < C) st1(Wd, g * wd_gs + ((long long)t * C + c) * N + n, v, w_f16);
     }
     if (blockIdx.x == 0 && vec) {
         for (int n = threadIdx.x; n < N; n += blockDim.x) {
@@ -77,8 +108,8 @@ __global__ void k_prep_conv_w(const float *__restrict__ params, VvIntG slot, lon
 // (288 contiguous floats per output channel) and both writes (128-byte runs along c for Wf, along n for Wd) are coalesced.
 __global__ void __launch_bounds__(256) k_prep_conv_w_tiled(const float *__restrict__ params, VvIntG slot, long long slot_stride,
                                                            long long w_off, long long b_off, long long g_off, long long beta_off, int N,
-                                                           int C, int Cp, float *__restrict__ Wf, long long wf_gs, float *__restrict__ Wd,
-                                                           long long wd_gs, float *__restrict__ vec, long long vec_gs) {
+                                                           int C, int Cp, void *__restrict__ Wf, long long wf_gs, void *__restrict__ Wd,
+                                                           long long wd_gs, int w_f16, float *__restrict__ vec, long long vec_gs) {
     __shared__ float tile[32][32 * 9 + 1];
     const int g = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *P = params + slot.v[g] * slot_stride;
@@ -90,12 +121,12 @@ __global__ void __launch_bounds__(256) k_prep_conv_w_tiled(const float *__restri
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
         const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
-        Wf[g * wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c] = tile[n][c * 9 + t];
+        st1(Wf, g * wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c, tile[n][c * 9 + t], w_f16);
     }
     if (Wd) {
         for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
             const int n = i & 31, c = (i >> 5) & 31, t = i >> 10;
-            if (c < cw) Wd[g * wd_gs + ((long long)t * C + c0 + c) * N + n0 + n] = tile[n][c * 9 + t];
+            if (c < cw) st1(Wd, g * wd_gs + ((long long)t * C + c0 + c) * N + n0 + n, tile[n][c * 9 + t], w_f16);
         }
     }
     if (blockIdx.x == 0 && blockIdx.y == 0 && vec) {
@@ -130,12 +161,12 @@ __global__ void __launch_bounds__(256) k_prep_conv_w_all(const float *__restrict
     __syncthreads();
     for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
         const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
-        U.Wf[g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c] = tile[n][c * 9 + t];
+        st1(U.Wf, g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c, tile[n][c * 9 + t], all.w_f16);
     }
     if (U.Wd) {
         for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
             const int n = i & 31, c = (i >> 5) & 31, t = i >> 10;
-            if (c < cw) U.Wd[g * U.wd_gs + ((long long)t * C + c0 + c) * N + n0 + n] = tile[n][c * 9 + t];
+            if (c < cw) st1(U.Wd, g * U.wd_gs + ((long long)t * C + c0 + c) * N + n0 + n, tile[n][c * 9 + t], all.w_f16);
         }
     }
     if (lb == 0) {
@@ -164,7 +195,7 @@ __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_all(float *__restric
     float *Gp = grads + slot.v[g] * slot_stride + U.w_off;
     for (int i = threadIdx.x; i < 32 * 288; i += 256) {
         const int n = i / 288, r = i - n * 288;
-        if (r < cw * 9) Gp[((long long)(n0 + n) * C + c0) * 9 + r] = tile[n][r];
+        if (r < cw * 9) Gp[((long long)(n0 + n) * C + c0) * 9 + r] = tile[n][r] * all.scale;
     }
 }
 
@@ -172,7 +203,7 @@ __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_all(float *__restric
 //   out[2y+py, 2x+px, co] = sum_{sy,sx in {0,1}} in[y+sy, x+sx, :] . Wt[:, co, ky, kx],  ky = py+1-2sy, kx = px+1-2sx (if in 0..2)
 //   Wbf[s][(p,co)][ci]  (forward, N = 4Co, Kt = Ci)      Wbd[s][ci][(p,co)]  (input gradient, N = Ci, Kt = 4Co)
 __global__ void k_prep_ct_w(const float *__restrict__ params, VvIntG slot, long long slot_stride, long long w_off, long long b_off,
-                            int Ci, int Co, float *__restrict__ Wbf, long long wf_gs, float *__restrict__ Wbd, long long wd_gs,
+                            int Ci, int Co, void *__restrict__ Wbf, long long wf_gs, void *__restrict__ Wbd, long long wd_gs, int w_f16,
                             float *__restrict__ vec, long long vec_gs) {
     const int g = blockIdx.y;
     const float *P = params + slot.v[g] * slot_stride;
@@ -186,8 +217,8 @@ __global__ void k_prep_ct_w(const float *__restrict__ params, VvIntG slot, long 
         int ky = (ph >> 1) + 1 - 2 * (s >> 1), kx = (ph & 1) + 1 - 2 * (s & 1);
         float v = 0.f;
         if (ky >= 0 && kx >= 0) v = P[w_off + (((long long)ci * Co + co) * 3 + ky) * 3 + kx];
-        Wbf[g * wf_gs + i] = v;                                                     // [s][ph*Co+co][ci]
-        Wbd[g * wd_gs + ((long long)s * Ci + ci) * (4 * Co) + ph * Co + co] = v;    // [s][ci][ph*Co+co]
+        st1(Wbf, g * wf_gs + i, v, w_f16);                                                     // [s][ph*Co+co][ci]
+        st1(Wbd, g * wd_gs + ((long long)s * Ci + ci) * (4 * Co) + ph * Co + co, v, w_f16);    // [s][ci][ph*Co+co]
     }
     if (blockIdx.x == 0)
         for (int n = threadIdx.x; n < Co; n += blockDim.x) vec[g * vec_gs + n] = P[b_off + n];
@@ -225,7 +256,9 @@ __device__ __forceinline__ void bn_scale_shift(const VvBnApply &p, int g, int c,
     }
 }
 
-// thread = (output pixel or pooled pixel, 4 channels).  blockDim = (C/4 <= 128 .. , rows)
+// thread = (output pixel or pooled pixel, 4 channels).  blockDim = (C/4 <= 128 .. , rows).  H: Y / P are fp16 (the operands of the
+// next contraction; rounded once, here, exactly as the tf32 path rounds them on their way into shared memory)
+template <bool H>
 __global__ void k_bn_apply(const VvBnApply p) {
     extern __shared__ float sm[];          // scale[C], shift[C]
     const int g = blockIdx.y;
@@ -239,8 +272,14 @@ __global__ void k_bn_apply(const VvBnApply p) {
     }
     __syncthreads();
     const float *Z = p.Z + g * p.z_gs;
-    float *Y = p.Y + g * p.y_gs;
+    const long long y0 = g * p.y_gs + p.y_coff;
     const int cq = p.C >> 2;
+    auto act = [](const float4 &z, const float4 &sc, const float4 &sh) {
+        float4 y;
+        y.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
+        y.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
+        return y;
+    };
     if (!p.pool) {
         for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
             const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c4 * 4);
@@ -253,23 +292,15 @@ __global__ void k_bn_apply(const VvBnApply p) {
 #pragma unroll
                 for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    float4 y;
-                    y.x = fmaxf(fmaf(z[u].x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z[u].y, sc.y, sh.y), 0.f);
-                    y.z = fmaxf(fmaf(z[u].z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z[u].w, sc.w, sh.w), 0.f);
-                    *reinterpret_cast<float4 *>(Y + (long long)(m + u * stride) * p.ldy + p.y_coff + c4 * 4) = y;
-                }
+                for (int u = 0; u < 4; u++) st4<H>(p.Y, y0 + (long long)(m + u * stride) * p.ldy + c4 * 4, act(z[u], sc, sh));
             }
             for (; m < p.M; m += stride) {
-                float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                float4 y;
-                y.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-                y.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
-                *reinterpret_cast<float4 *>(Y + (long long)m * p.ldy + p.y_coff + c4 * 4) = y;
+                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
+                st4<H>(p.Y, y0 + (long long)m * p.ldy + c4 * 4, act(z, sc, sh));
             }
         }
     } else {
-        float *Pl = p.P + g * p.p_gs;
+        const long long p0 = g * p.p_gs;
         const int Hp = p.H >> 1, Wp = p.W >> 1;
         const int Mp = p.M >> 2;
         for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
@@ -279,17 +310,20 @@ __global__ void k_bn_apply(const VvBnApply p) {
                 int b, yp, xp;
                 pix3(mp, Hp, Wp, b, yp, xp);
                 float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);   // post-ReLU values are >= 0
+                float4 z[4];
+                long long mi[4];
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
-                    long long m = ((long long)(b * p.H + 2 * yp + (w >> 1))) * p.W + 2 * xp + (w & 1);
-                    float4 z = *reinterpret_cast<const float4 *>(Z + m * p.C + c4 * 4);
-                    float4 y;
-                    y.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-                    y.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
-                    *reinterpret_cast<float4 *>(Y + m * p.ldy + p.y_coff + c4 * 4) = y;
+                    mi[w] = ((long long)(b * p.H + 2 * yp + (w >> 1))) * p.W + 2 * xp + (w & 1);
+                    z[w] = *reinterpret_cast<const float4 *>(Z + mi[w] * p.C + c4 * 4);
+                }
+#pragma unroll
+                for (int w = 0; w < 4; w++) {
+                    const float4 y = act(z[w], sc, sh);
+                    st4<H>(p.Y, y0 + mi[w] * p.ldy + c4 * 4, y);
                     mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
                 }
-                *reinterpret_cast<float4 *>(Pl + (long long)mp * p.C + c4 * 4) = mx;
+                st4<H>(p.P, p0 + (long long)mp * p.C + c4 * 4, mx);      // max of the fp32 values, rounded once (rounding is monotone)
             }
         }
     }
@@ -418,7 +452,7 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
 }
 
 //      pass 2: dz = scale * (dzhat - mean(dzhat) - xhat * mean(dzhat*xhat));  d gamma = sum dzhat*xhat, d beta = sum dzhat
-template <bool FUSED>
+template <bool FUSED, bool H>
 __global__ void k_bn_bwd_apply(const VvBnBwd p) {
     extern __shared__ float sm[];   // k1[C], k2[C]
     const int g = blockIdx.y;
@@ -432,16 +466,17 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         k2[c] = (float)(b / (double)p.M);
         if (blockIdx.x == 0) {
             float *G = p.grads + p.slot.v[g] * p.slot_param_stride;
-            G[p.gamma_off + c] = (float)b;
-            G[p.beta_off + c] = (float)a;
+            G[p.gamma_off + c] = (float)b * p.grad_unscale;
+            G[p.beta_off + c] = (float)a * p.grad_unscale;
         }
     }
     __syncthreads();
     const float *Z = p.Z + g * p.z_gs;
     const float *dY = p.dY + g * p.dy_gs;
-    float *dZ = p.dZ + g * p.dz_gs;
+    const long long dz0 = g * p.dz_gs;
     const float *sv = p.save + g * p.save_gs;
     const int cq = p.C >> 2;
+    const float ss = p.store_scale;
     for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
         const float4 sc = *reinterpret_cast<const float4 *>(sv + c4 * 4);
         const float4 sh = *reinterpret_cast<const float4 *>(sv + p.C + c4 * 4);
@@ -449,12 +484,13 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         const float4 is = *reinterpret_cast<const float4 *>(sv + 3 * p.C + c4 * 4);
         const float4 a1 = *reinterpret_cast<const float4 *>(k1 + c4 * 4);
         const float4 a2 = *reinterpret_cast<const float4 *>(k2 + c4 * 4);
+        const float4 scs = make_float4(sc.x * ss, sc.y * ss, sc.z * ss, sc.w * ss);      // store_scale is a power of two: exact
         auto dz_of = [&](const float4 &z, const float4 &d) {
             float4 o;
-            o.x = sc.x * ((fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f) - a1.x - (z.x - mu.x) * is.x * a2.x);
-            o.y = sc.y * ((fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f) - a1.y - (z.y - mu.y) * is.y * a2.y);
-            o.z = sc.z * ((fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f) - a1.z - (z.z - mu.z) * is.z * a2.z);
-            o.w = sc.w * ((fmaf(z.w, sc.w, sh.w) > 0.f ? d.w : 0.f) - a1.w - (z.w - mu.w) * is.w * a2.w);
+            o.x = scs.x * ((fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f) - a1.x - (z.x - mu.x) * is.x * a2.x);
+            o.y = scs.y * ((fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f) - a1.y - (z.y - mu.y) * is.y * a2.y);
+            o.z = scs.z * ((fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f) - a1.z - (z.z - mu.z) * is.z * a2.z);
+            o.w = scs.w * ((fmaf(z.w, sc.w, sh.w) > 0.f ? d.w : 0.f) - a1.w - (z.w - mu.w) * is.w * a2.w);
             return o;
         };
         const int stride = gridDim.x * blockDim.y;
@@ -481,24 +517,35 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
                     dd[u] = DO[m + u * stride];
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) *reinterpret_cast<float4 *>(dZ + (long long)(m + u * stride) * p.C + c4 * 4) = dz_of(z[u], dy_of(dd[u]));
+                for (int u = 0; u < 2; u++) st4<H>(p.dZ, dz0 + (long long)(m + u * stride) * p.C + c4 * 4, dz_of(z[u], dy_of(dd[u])));
             }
             for (; m < p.M; m += stride) {
                 const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = dz_of(z, dy_of(DO[m]));
+                st4<H>(p.dZ, dz0 + (long long)m * p.C + c4 * 4, dz_of(z, dy_of(DO[m])));
             }
+        }
+        for (; m + stride < p.M; m += 2 * stride) {          // four independent 16-byte loads in flight per thread
+            float4 z[2], d[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) st4<H>(p.dZ, dz0 + (long long)(m + u * stride) * p.C + c4 * 4, dz_of(z[u], d[u]));
         }
         for (; m < p.M; m += stride) {
             float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
             float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
-            *reinterpret_cast<float4 *>(dZ + (long long)m * p.C + c4 * 4) = dz_of(z, d);
+            st4<H>(p.dZ, dz0 + (long long)m * p.C + c4 * 4, dz_of(z, d));
         }
     }
 }
 
 // ---- MaxPool2d(2) backward: the gradient of each pooled element is added to the FIRST maximum of its 2x2 window in
 //      row-major order (ATen max_pool2d keeps the first index on ties, which are frequent after ReLU).
-__global__ void k_maxpool_bwd(const float *__restrict__ Y, long long y_gs, int ldy, int y_coff, const float *__restrict__ dP,
+template <bool H16>
+__global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ldy, int y_coff, const float *__restrict__ dP,
                               long long dp_gs, float *__restrict__ dY, long long dy_gs, int lddy, int dy_coff, int B, int H, int W,
                               int C) {
     const int g = blockIdx.y;
@@ -515,7 +562,7 @@ __global__ void k_maxpool_bwd(const float *__restrict__ Y, long long y_gs, int l
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             mi[w] = ((long long)(b * H + 2 * yp + (w >> 1))) * W + 2 * xp + (w & 1);
-            v[w] = *reinterpret_cast<const float4 *>(Y + g * y_gs + mi[w] * ldy + y_coff + c4 * 4);
+            v[w] = ld4<H16>(Y, g * y_gs + mi[w] * ldy + y_coff + c4 * 4);
         }
         int ax = 0, ay = 0, az = 0, aw = 0;
         float bx = v[0].x, by = v[0].y, bz = v[0].z, bw = v[0].w;
@@ -538,7 +585,8 @@ __global__ void k_maxpool_bwd(const float *__restrict__ Y, long long y_gs, int l
 }
 
 // ---- column sum of a (strided) gradient tensor -> ConvTranspose2d bias gradient
-__global__ void k_colsum(const float *__restrict__ D, long long d_gs, int ld, int coff, int M, int C, float *__restrict__ grads,
+template <bool H>
+__global__ void k_colsum(const void *__restrict__ D, long long d_gs, int ld, int coff, int M, int C, float scale, float *__restrict__ grads,
                          VvIntG slot, long long slot_stride, long long off) {
     extern __shared__ float sm[];   // [blockDim.y][C]
     const int g = blockIdx.y;
@@ -550,12 +598,12 @@ __global__ void k_colsum(const float *__restrict__ D, long long d_gs, int ld, in
         for (; m + 3 * stride < M; m += 4 * stride) {
             float4 d[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) d[u] = *reinterpret_cast<const float4 *>(D + g * d_gs + (long long)(m + u * stride) * ld + coff + c4 * 4);
+            for (int u = 0; u < 4; u++) d[u] = ld4<H>(D, g * d_gs + (long long)(m + u * stride) * ld + coff + c4 * 4);
 #pragma unroll
             for (int u = 0; u < 4; u++) { s.x += d[u].x; s.y += d[u].y; s.z += d[u].z; s.w += d[u].w; }
         }
         for (; m < M; m += stride) {
-            float4 d = *reinterpret_cast<const float4 *>(D + g * d_gs + (long long)m * ld + coff + c4 * 4);
+            float4 d = ld4<H>(D, g * d_gs + (long long)m * ld + coff + c4 * 4);
             s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
         }
         *reinterpret_cast<float4 *>(sm + threadIdx.y * C + c4 * 4) = s;
@@ -565,13 +613,14 @@ __global__ void k_colsum(const float *__restrict__ D, long long d_gs, int ld, in
     for (int c = tid; c < C; c += blockDim.x * blockDim.y) {
         float a = 0.f;
         for (int r = 0; r < blockDim.y; r++) a += sm[r * C + c];
-        atomicAdd(grads + slot.v[g] * slot_stride + off + c, a);
+        atomicAdd(grads + slot.v[g] * slot_stride + off + c, a * scale);
     }
 }
 
 // ---- 1x1 output conv (model/unet.py:63-70) with fused squared error and MSE gradient (train.py:385-392, 414-427).
 //      One CTA = 256 threads = one cube (S*S pixels, S*S/256 pixels per thread) of one UNet: the per-cube SSE is a
 //      deterministic in-CTA reduction.  U [G][B*S*S][F];  out NCHW;  dout [G][B*S*S][4].
+template <bool H>
 __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
     extern __shared__ float sm[];   // tile [256][F+1], w [4][F], b[4]
     const int g = blockIdx.y, b = blockIdx.x;
@@ -584,7 +633,7 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
     const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
     for (int i = threadIdx.x; i < 4 * F; i += 256) w[i] = (i < oc * F) ? P[p.w_off + i] : 0.f;
     if (threadIdx.x < 4) bs[threadIdx.x] = threadIdx.x < oc ? P[p.b_off + threadIdx.x] : 0.f;
-    const float *U = p.U + g * p.u_gs + (long long)b * SS * F;
+    const long long u0 = g * p.u_gs + (long long)b * SS * F;
     const bool flow = p.target_is_flow.v[g] != 0;
     float *out = flow ? p.of_out : p.raw_out;
     const int out_ctot = flow ? p.of_out_channels : p.raw_out_channels;
@@ -601,7 +650,7 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
         // coalesced load of 256 pixels x F channels
         for (int i = threadIdx.x; i < 256 * F / 4; i += 256) {
             int r = (i * 4) / F, c = (i * 4) % F;
-            float4 v = *reinterpret_cast<const float4 *>(U + (long long)(base + r) * F + c);
+            float4 v = ld4<H>(p.U, u0 + (long long)(base + r) * F + c);
             float *d = tile + r * (F + 1) + c;
             d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
         }
@@ -641,6 +690,7 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
 // backward of the 1x1 conv: dU[m][c] = sum_j dout[m][j] w[j][c];  dW[j][c] += sum_m dout[m][j] U[m][c];  db[j] += sum_m dout[m][j]
 // thread = (pixel slot, 4 channels): float4 loads of U / stores of dU, 256/(F/4) pixels per block iteration, two iterations in
 // flight; the weight / bias gradients are reduced in shared memory and flushed with one atomic per element per block.
+template <bool H>
 __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
     extern __shared__ float sm_ob[];            // dW partial [3][F], db partial [4]
     const int g = blockIdx.y;
@@ -649,7 +699,7 @@ __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
     const int oc = p.out_channels.v[g];
     const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
     float *G = p.grads + p.slot.v[g] * p.slot_param_stride;
-    const float *U = p.U + g * p.u_gs;
+    const long long u0 = g * p.u_gs;
     float *dU = p.dU + g * p.du_gs;
     const int SS = p.S * p.S;
     const bool flow = p.target_is_flow.v[g] != 0;
@@ -696,16 +746,16 @@ __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
         float d0[3], d1[3];
         load_d(m, d0);
         load_d(m + stride, d1);
-        const float4 u0 = *reinterpret_cast<const float4 *>(U + (long long)m * F + 4 * q);
-        const float4 u1 = *reinterpret_cast<const float4 *>(U + (long long)(m + stride) * F + 4 * q);
-        body(m, d0, u0);
-        body(m + stride, d1, u1);
+        const float4 ua = ld4<H>(p.U, u0 + (long long)m * F + 4 * q);
+        const float4 ub = ld4<H>(p.U, u0 + (long long)(m + stride) * F + 4 * q);
+        body(m, d0, ua);
+        body(m + stride, d1, ub);
     }
     if (m < p.M) {
         float d0[3];
         load_d(m, d0);
-        const float4 u0 = *reinterpret_cast<const float4 *>(U + (long long)m * F + 4 * q);
-        body(m, d0, u0);
+        const float4 ua = ld4<H>(p.U, u0 + (long long)m * F + 4 * q);
+        body(m, d0, ua);
     }
 #pragma unroll
     for (int j = 0; j < 3; j++) {
@@ -750,7 +800,7 @@ __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_tiled(const float *_
     }
 }
 
-__global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, int Ci, int Co, float *__restrict__ grads,
+__global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, int Ci, int Co, float scale, float *__restrict__ grads,
                                    VvIntG slot, long long slot_stride, long long w_off) {
     const int g = blockIdx.y;
     const int total = Ci * Co * 9;
@@ -761,7 +811,7 @@ __global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, 
     int py = (ky == 1) ? 0 : 1, sy = (ky == 0) ? 1 : 0;
     int px = (kx == 1) ? 0 : 1, sx = (kx == 0) ? 1 : 0;
     int s = sy * 2 + sx, ph = py * 2 + px;
-    grads[slot.v[g] * slot_stride + w_off + i] = dWb[g * gs + ((long long)s * 4 * Co + ph * Co + co) * Ci + ci];
+    grads[slot.v[g] * slot_stride + w_off + i] = dWb[g * gs + ((long long)s * 4 * Co + ph * Co + co) * Ci + ci] * scale;
 }
 
 // ---- losses from the per-cube SSE buffer: mean over B * ch * S * S (train.py:385-392)
@@ -846,22 +896,23 @@ static inline dim3 row_block(int C, int &rows) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-int vv_prep_input(const float *x, float *X0, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st) {
+int vv_prep_input(const float *x, void *X0, int x0_f16, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st) {
     int M = B * S * S;
-    k_prep_input<<<dim3(vv_cdiv(M, 256), G), 256, 0, st>>>(x, X0, B, T, S, cinp, padding, erase);
+    if (x0_f16) k_prep_input<true><<<dim3(vv_cdiv(M, 256), G), 256, 0, st>>>(x, X0, B, T, S, cinp, padding, erase);
+    else k_prep_input<false><<<dim3(vv_cdiv(M, 256), G), 256, 0, st>>>(x, X0, B, T, S, cinp, padding, erase);
     VV_CKL();
     return 0;
 }
 
 int vv_prep_conv_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, long long g_off,
-                   long long beta_off, int N, int C, int Cp, float *Wf, long long wf_gs, float *Wd, long long wd_gs, float *vec,
+                   long long beta_off, int N, int C, int Cp, void *Wf, long long wf_gs, void *Wd, long long wd_gs, int w_f16, float *vec,
                    long long vec_gs, int G, cudaStream_t st) {
     if (N % 32 == 0 && Cp % 32 == 0)
         k_prep_conv_w_tiled<<<dim3(N / 32, Cp / 32, G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C, Cp, Wf,
-                                                                    wf_gs, Wd, wd_gs, vec, vec_gs);
+                                                                    wf_gs, Wd, wd_gs, w_f16, vec, vec_gs);
     else
         k_prep_conv_w<<<dim3(vv_cdiv(9LL * N * Cp, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C,
-                                                                         Cp, Wf, wf_gs, Wd, wd_gs, vec, vec_gs);
+                                                                         Cp, Wf, wf_gs, Wd, wd_gs, w_f16, vec, vec_gs);
     VV_CKL();
     return 0;
 }
@@ -888,9 +939,9 @@ int vv_scatter_conv_wgrad_all(float *grads, const VvIntG &slot, long long slot_s
 }
 
 int vv_prep_ct_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, int Ci, int Co,
-                 float *Wbf, long long wf_gs, float *Wbd, long long wd_gs, float *vec, long long vec_gs, int G, cudaStream_t st) {
+                 void *Wbf, long long wf_gs, void *Wbd, long long wd_gs, int w_f16, float *vec, long long vec_gs, int G, cudaStream_t st) {
     k_prep_ct_w<<<dim3(vv_cdiv(16LL * Co * Ci, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, Ci, Co, Wbf, wf_gs, Wbd,
-                                                                     wd_gs, vec, vec_gs);
+                                                                     wd_gs, w_f16, vec, vec_gs);
     VV_CKL();
     return 0;
 }
@@ -902,7 +953,8 @@ int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st) {
     int gx = vv_cdiv(work, rows * 4);
     if (gx > 148 * 8) gx = 148 * 8;
     if (gx < 1) gx = 1;
-    k_bn_apply<<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    if (p.y_f16) k_bn_apply<true><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    else k_bn_apply<false><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
     VV_CKL();
     return 0;
 }
@@ -914,36 +966,46 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     if (gx > 148 * 4) gx = 148 * 4;
     if (gx < 1) gx = 1;
     if (p.dout) VV_REQUIRE(p.C % 4 == 0 && p.params && p.grads, "bn_bwd: fused output-conv backward needs params / grads");
+    VV_REQUIRE(!p.dz_f16 || (const void *)p.dZ != (const void *)p.dY, "bn_bwd: an fp16 dZ cannot alias dY");
     if (p.dout) k_bn_bwd_reduce<true><<<dim3(gx, G), blk, (5 * rows * p.C + 4 * rows) * sizeof(float), st>>>(p);
     else k_bn_bwd_reduce<false><<<dim3(gx, G), blk, 2 * rows * p.C * sizeof(float), st>>>(p);
     VV_CKL();
     int gx2 = vv_cdiv(p.M, rows * 4);
     if (gx2 > 148 * 8) gx2 = 148 * 8;
     if (gx2 < 1) gx2 = 1;
-    if (p.dout) k_bn_bwd_apply<true><<<dim3(gx2, G), blk, 2 * p.C * sizeof(float), st>>>(p);
-    else k_bn_bwd_apply<false><<<dim3(gx2, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    const dim3 grid(gx2, G);
+    const size_t sm = 2 * p.C * sizeof(float);
+    if (p.dout) {
+        if (p.dz_f16) k_bn_bwd_apply<true, true><<<grid, blk, sm, st>>>(p);
+        else k_bn_bwd_apply<true, false><<<grid, blk, sm, st>>>(p);
+    } else {
+        if (p.dz_f16) k_bn_bwd_apply<false, true><<<grid, blk, sm, st>>>(p);
+        else k_bn_bwd_apply<false, false><<<grid, blk, sm, st>>>(p);
+    }
     VV_CKL();
     return 0;
 }
 
-int vv_maxpool_bwd(const float *Y, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
+int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
                    int lddy, int dy_coff, int G, int B, int H, int W, int C, cudaStream_t st) {
     long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
     int gx = vv_cdiv(total, 256);
     if (gx > 148 * 16) gx = 148 * 16;
-    k_maxpool_bwd<<<dim3(gx, G), 256, 0, st>>>(Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
+    if (y_f16) k_maxpool_bwd<true><<<dim3(gx, G), 256, 0, st>>>(Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
+    else k_maxpool_bwd<false><<<dim3(gx, G), 256, 0, st>>>(Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
     VV_CKL();
     return 0;
 }
 
-int vv_colsum(const float *D, long long d_gs, int ld, int coff, int M, int C, float *grads, const VvIntG &slot, long long slot_stride,
-              long long off, int G, cudaStream_t st) {
+int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M, int C, float scale, float *grads, const VvIntG &slot,
+              long long slot_stride, long long off, int G, cudaStream_t st) {
     int rows;
     dim3 blk = row_block(C, rows);
     int gx = vv_cdiv(M, rows * 16);
     if (gx > 148 * 2) gx = 148 * 2;
     if (gx < 1) gx = 1;
-    k_colsum<<<dim3(gx, G), blk, rows * C * sizeof(float), st>>>(D, d_gs, ld, coff, M, C, grads, slot, slot_stride, off);
+    if (d_f16) k_colsum<true><<<dim3(gx, G), blk, rows * C * sizeof(float), st>>>(D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
+    else k_colsum<false><<<dim3(gx, G), blk, rows * C * sizeof(float), st>>>(D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
     VV_CKL();
     return 0;
 }
@@ -953,10 +1015,12 @@ int vv_outconv_fwd(const VvOutFwd &p, int G, cudaStream_t st) {
     size_t smem = (256 * (p.F + 1) + 4 * p.F + 4) * sizeof(float);
     static bool attr_set = false;
     if (!attr_set && smem > 48 * 1024) {
-        VV_CK(cudaFuncSetAttribute(k_outconv_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VV_CK(cudaFuncSetAttribute(k_outconv_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        VV_CK(cudaFuncSetAttribute(k_outconv_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    k_outconv_fwd<<<dim3(p.B, G), 256, smem, st>>>(p);
+    if (p.u_f16) k_outconv_fwd<true><<<dim3(p.B, G), 256, smem, st>>>(p);
+    else k_outconv_fwd<false><<<dim3(p.B, G), 256, smem, st>>>(p);
     VV_CKL();
     return 0;
 }
@@ -967,7 +1031,8 @@ int vv_outconv_bwd(const VvOutBwd &p, int G, cudaStream_t st) {
     int gx = vv_cdiv(p.M, npix * 8);
     if (gx > 148 * 8) gx = 148 * 8;
     if (gx < 1) gx = 1;
-    k_outconv_bwd<<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
+    if (p.u_f16) k_outconv_bwd<true><<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
+    else k_outconv_bwd<false><<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
     VV_CKL();
     return 0;
 }
@@ -982,9 +1047,9 @@ int vv_scatter_conv_wgrad(const float *dWf, long long gs, int N, int C, int Cp, 
     return 0;
 }
 
-int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float *grads, const VvIntG &slot, long long slot_stride,
+int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float scale, float *grads, const VvIntG &slot, long long slot_stride,
                         long long w_off, int G, cudaStream_t st) {
-    k_scatter_ct_wgrad<<<dim3(vv_cdiv(9LL * Ci * Co, 256), G), 256, 0, st>>>(dWb, gs, Ci, Co, grads, slot, slot_stride, w_off);
+    k_scatter_ct_wgrad<<<dim3(vv_cdiv(9LL * Ci * Co, 256), G), 256, 0, st>>>(dWb, gs, Ci, Co, scale, grads, slot, slot_stride, w_off);
     VV_CKL();
     return 0;
 }
@@ -1029,14 +1094,25 @@ __global__ void k_f32_to_f16(const float *__restrict__ src, int ld, int cols, lo
         const long long r = i / cq;
         const int c4 = (int)(i - r * cq);
         const float4 v = *reinterpret_cast<const float4 *>(src + r * ld + c4 * 4);
-        __half2 lo = __floats2half2_rn(v.x, v.y), hi = __floats2half2_rn(v.z, v.w);
-        uint2 o;
-        o.x = *reinterpret_cast<unsigned *>(&lo);
-        o.y = *reinterpret_cast<unsigned *>(&hi);
-        *reinterpret_cast<uint2 *>(dst + r * cols + c4 * 4) = o;
+        *reinterpret_cast<uint2 *>(dst + r * cols + c4 * 4) = pack_h4(v);
     }
 }
 }  // namespace
+
+namespace {
+__global__ void k_f16_to_f32(const __half *__restrict__ src, long long n, float *__restrict__ dst) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
+}
+}  // namespace
+
+int vv_f16_to_f32(const void *src, long long n, float *dst, cudaStream_t st) {
+    int gx = vv_cdiv(n, 256);
+    if (gx > 148 * 16) gx = 148 * 16;
+    if (gx < 1) gx = 1;
+    k_f16_to_f32<<<gx, 256, 0, st>>>((const __half *)src, n, dst);
+    VV_CKL();
+    return 0;
+}
 
 int vv_f32_to_f16(const float *src, int ld, int cols, long long rows, void *dst, cudaStream_t st) {
     VV_REQUIRE(cols % 4 == 0 && ld % 4 == 0, "f32_to_f16: cols / ld must be multiples of 4");

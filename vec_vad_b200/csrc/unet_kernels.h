@@ -10,9 +10,9 @@ struct VvIntG {
 
 struct VvBnApply {
     const float *Z;      long long z_gs;                  // [G][M][C] raw conv output
-    float *Y;            long long y_gs;  int ldy, y_coff; // destination view (may live inside a concat buffer)
-    float *P;            long long p_gs;                  // pooled destination [G][M/4][C] (pool != 0)
-    int pool;
+    void *Y;             long long y_gs;  int ldy, y_coff; // destination view (may live inside a concat buffer); fp32, or fp16 when y_f16
+    void *P;             long long p_gs;                  // pooled destination [G][M/4][C] (pool != 0), same element type as Y
+    int pool, y_f16;
     int M, H, W, C;
     int training;
     const double *stats; long long stats_gs;              // [G][2][C] sums (training)
@@ -24,7 +24,10 @@ struct VvBnApply {
 struct VvBnBwd {
     const float *Z;      long long z_gs;
     const float *dY;     long long dy_gs; int ldy, dy_coff;
-    float *dZ;           long long dz_gs;                 // dense [G][M][C] (may alias dY when dY is dense)
+    void *dZ;            long long dz_gs;                 // dense [G][M][C]: fp32 (may alias dY when dY is dense) or fp16 (dz_f16; never aliases)
+    int dz_f16;
+    float store_scale;                                    // dZ is multiplied by this when stored (the fp16 path's loss scale, applied once, at the last unit)
+    float grad_unscale;                                   // d gamma / d beta are multiplied by this (1 / loss scale where dY already carries it)
     int M, C;
     const float *save;   long long save_gs;
     double *sums;        long long sums_gs;               // [G][2][C], pre-zeroed
@@ -35,7 +38,7 @@ struct VvBnBwd {
 };
 
 struct VvOutFwd {
-    const float *U;      long long u_gs;                  // [G][B*S*S][F]
+    const void *U;       long long u_gs;  int u_f16;      // [G][B*S*S][F], fp32 or fp16
     const float *params; VvIntG slot;  long long slot_param_stride, w_off, b_off;
     VvIntG out_channels, target_is_flow, target_index, out_slot;
     int B, S, F;
@@ -49,7 +52,7 @@ struct VvOutFwd {
 };
 
 struct VvOutBwd {
-    const float *U;      long long u_gs;
+    const void *U;       long long u_gs;  int u_f16;
     float *dU;           long long du_gs;
     const float *params; float *grads; VvIntG slot; long long slot_param_stride, w_off, b_off;
     VvIntG out_channels, target_is_flow, out_slot;
@@ -63,7 +66,8 @@ struct VvOutBwd {
 struct VvPrepUnit {
     long long w_off, b_off, g_off, beta_off;
     int N, C, Cp;
-    float *Wf, *Wd, *vec;          // Wd may be NULL
+    void *Wf, *Wd;                 // fp32 or fp16 (VvPrepAll::w_f16); Wd may be NULL
+    float *vec;
     const float *dWf;              // scatter direction
     long long wf_gs, wd_gs, vec_gs;
     int blk0;                      // first block of this unit
@@ -71,29 +75,33 @@ struct VvPrepUnit {
 struct VvPrepAll {
     VvPrepUnit u[VECVAD_N_UNITS];
     int n, total_blocks;
+    int w_f16;                     // re-laid-out weights are written as fp16
+    float scale;                   // scatter direction: gradients are multiplied by this (1 / loss scale)
 };
 int vv_prep_conv_w_all(const float *params, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st);
 int vv_scatter_conv_wgrad_all(float *grads, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st);
-int vv_prep_input(const float *x, float *X0, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st);
+int vv_prep_input(const float *x, void *X0, int x0_f16, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st);
 int vv_prep_conv_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, long long g_off,
-                   long long beta_off, int N, int C, int Cp, float *Wf, long long wf_gs, float *Wd, long long wd_gs, float *vec,
+                   long long beta_off, int N, int C, int Cp, void *Wf, long long wf_gs, void *Wd, long long wd_gs, int w_f16, float *vec,
                    long long vec_gs, int G, cudaStream_t st);
 int vv_prep_ct_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, int Ci, int Co,
-                 float *Wbf, long long wf_gs, float *Wbd, long long wd_gs, float *vec, long long vec_gs, int G, cudaStream_t st);
+                 void *Wbf, long long wf_gs, void *Wbd, long long wd_gs, int w_f16, float *vec, long long vec_gs, int G, cudaStream_t st);
 int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st);
 int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st);
-int vv_maxpool_bwd(const float *Y, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
+int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
                    int lddy, int dy_coff, int G, int B, int H, int W, int C, cudaStream_t st);
-int vv_colsum(const float *D, long long d_gs, int ld, int coff, int M, int C, float *grads, const VvIntG &slot, long long slot_stride,
-              long long off, int G, cudaStream_t st);
+int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M, int C, float scale, float *grads, const VvIntG &slot,
+              long long slot_stride, long long off, int G, cudaStream_t st);
 int vv_outconv_fwd(const VvOutFwd &p, int G, cudaStream_t st);
 int vv_outconv_bwd(const VvOutBwd &p, int G, cudaStream_t st);
 int vv_scatter_conv_wgrad(const float *dWf, long long gs, int N, int C, int Cp, float *grads, const VvIntG &slot, long long slot_stride,
                           long long w_off, int G, cudaStream_t st);
-int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float *grads, const VvIntG &slot, long long slot_stride,
+int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float scale, float *grads, const VvIntG &slot, long long slot_stride,
                         long long w_off, int G, cudaStream_t st);
 int vv_losses(const float *sse, int G, int B, const VvIntG &is_flow, float inv_raw, float inv_of, float *out, cudaStream_t st);
 
-// fp32 [rows][ld] (first `cols` of each row) -> dense fp16 [rows][cols], round to nearest (operand staging of the fp16 tile experiments)
+// fp32 [rows][ld] (first `cols` of each row) -> dense fp16 [rows][cols], round to nearest, saturating (operand staging of the single-op
+// entry points in fp16 mode), and back (debug reads)
 int vv_f32_to_f16(const float *src, int ld, int cols, long long rows, void *dst, cudaStream_t st);
+int vv_f16_to_f32(const void *src, long long n, float *dst, cudaStream_t st);
 

@@ -3,18 +3,18 @@
 //
 //   dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]                     (VvWGrad, common.h; t = (dy, dx) in {-1,0,1}^2)
 //
-// k_wgrad_tc2 (wgrad_tc2.cu) issues one MMA per (dx, 8 pixels): M = (dy, 32 input channels), N = output channels; at 32 output
+// k_wgrad_tc2 (wgrad_tc2.cu) issues one MMA per (dx, 8 pixels; 16 with fp16 operands): M = (dy, 32 input channels), N = output channels; at 32 output
 // channels that is 48 MMAs of N = 32 per 128 pixels and the kernel runs at the rate one warp can issue them (~67 cycles each,
 // measured; issuing from two warps is slower for these MN-major operands).  Both shifts can ride on descriptor offsets when
 // activations AND output gradients sit in shared memory as sequences with one zero pixel between image rows (the TMA boxes
 // are W + 1 wide, the out-of-range column arrives as zeros; igemm_flat.cu): with q = p + dx
 //      dW[(dy,dx)][n][k] = sum_q Gd[q - dx][n] * A[q + dy * P][k],          P = W + 1
-//   * M operand: four 32-channel blocks of the activation box, P pixel-rows apart (leading-dimension byte offset = P * 128):
-//     dy = -1, 0, +1 (+ a fourth block nobody reads);
-//   * N operand: three 32-channel blocks of the gradient box ONE pixel-row apart (leading-dimension byte offset = 128):
+//   * M operand: four 32-channel blocks of the activation box, P pixel-rows apart (leading-dimension byte offset = P * row
+//     bytes): dy = -1, 0, +1 (+ a fourth block nobody reads);
+//   * N operand: three 32-channel blocks of the gradient box ONE pixel-row apart (leading-dimension byte offset = one row):
 //     dx = +1, 0, -1;
-//   so per 8 positions ONE MMA (M = 128, N = 96, K = 8) instead of three of N = 32, and one activation box per tile instead of
-//   three.  Zero separators make the wrapped-around neighbours of edge pixels vanish; positions past the image have zero gradient.
+//   so per K-step ONE MMA (M = 128, N = 96) instead of three of N = 32, and one activation box per tile instead of three.
+//   Pixel rows are 128 bytes (tf32, K = 8 positions per MMA) or 64 bytes (template F16: fp16 operands, K = 16 positions).  Zero separators make the wrapped-around neighbours of edge pixels vanish; positions past the image have zero gradient.
 // A CTA owns one 32-input-channel slab, 32 output channels and a share of the 128-position tiles; one TMEM accumulator of 96
 // columns, flushed to dW with fp32 reductions at the end.
 // warp 0: TMA producer | warp 1: MMA issuer (+ TMEM alloc) | warps 0-2: epilogue (warp = dy).
@@ -44,16 +44,23 @@ constexpr int WGF_SMEM_MAX = 227 * 1024;
 constexpr int WGF_GUARD = 128;      // zeroed bytes in front of a gradient box: a tile starting at x = 0 reads one pixel-row before it
 constexpr int WGF_NT = 32;          // output channels per CTA: N of the MMA = 3 * 32
 
-__device__ __forceinline__ uint64_t desc_mn_flat(uint32_t saddr, uint32_t lbo) {      // MN-major, SWIZZLE_128B with 32-byte atoms
+// MN-major operand descriptor: tf32 = SWIZZLE_128B with 32-byte atoms (layout type 1), fp16 = SWIZZLE_64B (layout type 4);
+// 4-row (tf32) / 8-row (fp16) groups 512 bytes apart in both (see wgrad_tc2.cu)
+template <bool F16>
+__device__ __forceinline__ uint64_t desc_mn_flat(uint32_t saddr, uint32_t lbo) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)1 << 61);
+           ((uint64_t)(F16 ? 4 : 1) << 61);
 }
-__device__ __forceinline__ uint32_t idesc_tf32_mnmn_flat(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+template <bool F16>
+__device__ __forceinline__ uint32_t idesc_mnmn_flat(int n) {
+    return (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(128, 1) k_wgrad_flat(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
                                                        const WgfParams p) {
+    constexpr int ROWB = F16 ? KS * 2 : KS * 4;             // bytes of one pixel row of a 32-channel slab
+    constexpr int KPOS = F16 ? 16 : 8;                      // positions (K) per MMA: 1024 bytes of either operand
     extern __shared__ uint8_t smem_raw[];
     // stage s: [activation box | slack][gradient box | slack]; the slack behind a box (>= WGF_GUARD bytes) is zeroed once and never
     // written by TMA: the slack of the activation box is the leading guard of the gradient box behind it
@@ -114,7 +121,7 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_flat(const __grid_constant__ C
             if (p.trace && blockIdx.x + blockIdx.y + blockIdx.z == 0) { p.trace[0] = t_wait; p.trace[1] = clock64() - t_begin; }
         } else if (warp == 1) {
             // ---------------- MMA issuer (warp-uniform loop, one elected lane issues)
-            const uint32_t idesc = idesc_tf32_mnmn_flat(3 * WGF_NT);
+            const uint32_t idesc = idesc_mnmn_flat<F16>(3 * WGF_NT);
             const uint32_t base = smem_u32(smem);
             int s = 0, ph = 0;
             long long t_wait = 0;
@@ -127,12 +134,15 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_flat(const __grid_constant__ C
                 { const long long t0 = clock64(); mbar_wait(&full[s], ph); t_wait += clock64() - t0; }
                 tc_fence_after();
                 // activation box row 0 = image row r_lo - 1: block dy starts at row g0 + (dy + 1) * P, i.e. block 0 (dy = -1) at g0
-                const uint64_t da = desc_mn_flat(base + s * p.stage_bytes + g0 * (KS * 4), p.P * KS * 4);
+                const uint64_t da = desc_mn_flat<F16>(base + s * p.stage_bytes + g0 * ROWB, p.P * ROWB);
                 // gradient block j = Gd[q + j - 1]  <->  dx = 1 - j; the first one starts one pixel-row before the tile
-                const uint64_t dg = desc_mn_flat(base + s * p.stage_bytes + a_span + (g0 - 1) * (KS * 4), KS * 4);
+                const uint64_t dg = desc_mn_flat<F16>(base + s * p.stage_bytes + a_span + (g0 - 1) * ROWB, ROWB);
 #pragma unroll
-                for (int k = 0; k < BM / 8; k++)      // 8 positions = 1024 bytes per MMA in both operands
-                    if (elect_one()) tc_mma_tf32(tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                for (int k = 0; k < BM / KPOS; k++)   // KPOS positions = 1024 bytes per MMA in both operands
+                    if (elect_one()) {
+                        if (F16) tc_mma_f16(tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                        else tc_mma_tf32(tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                    }
                 if (elect_one()) tc_commit(&empty[s]);
                 __syncwarp();
                 if (++s == p.stages) { s = 0; ph ^= 1; }
@@ -212,12 +222,13 @@ int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st) {
     wp.N = p.N; wp.Kt = p.Kt; wp.dW = p.dW; wp.dw_gs = p.dw_gs;
     wp.g_rows = (BM - 1) / wp.P + 2;                 // rows holding 128 consecutive positions
     wp.a_rows = wp.g_rows + 2;                       // + one halo row either side
-    wp.a_bytes = wp.a_rows * wp.P * KS * 4;
-    wp.g_bytes = wp.g_rows * wp.P * KS * 4;
+    const int esz = p.ab_f16 ? 2 : 4;
+    wp.a_bytes = wp.a_rows * wp.P * KS * esz;
+    wp.g_bytes = wp.g_rows * wp.P * KS * esz;
     const int a_span = (wp.a_bytes + WGF_GUARD + 1023) / 1024 * 1024, g_span = (wp.g_bytes + WGF_GUARD + 1023) / 1024 * 1024;
     wp.stage_bytes = a_span + g_span;
     // the fourth M block (dy = +2, never read back) starts 3 * P rows into the tile: keep its reads inside our allocation
-    const int overread = (3 * wp.P + BM + wp.P) * KS * 4;
+    const int overread = (3 * wp.P + BM + wp.P) * KS * esz;
     const int fixed = 1024 + 256 + (overread > wp.stage_bytes ? overread - wp.stage_bytes : 0);
     int stages = (WGF_SMEM_MAX - fixed) / wp.stage_bytes;
     {
@@ -237,27 +248,29 @@ int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st) {
     }
     const int smem = fixed + stages * wp.stage_bytes;
 
-    const CUtensorMapDataType dt = tmap_dtype();
+    const CUtensorMapDataType dt = p.ab_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : tmap_dtype();
+    const CUtensorMapSwizzle sw = p.ab_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const unsigned long long e = esz;
     alignas(64) CUtensorMap tmA, tmG;
     {
         // (channel, x, y, image, group); the boxes are P = W + 1 wide from x = 0: column W is out of range = the zero separator
         cuuint64_t dims[5] = {(cuuint64_t)p.Kt, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B, (cuuint64_t)p.G};
-        cuuint64_t strides[4] = {(cuuint64_t)p.lda * 4, (cuuint64_t)p.W * p.lda * 4, (cuuint64_t)p.H * p.W * p.lda * 4,
-                                 (cuuint64_t)(p.G > 1 ? p.a_gs : (long long)p.B * p.H * p.W * p.lda) * 4};
+        cuuint64_t strides[4] = {(cuuint64_t)p.lda * e, (cuuint64_t)p.W * p.lda * e, (cuuint64_t)p.H * p.W * p.lda * e,
+                                 (cuuint64_t)(p.G > 1 ? p.a_gs : (long long)p.B * p.H * p.W * p.lda) * e};
         cuuint32_t box[5] = {KS, (cuuint32_t)wp.P, (cuuint32_t)wp.a_rows, 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult r = enc(&tmA, dt, 5, (void *)(p.A + p.a_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(&tmA, dt, 5, (void *)((const char *)p.A + (long long)p.a_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "wgrad_flat: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     {
         cuuint64_t dims[5] = {(cuuint64_t)p.N, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B, (cuuint64_t)p.G};
-        cuuint64_t strides[4] = {(cuuint64_t)p.ldg * 4, (cuuint64_t)p.W * p.ldg * 4, (cuuint64_t)p.H * p.W * p.ldg * 4,
-                                 (cuuint64_t)(p.G > 1 ? p.g_gs : (long long)p.B * p.H * p.W * p.ldg) * 4};
+        cuuint64_t strides[4] = {(cuuint64_t)p.ldg * e, (cuuint64_t)p.W * p.ldg * e, (cuuint64_t)p.H * p.W * p.ldg * e,
+                                 (cuuint64_t)(p.G > 1 ? p.g_gs : (long long)p.B * p.H * p.W * p.ldg) * e};
         cuuint32_t box[5] = {KS, (cuuint32_t)wp.P, (cuuint32_t)wp.g_rows, 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult r = enc(&tmG, dt, 5, (void *)(p.Gd + p.g_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(&tmG, dt, 5, (void *)((const char *)p.Gd + (long long)p.g_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "wgrad_flat: cuTensorMapEncodeTiled(Gd) failed with %d", (int)r);
     }
     const int out_tiles = wp.kchunks * wp.n_tiles * p.G;
@@ -269,10 +282,12 @@ int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st) {
     dim3 grid(wp.kchunks * wp.n_tiles, splits, p.G);
     static bool attr = false;
     if (!attr) {
-        VV_CK(cudaFuncSetAttribute(k_wgrad_flat, cudaFuncAttributeMaxDynamicSharedMemorySize, WGF_SMEM_MAX));
+        VV_CK(cudaFuncSetAttribute(k_wgrad_flat<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGF_SMEM_MAX));
+        VV_CK(cudaFuncSetAttribute(k_wgrad_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGF_SMEM_MAX));
         attr = true;
     }
-    k_wgrad_flat<<<grid, 128, smem, st>>>(tmA, tmG, wp);
+    if (p.ab_f16) k_wgrad_flat<true><<<grid, 128, smem, st>>>(tmA, tmG, wp);
+    else k_wgrad_flat<false><<<grid, 128, smem, st>>>(tmA, tmG, wp);
     VV_CKL();
     if (wp.trace) {      // debugging aid: synchronous
         unsigned long long h[5];

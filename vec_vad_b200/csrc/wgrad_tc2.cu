@@ -1,12 +1,12 @@
-// Weight gradient on tensor cores, tap-reuse variant:   dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]     (VvWGrad, common.h)
+// Weight gradient on tensor cores, tap-reuse tiles:   dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]     (VvWGrad, common.h)
 //
-// k_wgrad_tc (igemm_tc.cu) loaded one shifted activation slab per (tap, 32 input channels): 9 loads of every activation
-// byte for a 3x3 conv and one reload of the output gradient per group of four slabs -- it ran at the TMA / L2->smem
-// delivery rate, not at the tensor rate.  Here a CTA owns one 32-input-channel slab and ALL taps:
+// Loading one shifted activation slab per (tap, 32 input channels) means 9 loads of every activation byte for a 3x3 conv: such a
+// kernel runs at the TMA / L2->smem delivery rate, not at the tensor rate.  Here a CTA owns one 32-input-channel slab and ALL taps:
 //   * per 128-pixel tile it loads one activation box per distinct dx, (bh + ndy - 1) pixel rows tall, laid out
-//     [row][image][x] (32 channels = 128 bytes per pixel, MN-major, 128B swizzle with 32B atoms);
-//   * ONE tcgen05.mma (M = 128, K = 8 pixels) covers the ndy taps that share a dx: the four 32-row blocks of the M
-//     operand are the same box read at starts dy * (bn*bw*128) bytes apart -- the descriptor's leading-dimension byte
+//     [row][image][x] (32 channels per pixel row, MN-major: tf32 = 128-byte rows, 128B swizzle with 32B atoms, K = 8 pixels per
+//     MMA; fp16 (template F16) = 64-byte rows, 64B swizzle, K = 16 pixels per MMA -- half the MMAs and half the bytes);
+//   * ONE tcgen05.mma (M = 128) covers the ndy taps that share a dx: the four 32-row blocks of the M
+//     operand are the same box read at starts dy * (bn*bw*row bytes) apart -- the descriptor's leading-dimension byte
 //     offset IS the dy step (block 3, and block 2 for 2x2 taps, computes rows nobody reads);
 //   * the output-gradient tile (NT <= 128 channels) is loaded once per pixel tile and shared by all dx;
 //   * one TMEM accumulator per dx (ndx * NT <= 384 columns), reduced over the CTA's share of pixel tiles, then added to
@@ -31,19 +31,28 @@ struct Wg2Params {
 };
 
 constexpr int WG2_SMEM_MAX = 227 * 1024;
-constexpr int G_SLAB = BM * KS * 4;     // 16 KiB: 128 pixels x 32 channels
 
-__device__ __forceinline__ uint64_t desc_mn_sw128_32b(uint32_t saddr, uint32_t lbo) {
+// MN-major operand descriptor.  Canonical layouts (in 16-byte units, cute/atom/mma_traits_sm100.hpp):
+//   tf32: SWIZZLE_128B_BASE32B  ((8,n),(4,k)):((1,LBO),(8,SBO))   rows of 128 bytes, 4-row groups 512 bytes apart   (layout type 1)
+//   fp16: SWIZZLE_64B           ((4,n),(8,k)):((1,LBO),(4,SBO))   rows of  64 bytes, 8-row groups 512 bytes apart   (layout type 4)
+// LBO = byte distance between consecutive 32-channel blocks of the MN dimension, SBO = 512 in both.
+template <bool F16>
+__device__ __forceinline__ uint64_t desc_mn(uint32_t saddr, uint32_t lbo) {
     return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-           ((uint64_t)1 << 61);
+           ((uint64_t)(F16 ? 4 : 1) << 61);
 }
-__device__ __forceinline__ uint32_t idesc_tf32_mnmn(int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// instruction descriptor: D fp32, A/B tf32 or fp16, both MN-major, M = 128, N = n
+template <bool F16>
+__device__ __forceinline__ uint32_t idesc_mnmn(int n) {
+    return (1u << 4) | (F16 ? 0u : ((2u << 7) | (2u << 10))) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-template <int NT>
+template <int NT, bool F16>
 __global__ void __launch_bounds__(128, 1) k_wgrad_tc2(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmG,
                                                       const Wg2Params p) {
+    constexpr int ROWB = F16 ? KS * 2 : KS * 4;             // bytes of one pixel row of a 32-channel slab
+    constexpr int KPIX = F16 ? 16 : 8;                      // pixels (K) per MMA: 1024 bytes of either operand
+    constexpr int G_SLAB = BM * ROWB;                       // 128 pixels x 32 channels
     constexpr int NS = NT / 32;
     constexpr int G_STAGE = NS * G_SLAB;
     constexpr int TMEM_COLS = (3 * NT <= 128) ? 128 : (3 * NT <= 256 ? 256 : 512);
@@ -116,23 +125,26 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_tc2(const __grid_constant__ CU
             }
         } else if (warp == 1) {
             // ---------------- MMA issuer (warp-uniform loop, one elected lane issues)
-            const uint32_t idesc = idesc_tf32_mnmn(NT);
+            const uint32_t idesc = idesc_mnmn<F16>(NT);
             const uint32_t a_base = smem_u32(a_ring), g_base = smem_u32(g_ring);
             int ia = 0;
             for (int ti = 0; ti < ntiles; ti++) {
                 const int sg = ti % p.g_stages;
                 mbar_wait(&g_full[sg], (ti / p.g_stages) & 1);
-                const uint64_t dg = desc_mn_sw128_32b(g_base + sg * G_STAGE, G_SLAB);
+                const uint64_t dg = desc_mn<F16>(g_base + sg * G_STAGE, G_SLAB);
                 for (int dxi = 0; dxi < p.ndx; dxi++, ia++) {
                     const int s = ia % p.a_stages;
                     mbar_wait(&a_full[s], (ia / p.a_stages) & 1);
                     tc_fence_after();
                     // M operand: four 32-channel blocks = the same box, dy * row_shift bytes apart (LBO = one dy step)
-                    const uint64_t da = desc_mn_sw128_32b(a_base + s * p.a_bytes, p.row_shift);
+                    const uint64_t da = desc_mn<F16>(a_base + s * p.a_bytes, p.row_shift);
                     const uint32_t d_tmem = tmem + dxi * NT;
 #pragma unroll
-                    for (int k = 0; k < BM / 8; k++)      // 8 pixels = 1024 bytes per MMA in both operands
-                        if (elect_one()) tc_mma_tf32(d_tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                    for (int k = 0; k < BM / KPIX; k++)   // KPIX pixels = 1024 bytes per MMA in both operands
+                        if (elect_one()) {
+                            if (F16) tc_mma_f16(d_tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                            else tc_mma_tf32(d_tmem, da + 64 * k, dg + 64 * k, idesc, (ti | k) ? 1u : 0u);
+                        }
                     if (elect_one()) tc_commit(&a_empty[s]);
                     __syncwarp();
                 }
@@ -192,16 +204,14 @@ bool analyse_taps_wg(const VvTaps &t, Wg2Params &wp) {
     return true;
 }
 
-bool g_wg2_disabled = false;
-
-template <int NT>
+template <int NT, bool F16>
 int launch_wg2(const CUtensorMap &tmA, const CUtensorMap &tmG, const Wg2Params &wp, dim3 grid, int smem, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        VV_CK(cudaFuncSetAttribute(k_wgrad_tc2<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_MAX));
+        VV_CK(cudaFuncSetAttribute(k_wgrad_tc2<NT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_MAX));
         attr = true;
     }
-    k_wgrad_tc2<NT><<<grid, 128, smem, st>>>(tmA, tmG, wp);
+    k_wgrad_tc2<NT, F16><<<grid, 128, smem, st>>>(tmA, tmG, wp);
     VV_CKL();
     return 0;
 }
@@ -214,11 +224,11 @@ bool vv_wgrad_tc2_supported(const VvWGrad &p) {
         const char *e = getenv("VECVAD_NO_TC2");
         off = (e && e[0] == '1') ? 1 : 0;
     }
-    if (off || g_wg2_disabled || !vv_wgrad_tc_supported(p)) return false;
+    if (off || !vv_wgrad_tc_supported(p)) return false;
     Wg2Params wp;
     int bw, bh, bn;
     if (!tile_geometry_n(p.H, p.W, BM, bw, bh, bn)) return false;
-    if (bn * bw < 4) return false;                        // a dy step must be a multiple of the 512-byte swizzle pattern
+    if (bn * bw * KS * (p.ab_f16 ? 2 : 4) < 512) return false;   // a dy step must be a multiple of the 512-byte swizzle pattern
     return analyse_taps_wg(p.taps, wp);
 }
 
@@ -235,11 +245,12 @@ int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st) {
     wp.N = p.N; wp.Kt = p.Kt; wp.cq = p.g_s2d ? p.N / 4 : 0;
     wp.dW = p.dW; wp.dw_gs = p.dw_gs;
     const int rows = wp.bh + wp.ndy - 1;
-    wp.row_shift = wp.bn * wp.bw * KS * 4;
+    const int esz = p.ab_f16 ? 2 : 4;
+    wp.row_shift = wp.bn * wp.bw * KS * esz;
     wp.a_bytes = rows * wp.row_shift;
     const int nt_tile = p.N % 128 == 0 ? 128 : (p.N % 64 == 0 ? 64 : 32);
     wp.n_tiles = p.N / nt_tile;
-    const int g_stage = (nt_tile / 32) * G_SLAB;
+    const int g_stage = (nt_tile / 32) * BM * KS * esz;
     const int fixed = 1024 + 256 + 2 * wp.row_shift;
     wp.g_stages = 2;
     int a_stages = (WG2_SMEM_MAX - fixed - wp.g_stages * g_stage) / wp.a_bytes;
@@ -254,33 +265,32 @@ int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st) {
     wp.a_stages = a_stages;
     const int smem = fixed + wp.g_stages * g_stage + a_stages * wp.a_bytes;
 
-    const CUtensorMapDataType dt = tmap_dtype();
+    const CUtensorMapDataType dt = p.ab_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : tmap_dtype();
+    const CUtensorMapSwizzle sw = p.ab_f16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+    const unsigned long long e = esz;
     alignas(64) CUtensorMap tmA, tmG;
     {
         // dimensions (channel, x, image, y, group): boxes land in shared memory as [row][image][x][32 ch]; images past the
         // batch (ragged last tile) are out of bounds in their own dimension and arrive as zeros
         cuuint64_t dims[5] = {(cuuint64_t)p.Kt, (cuuint64_t)p.W, (cuuint64_t)p.B, (cuuint64_t)p.H, (cuuint64_t)p.G};
-        cuuint64_t strides[4] = {(cuuint64_t)p.lda * 4, (cuuint64_t)p.H * p.W * p.lda * 4, (cuuint64_t)p.W * p.lda * 4,
-                                 (cuuint64_t)(p.G > 1 ? p.a_gs : (long long)p.B * p.H * p.W * p.lda) * 4};
+        cuuint64_t strides[4] = {(cuuint64_t)p.lda * e, (cuuint64_t)p.H * p.W * p.lda * e, (cuuint64_t)p.W * p.lda * e,
+                                 (cuuint64_t)(p.G > 1 ? p.a_gs : (long long)p.B * p.H * p.W * p.lda) * e};
         cuuint32_t box[5] = {KS, (cuuint32_t)wp.bw, (cuuint32_t)wp.bn, (cuuint32_t)rows, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-        CUresult r = enc(&tmA, dt, 5, (void *)(p.A + p.a_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            g_wg2_disabled = true;
-            return vv_launch_wgrad_tc(p, st);
-        }
+        CUresult r = enc(&tmA, dt, 5, (void *)((const char *)p.A + (long long)p.a_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        VV_REQUIRE(r == CUDA_SUCCESS, "wgrad_tc2: cuTensorMapEncodeTiled(A) failed with %d", (int)r);
     }
     {
         const int sc = p.g_s2d ? 2 : 1;
         const cuuint64_t C = p.g_s2d ? p.N / 4 : p.N;
         cuuint64_t dims[5] = {C, (cuuint64_t)sc * p.W, (cuuint64_t)p.B, (cuuint64_t)sc * p.H, (cuuint64_t)p.G};
-        cuuint64_t strides[4] = {(cuuint64_t)p.ldg * 4, (cuuint64_t)sc * p.H * sc * p.W * p.ldg * 4, (cuuint64_t)sc * p.W * p.ldg * 4,
-                                 (cuuint64_t)(p.G > 1 ? p.g_gs : (long long)p.B * sc * p.H * sc * p.W * p.ldg) * 4};
+        cuuint64_t strides[4] = {(cuuint64_t)p.ldg * e, (cuuint64_t)sc * p.H * sc * p.W * p.ldg * e, (cuuint64_t)sc * p.W * p.ldg * e,
+                                 (cuuint64_t)(p.G > 1 ? p.g_gs : (long long)p.B * sc * p.H * sc * p.W * p.ldg) * e};
         cuuint32_t box[5] = {KS, (cuuint32_t)(sc * wp.bw), (cuuint32_t)wp.bn, (cuuint32_t)(sc * wp.bh), 1};
         cuuint32_t estr[5] = {1, (cuuint32_t)sc, 1, (cuuint32_t)sc, 1};
-        CUresult r = enc(&tmG, dt, 5, (void *)(p.Gd + p.g_coff), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r = enc(&tmG, dt, 5, (void *)((const char *)p.Gd + (long long)p.g_coff * esz), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         VV_REQUIRE(r == CUDA_SUCCESS, "wgrad_tc2: cuTensorMapEncodeTiled(Gd) failed with %d", (int)r);
     }
     const int out_tiles = wp.kchunks * wp.n_tiles * p.G;
@@ -290,7 +300,12 @@ int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st) {
     wp.tiles_per_split = (wp.m_tiles + splits - 1) / splits;
     splits = (wp.m_tiles + wp.tiles_per_split - 1) / wp.tiles_per_split;
     dim3 grid(wp.kchunks * wp.n_tiles, splits, p.G);
-    if (nt_tile == 128) return launch_wg2<128>(tmA, tmG, wp, grid, smem, st);
-    if (nt_tile == 64) return launch_wg2<64>(tmA, tmG, wp, grid, smem, st);
-    return launch_wg2<32>(tmA, tmG, wp, grid, smem, st);
+    if (p.ab_f16) {
+        if (nt_tile == 128) return launch_wg2<128, true>(tmA, tmG, wp, grid, smem, st);
+        if (nt_tile == 64) return launch_wg2<64, true>(tmA, tmG, wp, grid, smem, st);
+        return launch_wg2<32, true>(tmA, tmG, wp, grid, smem, st);
+    }
+    if (nt_tile == 128) return launch_wg2<128, false>(tmA, tmG, wp, grid, smem, st);
+    if (nt_tile == 64) return launch_wg2<64, false>(tmA, tmG, wp, grid, smem, st);
+    return launch_wg2<32, false>(tmA, tmG, wp, grid, smem, st);
 }

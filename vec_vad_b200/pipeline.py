@@ -414,14 +414,16 @@ def _stats(scores):
 
 @torch.no_grad()
 def score_frames(cfg, net_for, stats_for, foreground_set, foreground_set2, foreground_bbox_set, device, out_dir=None, scene_idx=None,
-                 max_cubes=4096):
+                 max_cubes=4096, score_batch=512):
     """test.py:270-358: per frame, per block: forward all cubes of the block, per-cube SSE, z-normalise with the training
     statistics, weight, paint the bbox rectangles with a running max.  Returns the list of per-frame score masks.
 
     The reference forwards one tiny batch per (frame, block) (about 17 cubes per frame on UCSDped2: launch-bound).  Eval-mode
     scores are per-cube and independent of what else is in the batch -- bit for bit, tests/test_unet_gpu.py::
     test_full_batch_properties -- so the cubes of consecutive frames that use the same model are scored in batches of up to
-    ``max_cubes`` and scattered back; the masks are identical to frame-by-frame scoring."""
+    ``max_cubes`` and scattered back; the masks are identical to frame-by-frame scoring.  Each flush runs through the engine in
+    fixed sub-batches of ``score_batch`` cubes, so the activation workspace is bounded (28.5 MB per cube for 5raw5of: 14.6 GB at
+    512) and never re-allocated for a slightly larger flush."""
     h, w = vd.frame_size[cfg.dataset_name][:2]
     n_frames = len(foreground_set)
     scores = [[[None for _ in foreground_set[f][hh]] for hh in range(len(foreground_set[f]))] for f in range(n_frames)]
@@ -435,12 +437,18 @@ def score_frames(cfg, net_for, stats_for, foreground_set, foreground_set2, foreg
         net = net_for(s_, hh, ww)
         raw_np = np.concatenate([foreground_set[f][a][b] for (f, a, b, _) in items], axis=0)
         flow_np = np.concatenate([foreground_set2[f][a][b] for (f, a, b, _) in items], axis=0)
-        x, x_of = vd.cubes_to_device_tensors(torch.as_tensor(raw_np).to(device), torch.as_tensor(flow_np).to(device, torch.float32))
-        raw, of = net.score(x, x_of)
+        raw_parts, of_parts = [], []
+        for o in range(0, raw_np.shape[0], score_batch):
+            x, x_of = vd.cubes_to_device_tensors(torch.as_tensor(raw_np[o:o + score_batch]).to(device),
+                                                 torch.as_tensor(flow_np[o:o + score_batch]).to(device, torch.float32))
+            r_, o_ = net.score(x, x_of)
+            raw_parts.append(r_.cpu().numpy())
+            if o_ is not None:
+                of_parts.append(o_.cpu().numpy())
         (rm, rs), (om, os_) = stats_for(s_, hh, ww)
-        sc = cfg.w_raw * ((raw.cpu().numpy() - rm) / rs)
+        sc = cfg.w_raw * ((np.concatenate(raw_parts) - rm) / rs)
         if cfg.useFlow:
-            sc = sc + cfg.w_of * ((of.cpu().numpy() - om) / os_)
+            sc = sc + cfg.w_of * ((np.concatenate(of_parts) - om) / os_)
         o = 0
         for (f, a, b, n) in items:
             scores[f][a][b] = sc[o:o + n]
@@ -501,6 +509,7 @@ def test(cfg_path='config.cfg', results_dir='results', use_tensor_cores=True):
         raw_tr = torch.load(cfg.path('raw_training_scores_{}.npy'.format(cfg.tag())), weights_only=False)
         of_tr = torch.load(cfg.path('of_training_scores_{}.npy'.format(cfg.tag())), weights_only=False)
         nets = {}
+        pool = vu.WorkspacePool()              # ONE activation workspace for all per-block models (they are scored one at a time)
 
         def pick(tree, s, hh, ww):
             return tree[s][hh][ww] if sh else tree[hh][ww]
@@ -514,7 +523,7 @@ def test(cfg_path='config.cfg', results_dir='results', use_tensor_cores=True):
                 else:
                     net = build_network(cfg, use_tensor_cores=use_tensor_cores)
                     load_block_state(net, sd[0])
-                    nets[key] = net.to(device).eval()
+                    nets[key] = net.to(device).eval().share_workspace(pool)
             return nets[key]
 
         def stats_for(s, hh, ww):

@@ -101,6 +101,22 @@ class _NetFn(torch.autograd.Function):
         return (None, None, None) + tuple(grads)
 
 
+class WorkspacePool:
+    """One device buffer shared by several CompletionNets that are never between a training forward and its backward at the
+    same time -- e.g. the per-block models ``test.py`` keeps (one model per (scene, h_block, w_block)): without it every cached
+    model would own a full activation workspace (28.5 MB per cube for 5raw5of)."""
+
+    def __init__(self):
+        self.buf, self.gen = None, 0
+
+    def get(self, nbytes, device):
+        if self.buf is None or self.buf.numel() < nbytes or self.buf.device != device:
+            self.buf = None                          # release before allocating the larger one
+            self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+            self.gen += 1
+        return self.buf
+
+
 class CompletionNet(nn.Module):
     """G independent completion UNets over one cube batch, computed by the sm_100a engine."""
 
@@ -131,7 +147,12 @@ class CompletionNet(nn.Module):
         assert self.raw_of_offset >= 0
         self.useFlow, self.padding = useFlow, padding
         self.features_root, self.patch_size = features_root, patch_size
-        self.use_tensor_cores = bool(use_tensor_cores)
+        # contraction path: False / 0 = fp32 SIMT tiles; True / 1 / 'tf32' = tcgen05 kind::tf32 tiles; 2 / 'f16' = tcgen05 kind::f16 tiles
+        # over fp16 activations / gradients / weights in HBM (fp32 accumulation, statistics, losses, optimiser)
+        self.use_tensor_cores = {'tf32': 1, 'f16': 2, 'fp16': 2, 'simt': 0, 'fp32': 0}.get(use_tensor_cores, use_tensor_cores)
+        self.use_tensor_cores = int(self.use_tensor_cores)
+        if self.use_tensor_cores not in (0, 1, 2):
+            raise ValueError('use_tensor_cores must be False, True / "tf32" or 2 / "f16"')
         if kind != '1raw1of' and tot_raw_num != 5:
             raise NotImplementedError('the reference builds exactly five raw UNets (model/unet.py:110-158)')
         cin = RAW_CH * (tot_raw_num if padding else tot_raw_num - 1)       # model/unet.py:100-103
@@ -174,6 +195,7 @@ class CompletionNet(nn.Module):
         # ---- engine state
         self._parts = None                    # [dict(net, ws, g0, g1, stream)]: the UNets split over concurrent streams
         self._ws_batch = 0
+        self._ws_pool, self._ws_pool_gen = None, -1     # optional WorkspacePool shared with other nets (scoring)
         self._gen = 0
         self._adam = None
         self._plan()
@@ -459,16 +481,31 @@ class CompletionNet(nn.Module):
                 _lib.check(L.vecvad_net_create(C.byref(cfg), C.byref(h)), 'net_create')
                 self._parts.append(dict(net=h, ws=None, g0=g0, g1=g1,
                                         stream=None if i == 0 else torch.cuda.Stream(device=self._pflat.device)))
-        if batch > self._ws_batch:
+        pool = self._ws_pool if len(self._parts) == 1 else None
+        if batch > self._ws_batch or (pool is not None and pool.gen != self._ws_pool_gen):
+            batch = max(batch, self._ws_batch)
             for part in self._parts:
                 nb = C.c_int64()
                 _lib.check(L.vecvad_net_workspace_bytes(part['net'], batch, C.byref(nb)), 'workspace_bytes')
-                part['ws'] = torch.empty(nb.value + 256, dtype=torch.uint8, device=self._pflat.device)
+                part['ws'] = None                       # drop the old workspace BEFORE allocating its replacement
+                part['ws'] = (pool.get(nb.value + 256, self._pflat.device) if pool is not None else
+                              torch.empty(nb.value + 256, dtype=torch.uint8, device=self._pflat.device))
                 base = (part['ws'].data_ptr() + 255) // 256 * 256
                 _lib.check(L.vecvad_net_bind(part['net'], _lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(self._sflat),
                                              C.c_void_p(base), nb.value, batch), 'net_bind')
             self._ws_batch = batch
+            if pool is not None:
+                self._ws_pool_gen = pool.gen
         return self._parts
+
+    def share_workspace(self, pool):
+        """Use ``pool`` (a WorkspacePool) instead of a private workspace.  Only for nets that are scored, or trained one at a
+        time: the pool's bytes are overwritten by whichever net runs next."""
+        self._ws_pool, self._ws_pool_gen = pool, -1
+        for part in (self._parts or []):
+            part['ws'] = None
+        self._ws_batch = 0
+        return self
 
     def _on_parts(self, fn):
         """Run fn(part, stream_handle) for every part: part 0 on the caller's stream, the others on their own stream, forked
