@@ -58,6 +58,7 @@ struct VvIGemm {
     // conv's output gradient) instead of O; 0 = no split
     int o_split;
     void *O2;           long long o2_gs; int ldo2;
+    int rev;                                                       // tcgen05 tiles: walk the pixel tiles from the last to the first (serpentine order for L2 reuse)
 };
 
 // dW[t][n][k] += sum_m Gd[m, n] * A[shift(m, t), k]

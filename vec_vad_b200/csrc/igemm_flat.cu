@@ -51,6 +51,8 @@ struct FlatParams {
     __half *O2;
     long long o2_gs;
     int ldo2;
+    int o_f16;                      // O itself is fp16 (raw conv outputs of the fp16 mode)
+    int rev;                        // walk the tiles from the last to the first
 };
 
 constexpr int FL_THREADS = 352;
@@ -131,7 +133,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
             long long t_wait = 0;
             const long long t_begin = clock64();
             int tcount = 0;
-            for (int tile = blockIdx.x; tile < p.m_tiles; tile += gridDim.x, tcount++) {
+            for (int lt = blockIdx.x; lt < p.m_tiles; lt += gridDim.x, tcount++) {
+                const int tile = p.rev ? p.m_tiles - 1 - lt : lt;
                 const int r = tcount & 1;
                 const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
                 const int r_lo = (int)__umulhi((unsigned)(tt * BM), p.mP);                      // first image row with a position in this tile
@@ -167,7 +170,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
         mbar_wait(bfull, 0);
         t_wb = clock64() - t_begin;
         int use = 0, s = 0, ph = 0;
-        for (int tile = blockIdx.x + mw * gridDim.x; tile < p.m_tiles; tile += 2 * gridDim.x, use++) {
+        for (int lt = blockIdx.x + mw * gridDim.x; lt < p.m_tiles; lt += 2 * gridDim.x, use++) {
+            const int tile = p.rev ? p.m_tiles - 1 - lt : lt;
             const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
             const int r_lo = (int)__umulhi((unsigned)(tt * BM), p.mP);
             const int q0 = tt * BM - r_lo * p.P + p.P;                 // box row of the tile's first position (box row 0 = image row r_lo-1, x=0)
@@ -231,7 +235,8 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
         for (int c = 0; c < BN / 32; c++) { c_sum[c] = 0.f; c_sq[c] = 0.f; }
         const long long t_begin = clock64();
         int use = 0;
-        for (int tile = blockIdx.x + es * gridDim.x; tile < p.m_tiles; tile += 2 * gridDim.x, use++) {
+        for (int lt = blockIdx.x + es * gridDim.x; lt < p.m_tiles; lt += 2 * gridDim.x, use++) {
+            const int tile = p.rev ? p.m_tiles - 1 - lt : lt;
             const int buf = es;
             const int img = (p.tpi == 1 ? tile : (int)__umulhi((unsigned)tile, p.mtpi)), tt = tile - img * p.tpi;
             const int pos = tt * BM + row;
@@ -281,14 +286,17 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
                     c_sq[c0 / 32] += sq;
                 }
                 { const long long t2 = clock64(); t_stat += t2 - t1; t1 = t2; }
-                if (p.o_split && n0 + c0 >= p.o_split) {       // this 32-column block belongs to the fp16 side output
-                    __half *O2 = p.O2 + g * p.o2_gs + (n0 + c0 - p.o_split) + 4 * (lane & 7);
+                if (p.o_f16 || (p.o_split && n0 + c0 >= p.o_split)) {       // fp16 destination: O itself, or the side output of this block
+                    const bool side = p.o_split && n0 + c0 >= p.o_split;
+                    __half *Oh = side ? p.O2 + g * p.o2_gs + (n0 + c0 - p.o_split) + 4 * (lane & 7)
+                                      : reinterpret_cast<__half *>(p.O) + g * p.o_gs + p.o_coff + n0 + c0 + 4 * (lane & 7);
+                    const int ldh = side ? p.ldo2 : p.ldo;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int r = 4 * i + (lane >> 3);
                         const float4 o = *reinterpret_cast<const float4 *>(stg + r * FL_STG_LD + 4 * (lane & 7));
                         const int rp = __shfl_sync(0xffffffffu, pix, r);
-                        if ((vmask >> r) & 1) *reinterpret_cast<uint2 *>(O2 + (long long)rp * p.ldo2) = pack_half4(o);
+                        if ((vmask >> r) & 1) *reinterpret_cast<uint2 *>(Oh + (long long)rp * ldh) = pack_half4(o);
                     }
                 } else {                                  // store instruction i: rows 4i .. 4i+3, eight lanes per 128-byte pixel row
 #pragma unroll
@@ -379,7 +387,8 @@ int launch_flat(const CUtensorMap &tmA, const CUtensorMap &tmB, const FlatParams
 // shapes the flattened-sequence tiles take: 3x3 taps, plain NHWC in/out, all nine weight tiles resident (<= 72 KB)
 bool vv_igemm_flat_shape_ok(const VvIGemm &p) {
     FlatParams fp;
-    if (!vv_igemm_tc_supported(p) || p.a_s2d || p.o_d2s || p.o_f16 || !analyse_3x3(p.taps, fp)) return false;
+    if (!vv_igemm_tc_supported(p) || p.a_s2d || p.o_d2s || !analyse_3x3(p.taps, fp)) return false;
+    if (p.o_f16 && (p.ldo % 8 || p.o_coff % 8)) return false;
     if (p.W + 1 > 256 || p.W < 8) return false;
     if (p.ab_f16 && (p.lda % 8 || p.a_coff % 8)) return false;           // 16-byte aligned pixel rows
     const int b_all = 9 * (p.Kt / KS) * flat_bn_tile(p.N) * KS * (p.ab_f16 ? 2 : 4);
@@ -405,7 +414,7 @@ int vv_launch_igemm_flat(const VvIGemm &p, cudaStream_t st) {
     fp.stage_bytes = (fp.a_bytes + KS * esz + 1023) / 1024 * 1024;    // >= one zero pixel-row of slack: the next stage's leading guard
     fp.N = p.N; fp.O = p.O; fp.o_gs = p.o_gs; fp.ldo = p.ldo; fp.o_coff = p.o_coff;
     fp.bias = p.bias; fp.bias_gs = p.bias_gs; fp.stats = p.stats; fp.stats_gs = p.stats_gs;
-    fp.o_split = p.o_split; fp.O2 = (__half *)p.O2; fp.o2_gs = p.o2_gs; fp.ldo2 = p.ldo2;
+    fp.o_split = p.o_split; fp.O2 = (__half *)p.O2; fp.o2_gs = p.o2_gs; fp.ldo2 = p.ldo2; fp.o_f16 = p.o_f16; fp.rev = p.rev;
     const int bn_tile = flat_bn_tile(p.N);
     const int b_all = 9 * fp.kchunks * bn_tile * KS * esz;
     const int fixed = 1024 /*alignment*/ + FL_GUARD + 8 * FL_STG_BYTES + 256 /*barriers*/ + 3 * bn_tile * 4;

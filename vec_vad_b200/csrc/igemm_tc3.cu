@@ -48,6 +48,7 @@ struct Tc3Params {
     __half *O2;
     long long o2_gs;
     int ldo2;
+    int rev;                        // walk the pairs from the last to the first
 };
 
 constexpr int T3_THREADS = 352;
@@ -121,7 +122,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
             int s = 0, round = 0;
             long long t_wait = 0;
             const long long t_begin = clock64();
-            for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x) {
+            for (int lp = blockIdx.x; lp < p.pairs; lp += gridDim.x) {
+                const int pair = p.rev ? p.pairs - 1 - lp : lp;
                 int img0[2], y0[2], x0[2];
 #pragma unroll
                 for (int w = 0; w < 2; w++) {
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
         const long long t_begin = clock64();
         if (p.stationary) mbar_wait(bfull, 0);
         int s = 0, ph = 0, pcount = 0;
-        for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x, pcount++) {
+        for (int lp = blockIdx.x; lp < p.pairs; lp += gridDim.x, pcount++) {
             const int buf = (NBUF == 2) ? (pcount & 1) : 0, use = (NBUF == 2) ? (pcount >> 1) : pcount;
             if (use > 0) {
                 const long long t0 = clock64();
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
         long long t_wfull = 0;
         const long long t_begin = clock64();
         int pcount = 0;
-        for (int pair = blockIdx.x; pair < p.pairs; pair += gridDim.x, pcount++) {
+        for (int lp = blockIdx.x; lp < p.pairs; lp += gridDim.x, pcount++) {
+            const int pair = p.rev ? p.pairs - 1 - lp : lp;
             const int buf = (NBUF == 2) ? (pcount & 1) : 0, use = (NBUF == 2) ? (pcount >> 1) : pcount;
             int r = 2 * pair + es;
             const int tx = r % p.tiles_x; r /= p.tiles_x;
@@ -292,9 +295,10 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
                     pixc = pix + (phs >> 1) * (2 * p.W) + (phs & 1);
                 }
                 if (p.o_f16 || (p.o_split && ncol >= p.o_split)) {      // fp16 destination: 8 bytes per lane, 64-byte pixel rows
-                    __half *Oh = p.o_f16 ? reinterpret_cast<__half *>(p.O) + g * p.o_gs + p.o_coff + col + 4 * (lane & 7)
-                                         : p.O2 + g * p.o2_gs + (ncol - p.o_split) + 4 * (lane & 7);
-                    const int ldh = p.o_f16 ? p.ldo : p.ldo2;
+                    const bool side = p.o_split && ncol >= p.o_split;
+                    __half *Oh = side ? p.O2 + g * p.o2_gs + (ncol - p.o_split) + 4 * (lane & 7)
+                                      : reinterpret_cast<__half *>(p.O) + g * p.o_gs + p.o_coff + col + 4 * (lane & 7);
+                    const int ldh = side ? p.ldo2 : p.ldo;
 #pragma unroll
                     for (int i = 0; i < 8; i++) {
                         const int rr = 4 * i + (lane >> 3);
@@ -443,7 +447,7 @@ int vv_launch_igemm_tc3(const VvIGemm &p, cudaStream_t st) {
     VV_REQUIRE(enc && plan3(p, tp, smem), "igemm_tc3: unsupported shape (Kt=%d N=%d H=%d W=%d taps=%d)", p.Kt, p.N, p.H, p.W, p.taps.n);
     tp.N = p.N; tp.O = p.O; tp.o_gs = p.o_gs; tp.ldo = p.ldo; tp.o_coff = p.o_coff; tp.o_d2s = p.o_d2s;
     tp.bias = p.bias; tp.bias_gs = p.bias_gs; tp.stats = p.stats; tp.stats_gs = p.stats_gs;
-    tp.o_f16 = p.o_f16; tp.o_split = p.o_split; tp.O2 = (__half *)p.O2; tp.o2_gs = p.o2_gs; tp.ldo2 = p.ldo2;
+    tp.o_f16 = p.o_f16; tp.o_split = p.o_split; tp.O2 = (__half *)p.O2; tp.o2_gs = p.o2_gs; tp.ldo2 = p.ldo2; tp.rev = p.rev;
     {
         static int tr = -1;
         static unsigned long long *buf = nullptr;

@@ -41,6 +41,7 @@ constexpr int NT = VECVAD_N_UPS;
 struct vecvad_net {
     vecvad_net_config cfg;
     int G, F, S, T, cin_real, cinp;
+    int serp;                                // serpentine row / tile order through consecutive kernels (VECVAD_SERPENTINE, default on)
     int f16;                                 // use_tensor_cores == 2: activations, dZ and re-laid-out weights are fp16 (operands of kind::f16 tiles)
     float lscale, lscale_user;               // power-of-two loss scale of the fp16 gradient operands (1 in the other modes); user override (<= 0: automatic)
     VvIntG slot, erase, outc, isflow, tidx, oslot;
@@ -54,8 +55,9 @@ struct vecvad_net {
     int64_t ws_bytes;
     int maxB;
     // workspace sub-buffers (float offsets resolved to pointers at bind time)
-    void *X0, *A[NU], *CAT[3], *PL[3], *X4, *UU[3];           // activations: fp32, or fp16 in the fp16-operand mode
-    float *Z[NU], *dCAT[3], *GA, *GB, *DOUT;                  // raw conv outputs and output gradients (dY): always fp32
+    void *X0, *A[NU], *CAT[3], *PL[3], *X4, *UU[3], *Z[NU];   // activations and raw conv outputs: fp32, or fp16 in the fp16-operand mode
+    void *dCAT[3], *GA, *GB;                                  // output gradients (dY): fp32, or (loss-scaled) fp16 in the fp16-operand mode
+    float *DOUT;                                              // staged d loss / d out [m][4]: fp32
     void *dUP[3], *HZ[4];                                     // fp16 mode only: transposed-conv output gradients, ring of dZ operand buffers
     void *Wf[NU], *Wd[NU], *tWf[NT], *tWd[NT];                // re-laid-out weights: fp32 or fp16
     float *vec[NU], *save[NU], *tvec[NT];
@@ -89,21 +91,21 @@ long long layout(vecvad_net *n, int B, char *base) {
     auto fl = [&](long long count) { return (float *)take(count * (long long)sizeof(float)); };
     auto act = [&](long long count) { return (void *)take(count * es); };
     n->X0 = act(G * M(S) * n->cinp);
-    for (int u = 0; u < NU; u++) n->Z[u] = fl(G * M(n->uH[u]) * n->uN[u]);
+    for (int u = 0; u < NU; u++) n->Z[u] = act(G * M(n->uH[u]) * n->uN[u]);
     for (int u = 0; u < NU; u += 2) n->A[u] = act(G * M(n->uH[u]) * n->uN[u]);
     // CAT[k]: concat input of up-block k+1:  k=0 @S/4 (8F), k=1 @S/2 (4F), k=2 @S (2F)
     for (int k = 0; k < 3; k++) {
         int H = S >> (2 - k), C = F << (3 - k);
         n->CAT[k] = act(G * M(H) * C);
-        n->dCAT[k] = fl(G * M(H) * C);
+        n->dCAT[k] = act(G * M(H) * C);
         n->dUP[k] = n->f16 ? take(G * M(H) * (C / 2) * 2) : nullptr;
     }
     // PL[k]: pooled input of down-block k+1: k=0 @S/2 (F), k=1 @S/4 (2F), k=2 @S/8 (4F)
     for (int k = 0; k < 3; k++) n->PL[k] = act(G * M(S >> (k + 1)) * (F << k));
     n->X4 = act(G * M(S >> 3) * 8 * F);
     for (int k = 0; k < 3; k++) n->UU[k] = act(G * M(S >> (2 - k)) * (F << (2 - k)));   // U1 @S/4 4F, U2 @S/2 2F, U3 @S F
-    n->GA = fl(G * M(S) * F);
-    n->GB = fl(G * M(S) * F);
+    n->GA = act(G * M(S) * F);
+    n->GB = act(G * M(S) * F);
     for (int i = 0; i < 4; i++) n->HZ[i] = n->f16 ? take(G * M(S) * F * 2) : nullptr;
     n->DOUT = fl(G * M(S) * 4);
     for (int u = 0; u < NU; u++) {
@@ -237,6 +239,10 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
     n->cinp = (n->cin_real + 15) / 16 * 16;
     if (cfg->use_tensor_cores) n->cinp = (n->cin_real + 31) / 32 * 32;   // tcgen05 tiles use 32-channel K slabs (128 bytes of tf32, 64 of fp16)
     n->f16 = cfg->use_tensor_cores == 2;
+    {
+        const char *e = getenv("VECVAD_SERPENTINE");
+        n->serp = !(e && e[0] == '0');
+    }
     n->lscale = 1.f; n->lscale_user = 0.f;
     int max_raw = -1, max_of = -1;
     for (int g = 0; g < n->G; g++) {
@@ -383,7 +389,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         p.A = (const float *)in.p; p.a_gs = in.gs; p.lda = in.ld; p.a_coff = in.coff; p.a_s2d = 0; p.Kt = n->uCp[u];
         p.B = B; p.H = H; p.W = H; p.ab_f16 = n->f16;
         p.Wt = (const float *)n->Wf[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3; p.N = N;
-        p.O = n->Z[u]; p.o_gs = (long long)B * H * H * N; p.ldo = N; p.o_coff = 0; p.o_d2s = 0;
+        p.O = (float *)n->Z[u]; p.o_gs = (long long)B * H * H * N; p.ldo = N; p.o_coff = 0; p.o_d2s = 0; p.o_f16 = n->f16;
         p.bias = n->vec[u]; p.bias_gs = 3LL * N;
         p.stats = training ? n->stats[u] : nullptr; p.stats_gs = 2LL * N;
         p.G = G;
@@ -397,6 +403,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         q.pool = f.pool[u] >= 0;
         if (q.pool) { q.P = n->PL[f.pool[u]]; q.p_gs = (long long)B * (H / 2) * (H / 2) * N; }
         q.M = B * H * H; q.H = H; q.W = H; q.C = N; q.training = training;
+        q.rev = n->serp;                                    // conv tiles walked the rows upwards: come back down (L2 reuse)
         q.stats = n->stats[u]; q.stats_gs = 2LL * N;
         q.vec = n->vec[u]; q.vec_gs = 3LL * N;
         q.running = n->running; q.slot = n->slot; q.slot_stat_stride = c.slot_stat_stride; q.rm_off = c.run_mean[u]; q.rv_off = c.run_var[u];
@@ -491,7 +498,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         VvOutBwd q;
         memset(&q, 0, sizeof(q));
         q.U = n->UU[2]; q.u_gs = (long long)B * S * S * F; q.u_f16 = f16;
-        q.dU = n->GA; q.du_gs = q.u_gs;
+        q.dU = n->GA; q.du_gs = q.u_gs; q.du_scale = LS;       // fp16 mode: dU enters the chain already loss-scaled
         q.params = n->params; q.grads = n->grads; q.slot = n->slot; q.slot_param_stride = c.slot_param_stride; q.w_off = c.out_w; q.b_off = c.out_b;
         q.out_channels = n->outc; q.target_is_flow = n->isflow; q.out_slot = n->oslot;
         q.M = B * S * S; q.S = S; q.F = F;
@@ -547,16 +554,21 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     // dz_inplace: where dZ goes in the fp32 modes (it may overwrite dY); the fp16 mode takes the next buffer of its dZ ring.
     // up_k >= 0: unit u is the first conv of up-block up_k, whose input gradient splits into the skip half (din, fp32) and the
     // transposed conv's output gradient (fp16 mode: stored as fp16 in dUP[up_k], the operand of the two transposed-conv backward tiles).
-    auto unit_bwd = [&](int u, const View &dyv, float *dz_inplace, const View *din, int up_k) -> int {
+    auto unit_bwd = [&](int u, const View &dyv, void *dz_inplace, const View *din, int up_k) -> int {
         const int H = n->uH[u], N = n->uN[u], M = B * H * H;
-        void *dz_buf = f16 ? n->HZ[(hz_next++) & 3] : (void *)dz_inplace;
+        void *dz_buf = f16 ? n->HZ[(hz_next++) & 3] : dz_inplace;
         VvBnBwd q;
         memset(&q, 0, sizeof(q));
-        q.Z = n->Z[u]; q.z_gs = (long long)M * N;
-        q.dY = (const float *)dyv.p; q.dy_gs = dyv.gs; q.ldy = dyv.ld; q.dy_coff = dyv.coff;
+        q.Z = n->Z[u]; q.z_gs = (long long)M * N; q.z_f16 = f16;
+        q.dY = dyv.p; q.dy_gs = dyv.gs; q.ldy = dyv.ld; q.dy_coff = dyv.coff;
         q.dZ = dz_buf; q.dz_gs = (long long)M * N; q.dz_f16 = f16;
-        q.store_scale = (u == NU - 1) ? LS : 1.f;              // the loss scale enters where the last unit's dZ is stored ...
-        q.grad_unscale = (u == NU - 1) ? 1.f : inv_LS;         // ... so every earlier dY carries it: removed from d gamma / d beta
+        // serpentine row order: every kernel of the backward chain walks against its predecessor, so what was written / read last
+        // (still in L2) is read first: dgrad of unit u+1 -> reduce(u) -> apply(u) -> dgrad(u) alternate, hence the parity of u
+        const int up = n->serp ? (u & 1) : 0;
+        q.rev_reduce = n->serp ? !up : 0; q.rev_apply = up;
+        const bool unscaled_dy = fuse_out && u == NU - 1;      // the fused last unit forms dY from the (unscaled) staged loss gradient:
+        q.store_scale = unscaled_dy ? LS : 1.f;                // the loss scale enters where its dZ is stored ...
+        q.grad_unscale = unscaled_dy ? 1.f : inv_LS;           // ... every other dY carries it already: removed from d gamma / d beta
         q.M = M; q.C = N;
         q.save = n->save[u]; q.save_gs = 4LL * N;
         q.sums = n->bsums[u]; q.sums_gs = 2LL * N;
@@ -593,11 +605,12 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             p.A = (const float *)dz_buf; p.a_gs = (long long)M * N; p.lda = N; p.a_coff = 0; p.a_s2d = 0; p.Kt = N; p.ab_f16 = f16;
             p.B = B; p.H = H; p.W = H;
             p.Wt = (const float *)n->Wd[u]; p.w_gs = 9LL * N * n->uCp[u]; p.taps = t3b; p.N = n->uC[u];
-            p.O = (float *)din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0;
+            p.O = (float *)din->p; p.o_gs = din->gs; p.ldo = din->ld; p.o_coff = din->coff; p.o_d2s = 0; p.o_f16 = f16;
             if (f16 && up_k >= 0) {
                 p.o_split = n->uC[u] / 2; p.O2 = n->dUP[up_k]; p.ldo2 = n->uC[u] / 2; p.o2_gs = (long long)M * (n->uC[u] / 2);
             }
             p.bias = nullptr; p.stats = nullptr; p.G = G;
+            p.rev = n->serp ? !up : 0;                        // apply(u) walked up (up = 1) or down: the input-gradient tiles go the other way
             if ((rr = before_write(din->p))) return rr;
             if ((rr = run_igemm(c.use_tensor_cores != 0, p, st))) return rr;
         }
@@ -627,14 +640,14 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         p.A = (const float *)dhalf.p; p.a_gs = dhalf.gs; p.lda = dhalf.ld; p.a_coff = dhalf.coff; p.a_s2d = 1; p.Kt = 4 * Co; p.ab_f16 = f16;
         p.B = B; p.H = Hi; p.W = Hi;
         p.Wt = (const float *)n->tWd[k]; p.w_gs = 16LL * Co * Ci; p.taps = t2b; p.N = Ci;
-        p.O = (float *)ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0;
+        p.O = (float *)ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0; p.o_f16 = f16;
         p.bias = nullptr; p.stats = nullptr; p.G = G;
         if ((rr = before_write(ddeep.p))) return rr;
         return run_igemm(c.use_tensor_cores != 0, p, st);
     };
 
     // ---- decoder, deepest last.  GA holds dU3 now (external gradients), or nothing (fused: formed from DOUT on the fly).
-    float *ga = n->GA, *gb = n->GB;
+    void *ga = n->GA, *gb = n->GB;
     for (int k = 2; k >= 0; k--) {
         const int H = S >> (2 - k), C = F << (3 - k);          // concat geometry of up-block k
         const int u2 = 9 + 2 * k, u1 = 8 + 2 * k;
@@ -655,9 +668,9 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         else dy2 = mk(n->dCAT[2 - k], B, H, 2 * N, 0, N);       // first half of the concat gradient (+ pooled path, added below)
         // fp32 modes: dZ of the second conv replaces its dY in place (ga), or goes to gb when dY sits in dCAT; d(mid) takes the other
         // scratch buffer and d(pooled input) the first again.  fp16 mode: dZ lives in the ring, so d(mid) -> gb, d(pooled input) -> ga.
-        float *dz2 = (k == 3) ? ga : gb;
-        float *other = f16 ? gb : ((dz2 == ga) ? gb : ga);
-        float *pool_buf = f16 ? ga : dz2;
+        void *dz2 = (k == 3) ? ga : gb;
+        void *other = f16 ? gb : ((dz2 == ga) ? gb : ga);
+        void *pool_buf = f16 ? ga : dz2;
         View dmid = mk(other, B, H, N, 0, N);
         if ((r = unit_bwd(u2, dy2, dz2, &dmid, -1))) return r;
         if (k == 0) {
@@ -669,7 +682,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             const int Hs = 2 * H, Cs = n->uC[u1];                 // skip tensor geometry (x_k) : [B,Hs,Hs,Cs] inside CAT[3-k]
             View ysk = mk(n->CAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
             View dsk = mk(n->dCAT[3 - k], B, Hs, 2 * Cs, 0, Cs);
-            if ((r = vv_maxpool_bwd(ysk.p, f16, ysk.gs, ysk.ld, ysk.coff, (const float *)dpool.p, dpool.gs, (float *)dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B,
+            if ((r = vv_maxpool_bwd(ysk.p, f16, ysk.gs, ysk.ld, ysk.coff, dpool.p, dpool.gs, dsk.p, dsk.gs, dsk.ld, dsk.coff, G, B,
                                     Hs, Hs, Cs, st)))
                 return r;
         }
@@ -711,15 +724,15 @@ extern "C" int vecvad_net_debug_read(vecvad_net *n, int kind, int index, float *
     const int u = index, k = index;
     switch (kind) {
         case 0: src = n->X0; cnt = G * M(S) * n->cinp; half = true; break;
-        case 1: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Z[u]; cnt = G * M(n->uH[u]) * n->uN[u]; break;
+        case 1: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Z[u]; cnt = G * M(n->uH[u]) * n->uN[u]; half = true; break;
         case 2: VV_REQUIRE(u >= 0 && u < NU && u % 2 == 0, "debug_read: unit"); src = n->A[u]; cnt = G * M(n->uH[u]) * n->uN[u]; half = true; break;
         case 3: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->CAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); half = true; break;
         case 4: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->PL[k]; cnt = G * M(S >> (k + 1)) * (F << k); half = true; break;
         case 5: src = n->X4; cnt = G * M(S >> 3) * 8 * F; half = true; break;
         case 6: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->UU[k]; cnt = G * M(S >> (2 - k)) * (F << (2 - k)); half = true; break;
-        case 7: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->dCAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); break;
-        case 8: src = n->GA; cnt = G * M(S) * F; break;
-        case 9: src = n->GB; cnt = G * M(S) * F; break;
+        case 7: VV_REQUIRE(k >= 0 && k < 3, "debug_read: k"); src = n->dCAT[k]; cnt = G * M(S >> (2 - k)) * (F << (3 - k)); half = true; break;
+        case 8: src = n->GA; cnt = G * M(S) * F; half = true; break;
+        case 9: src = n->GB; cnt = G * M(S) * F; half = true; break;
         case 10: src = n->DOUT; cnt = G * M(S) * 4; break;
         case 11: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->Wf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; half = true; break;
         case 12: VV_REQUIRE(u >= 0 && u < NU, "debug_read: unit"); src = n->dWf[u]; cnt = G * 9 * n->uN[u] * n->uCp[u]; break;

@@ -256,10 +256,28 @@ __device__ __forceinline__ void bn_scale_shift(const VvBnApply &p, int g, int c,
     }
 }
 
-// thread = (output pixel or pooled pixel, 4 channels).  blockDim = (C/4 <= 128 .. , rows).  H: Y / P are fp16 (the operands of the
-// next contraction; rounded once, here, exactly as the tf32 path rounds them on their way into shared memory)
+// ---- element-typed row access for the bandwidth-bound passes: a thread owns CH = 4 consecutive channels of a pixel row (16 bytes of
+//      fp32, 8 bytes of fp16) and keeps UNR rows in flight.  Measured (profiles/r02_bn_ncu.txt): 8 channels per thread (16-byte fp16
+//      accesses) costs registers (116 / thread, 25 % occupancy) and ran slower; these passes need threads in flight, not wider loads.
+template <bool H> struct RowVec { static constexpr int CH = 4; float v[CH]; };
 template <bool H>
-__global__ void k_bn_apply(const VvBnApply p) {
+__device__ __forceinline__ RowVec<H> ldv(const void *base, long long idx) {
+    RowVec<H> r;
+    const float4 q = ld4<H>(base, idx);
+    r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    return r;
+}
+template <bool H>
+__device__ __forceinline__ void stv(void *base, long long idx, const RowVec<H> &r) {
+    st4<H>(base, idx, make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
+}
+
+// thread = (output pixel or pooled pixel, CH channels).  blockDim = (C/CH <= 64, rows).  H: Z, Y and P are fp16 (Y / P are the
+// operands of the next contraction; rounded once, here, exactly as the tf32 path rounds them on their way into shared memory)
+template <bool H>
+__global__ void __launch_bounds__(256, 4) k_bn_apply(const VvBnApply p) {
+    constexpr int CH = RowVec<H>::CH;
+    constexpr int UNR = 4;                 // rows in flight per thread: these passes are bound by bytes in flight
     extern __shared__ float sm[];          // scale[C], shift[C]
     const int g = blockIdx.y;
     float *s_scale = sm, *s_shift = sm + p.C;
@@ -271,157 +289,157 @@ __global__ void k_bn_apply(const VvBnApply p) {
         s_scale[c] = sc; s_shift[c] = sh;
     }
     __syncthreads();
-    const float *Z = p.Z + g * p.z_gs;
+    const long long z0 = g * p.z_gs;
     const long long y0 = g * p.y_gs + p.y_coff;
-    const int cq = p.C >> 2;
-    auto act = [](const float4 &z, const float4 &sc, const float4 &sh) {
-        float4 y;
-        y.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); y.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-        y.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); y.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
-        return y;
-    };
-    if (!p.pool) {
-        for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
-            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c4 * 4);
-            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c4 * 4);
-            // four independent 16-byte loads in flight per thread: these passes are HBM-bound
+    const int cg = p.C / CH;
+    // rev: rows are walked from the END -- the conv tile that produced Z wrote its last rows most recently (still in L2), and the
+    // rows written last here are the ones the next conv tile reads first
+    auto RV = [&](long long r, long long n) -> long long { return p.rev ? n - 1 - r : r; };
+    for (int cv = threadIdx.x; cv < cg; cv += blockDim.x) {
+        const int c0 = cv * CH;
+        float sc[CH], sh[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) { sc[j] = s_scale[c0 + j]; sh[j] = s_shift[c0 + j]; }
+        auto act = [&](RowVec<H> z) {
+#pragma unroll
+            for (int j = 0; j < CH; j++) z.v[j] = fmaxf(fmaf(z.v[j], sc[j], sh[j]), 0.f);
+            return z;
+        };
+        if (!p.pool) {
             const int stride = gridDim.x * blockDim.y;
             int m = blockIdx.x * blockDim.y + threadIdx.y;
-            for (; m + 3 * stride < p.M; m += 4 * stride) {
-                float4 z[4];
+            for (; m + (UNR - 1) * stride < p.M; m += UNR * stride) {
+                RowVec<H> z[UNR];
 #pragma unroll
-                for (int u = 0; u < 4; u++) z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
+                for (int u = 0; u < UNR; u++) z[u] = ldv<H>(p.Z, z0 + RV(m + u * stride, p.M) * p.C + c0);
 #pragma unroll
-                for (int u = 0; u < 4; u++) st4<H>(p.Y, y0 + (long long)(m + u * stride) * p.ldy + c4 * 4, act(z[u], sc, sh));
+                for (int u = 0; u < UNR; u++) stv<H>(p.Y, y0 + RV(m + u * stride, p.M) * p.ldy + c0, act(z[u]));
             }
-            for (; m < p.M; m += stride) {
-                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                st4<H>(p.Y, y0 + (long long)m * p.ldy + c4 * 4, act(z, sc, sh));
-            }
-        }
-    } else {
-        const long long p0 = g * p.p_gs;
-        const int Hp = p.H >> 1, Wp = p.W >> 1;
-        const int Mp = p.M >> 2;
-        for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
-            const float4 sc = *reinterpret_cast<const float4 *>(s_scale + c4 * 4);
-            const float4 sh = *reinterpret_cast<const float4 *>(s_shift + c4 * 4);
-            for (int mp = blockIdx.x * blockDim.y + threadIdx.y; mp < Mp; mp += gridDim.x * blockDim.y) {
+            for (; m < p.M; m += stride) stv<H>(p.Y, y0 + RV(m, p.M) * p.ldy + c0, act(ldv<H>(p.Z, z0 + RV(m, p.M) * p.C + c0)));
+        } else {
+            const long long p0 = g * p.p_gs;
+            const int Hp = p.H >> 1, Wp = p.W >> 1;
+            const int Mp = p.M >> 2;
+            for (int mq = blockIdx.x * blockDim.y + threadIdx.y; mq < Mp; mq += gridDim.x * blockDim.y) {
+                const int mp = (int)RV(mq, Mp);
                 int b, yp, xp;
                 pix3(mp, Hp, Wp, b, yp, xp);
-                float4 mx = make_float4(0.f, 0.f, 0.f, 0.f);   // post-ReLU values are >= 0
-                float4 z[4];
+                RowVec<H> z[4], mx;
                 long long mi[4];
 #pragma unroll
                 for (int w = 0; w < 4; w++) {
                     mi[w] = ((long long)(b * p.H + 2 * yp + (w >> 1))) * p.W + 2 * xp + (w & 1);
-                    z[w] = *reinterpret_cast<const float4 *>(Z + mi[w] * p.C + c4 * 4);
+                    z[w] = ldv<H>(p.Z, z0 + mi[w] * p.C + c0);
                 }
 #pragma unroll
+                for (int j = 0; j < CH; j++) mx.v[j] = 0.f;     // post-ReLU values are >= 0
+#pragma unroll
                 for (int w = 0; w < 4; w++) {
-                    const float4 y = act(z[w], sc, sh);
-                    st4<H>(p.Y, y0 + mi[w] * p.ldy + c4 * 4, y);
-                    mx.x = fmaxf(mx.x, y.x); mx.y = fmaxf(mx.y, y.y); mx.z = fmaxf(mx.z, y.z); mx.w = fmaxf(mx.w, y.w);
+                    const RowVec<H> y = act(z[w]);
+                    stv<H>(p.Y, y0 + mi[w] * p.ldy + c0, y);
+#pragma unroll
+                    for (int j = 0; j < CH; j++) mx.v[j] = fmaxf(mx.v[j], y.v[j]);
                 }
-                st4<H>(p.P, p0 + (long long)mp * p.C + c4 * 4, mx);      // max of the fp32 values, rounded once (rounding is monotone)
+                stv<H>(p.P, p0 + (long long)mp * p.C + c0, mx);      // max of the fp32 values, rounded once (rounding is monotone)
             }
         }
     }
 }
 
 // ---- BatchNorm backward through ReLU.  dzhat = dy * [z*scale+shift > 0];  xhat = (z-mean)*invstd
-//      pass 1: sums[g][0][c] = sum dzhat, sums[g][1][c] = sum dzhat*xhat  (double atomics)
-template <bool FUSED>
-__global__ void k_bn_bwd_reduce(const VvBnBwd p) {
-    extern __shared__ float sm[];   // [2][blockDim.y][C] partials
+//      pass 1: sums[g][0][c] = sum dzhat, sums[g][1][c] = sum dzhat*xhat  (double atomics).  H: Z and dY are fp16.
+//      FUSED (last unit): dY[m][c] = sum_j dout[m][j] * w_out[j][c] is formed from the staged loss gradient and the 1x1 output conv's
+//      own weight / bias gradients are reduced alongside: dW_out[j][c] += dout[m][j] * relu(bn(z))[m][c]
+template <bool FUSED, bool H>
+__global__ void __launch_bounds__(256, FUSED ? 2 : 4) k_bn_bwd_reduce(const VvBnBwd p) {
+    constexpr int CH = RowVec<H>::CH;
+    constexpr int UNR = 4;
+    extern __shared__ float sm[];   // [2][blockDim.y][C] partials (+ FUSED: [3][blockDim.y][C] + [blockDim.y][4])
     const int g = blockIdx.y;
-    const float *Z = p.Z + g * p.z_gs;
-    const float *dY = p.dY + g * p.dy_gs;
+    const long long z0 = g * p.z_gs;
+    const long long dy0 = g * p.dy_gs + p.dy_coff;
     const float *sv = p.save + g * p.save_gs;
-    const int cq = p.C >> 2;
+    const int cg = p.C / CH;
     float *ps = sm, *pq = sm + blockDim.y * p.C;
-    for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
-        const float4 sc = *reinterpret_cast<const float4 *>(sv + c4 * 4);
-        const float4 sh = *reinterpret_cast<const float4 *>(sv + p.C + c4 * 4);
-        const float4 mu = *reinterpret_cast<const float4 *>(sv + 2 * p.C + c4 * 4);
-        const float4 is = *reinterpret_cast<const float4 *>(sv + 3 * p.C + c4 * 4);
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
-        auto acc = [&](const float4 &z, const float4 &d) {
-            float dx = fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f;
-            float dy = fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f;
-            float dz = fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f;
-            float dw = fmaf(z.w, sc.w, sh.w) > 0.f ? d.w : 0.f;
-            s.x += dx; s.y += dy; s.z += dz; s.w += dw;
-            q.x += dx * (z.x - mu.x) * is.x; q.y += dy * (z.y - mu.y) * is.y;
-            q.z += dz * (z.z - mu.z) * is.z; q.w += dw * (z.w - mu.w) * is.w;
-        };
+    const long long last = p.M - 1;
+    auto RV = [&](int r) -> long long { return p.rev_reduce ? last - r : (long long)r; };
+    for (int cv = threadIdx.x; cv < cg; cv += blockDim.x) {
+        const int c0 = cv * CH;
+        float sc[CH], sh[CH], mu[CH], is[CH], s[CH], q[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            sc[j] = sv[c0 + j]; sh[j] = sv[p.C + c0 + j]; mu[j] = sv[2 * p.C + c0 + j]; is[j] = sv[3 * p.C + c0 + j];
+            s[j] = 0.f; q[j] = 0.f;
+        }
         const int stride = gridDim.x * blockDim.y;
         int m = blockIdx.x * blockDim.y + threadIdx.y;
         if (!FUSED) {
-            for (; m + 3 * stride < p.M; m += 4 * stride) {      // eight independent 16-byte loads in flight per thread
-                float4 z[4], d[4];
+            auto acc = [&](const RowVec<H> &z, const RowVec<H> &d) {
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
-                    d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
+                for (int j = 0; j < CH; j++) {
+                    const float dm = fmaf(z.v[j], sc[j], sh[j]) > 0.f ? d.v[j] : 0.f;
+                    s[j] += dm;
+                    q[j] = fmaf(dm, z.v[j] - mu[j], q[j]);        // invstd is applied once, below
+                }
+            };
+            for (; m + (UNR - 1) * stride < p.M; m += UNR * stride) {      // 2 * UNR independent 16-byte loads in flight per thread
+                RowVec<H> z[UNR], d[UNR];
+#pragma unroll
+                for (int u = 0; u < UNR; u++) {
+                    z[u] = ldv<H>(p.Z, z0 + RV(m + u * stride) * p.C + c0);
+                    d[u] = ldv<H>(p.dY, dy0 + RV(m + u * stride) * p.ldy + c0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) acc(z[u], d[u]);
+                for (int u = 0; u < UNR; u++) acc(z[u], d[u]);
             }
-            for (; m < p.M; m += stride) {
-                float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
-                acc(z, d);
-            }
+            for (; m < p.M; m += stride) acc(ldv<H>(p.Z, z0 + RV(m) * p.C + c0), ldv<H>(p.dY, dy0 + RV(m) * p.ldy + c0));
         } else {
-            // fused 1x1 output conv backward: dY from the staged loss gradient; dW_out[j][c] += dout[m][j] * relu(bn(z))[m][c]
             const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
             const int oc = p.out_channels.v[g];
-            float4 w[3], a[3];
-            float db[3] = {0.f, 0.f, 0.f};
+            float w[3][CH], a[3][CH], db[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int j = 0; j < 3; j++) {
-                w[j] = j < oc ? *reinterpret_cast<const float4 *>(P + p.ow_off + j * p.C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-                a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int c = 0; c < CH; c++) { w[j][c] = j < oc ? P[p.ow_off + j * p.C + c0 + c] : 0.f; a[j][c] = 0.f; }
             const float4 *DO = reinterpret_cast<const float4 *>(p.dout) + (long long)g * p.M;
-            auto one = [&](const float4 &z, const float4 &dd) {
+            auto one = [&](const RowVec<H> &z, const float4 &dd) {
                 const float dj[3] = {dd.x, dd.y, dd.z};
-                float4 d, u;
-                d.x = dd.x * w[0].x + dd.y * w[1].x + dd.z * w[2].x; d.y = dd.x * w[0].y + dd.y * w[1].y + dd.z * w[2].y;
-                d.z = dd.x * w[0].z + dd.y * w[1].z + dd.z * w[2].z; d.w = dd.x * w[0].w + dd.y * w[1].w + dd.z * w[2].w;
-                u.x = fmaxf(fmaf(z.x, sc.x, sh.x), 0.f); u.y = fmaxf(fmaf(z.y, sc.y, sh.y), 0.f);
-                u.z = fmaxf(fmaf(z.z, sc.z, sh.z), 0.f); u.w = fmaxf(fmaf(z.w, sc.w, sh.w), 0.f);
 #pragma unroll
-                for (int j = 0; j < 3; j++) {
-                    a[j].x = fmaf(dj[j], u.x, a[j].x); a[j].y = fmaf(dj[j], u.y, a[j].y);
-                    a[j].z = fmaf(dj[j], u.z, a[j].z); a[j].w = fmaf(dj[j], u.w, a[j].w);
-                    db[j] += dj[j];
+                for (int c = 0; c < CH; c++) {
+                    const float y = fmaf(z.v[c], sc[c], sh[c]);
+                    const float u = fmaxf(y, 0.f);
+                    const float d = dj[0] * w[0][c] + dj[1] * w[1][c] + dj[2] * w[2][c];
+#pragma unroll
+                    for (int j = 0; j < 3; j++) a[j][c] = fmaf(dj[j], u, a[j][c]);
+                    const float dm = y > 0.f ? d : 0.f;
+                    s[c] += dm;
+                    q[c] = fmaf(dm, z.v[c] - mu[c], q[c]);
                 }
-                acc(z, d);
+#pragma unroll
+                for (int j = 0; j < 3; j++) db[j] += dj[j];
             };
-            for (; m + stride < p.M; m += 2 * stride) {
-                float4 z[2], dd[2];
+            for (; m + (UNR - 1) * stride < p.M; m += UNR * stride) {
+                RowVec<H> z[UNR];
+                float4 dd[UNR];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
-                    dd[u] = DO[m + u * stride];
+                for (int u = 0; u < UNR; u++) {
+                    z[u] = ldv<H>(p.Z, z0 + RV(m + u * stride) * p.C + c0);
+                    dd[u] = DO[RV(m + u * stride)];
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) one(z[u], dd[u]);
+                for (int u = 0; u < UNR; u++) one(z[u], dd[u]);
             }
-            for (; m < p.M; m += stride) {
-                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                one(z, DO[m]);
-            }
+            for (; m < p.M; m += stride) one(ldv<H>(p.Z, z0 + RV(m) * p.C + c0), DO[RV(m)]);
             // block-level reduction of the 1x1 conv's gradients: [3][rows][C] + [rows][4] behind the two BN partial arrays
             float *pw = sm + 2 * blockDim.y * p.C, *pb = pw + 3 * blockDim.y * p.C;
 #pragma unroll
-            for (int j = 0; j < 3; j++) *reinterpret_cast<float4 *>(pw + (j * blockDim.y + threadIdx.y) * p.C + c4 * 4) = a[j];
-            if (c4 == 0) { pb[threadIdx.y * 4 + 0] = db[0]; pb[threadIdx.y * 4 + 1] = db[1]; pb[threadIdx.y * 4 + 2] = db[2]; }
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int c = 0; c < CH; c++) pw[(j * blockDim.y + threadIdx.y) * p.C + c0 + c] = a[j][c];
+            if (cv == 0) { pb[threadIdx.y * 4 + 0] = db[0]; pb[threadIdx.y * 4 + 1] = db[1]; pb[threadIdx.y * 4 + 2] = db[2]; }
         }
-        *reinterpret_cast<float4 *>(ps + threadIdx.y * p.C + c4 * 4) = s;
-        *reinterpret_cast<float4 *>(pq + threadIdx.y * p.C + c4 * 4) = q;
+#pragma unroll
+        for (int j = 0; j < CH; j++) { ps[threadIdx.y * p.C + c0 + j] = s[j]; pq[threadIdx.y * p.C + c0 + j] = q[j] * is[j]; }
     }
     __syncthreads();
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -452,8 +470,11 @@ __global__ void k_bn_bwd_reduce(const VvBnBwd p) {
 }
 
 //      pass 2: dz = scale * (dzhat - mean(dzhat) - xhat * mean(dzhat*xhat));  d gamma = sum dzhat*xhat, d beta = sum dzhat
+//      H: Z, dY and dZ are fp16
 template <bool FUSED, bool H>
-__global__ void k_bn_bwd_apply(const VvBnBwd p) {
+__global__ void __launch_bounds__(256, FUSED ? 3 : 4) k_bn_bwd_apply(const VvBnBwd p) {
+    constexpr int CH = RowVec<H>::CH;
+    constexpr int UNR = 4;
     extern __shared__ float sm[];   // k1[C], k2[C]
     const int g = blockIdx.y;
     const double *sums = p.sums + g * p.sums_gs;
@@ -471,26 +492,31 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         }
     }
     __syncthreads();
-    const float *Z = p.Z + g * p.z_gs;
-    const float *dY = p.dY + g * p.dy_gs;
+    const long long z0 = g * p.z_gs;
+    const long long dy0 = g * p.dy_gs + p.dy_coff;
     const long long dz0 = g * p.dz_gs;
     const float *sv = p.save + g * p.save_gs;
-    const int cq = p.C >> 2;
+    const int cg = p.C / CH;
     const float ss = p.store_scale;
-    for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
-        const float4 sc = *reinterpret_cast<const float4 *>(sv + c4 * 4);
-        const float4 sh = *reinterpret_cast<const float4 *>(sv + p.C + c4 * 4);
-        const float4 mu = *reinterpret_cast<const float4 *>(sv + 2 * p.C + c4 * 4);
-        const float4 is = *reinterpret_cast<const float4 *>(sv + 3 * p.C + c4 * 4);
-        const float4 a1 = *reinterpret_cast<const float4 *>(k1 + c4 * 4);
-        const float4 a2 = *reinterpret_cast<const float4 *>(k2 + c4 * 4);
-        const float4 scs = make_float4(sc.x * ss, sc.y * ss, sc.z * ss, sc.w * ss);      // store_scale is a power of two: exact
-        auto dz_of = [&](const float4 &z, const float4 &d) {
-            float4 o;
-            o.x = scs.x * ((fmaf(z.x, sc.x, sh.x) > 0.f ? d.x : 0.f) - a1.x - (z.x - mu.x) * is.x * a2.x);
-            o.y = scs.y * ((fmaf(z.y, sc.y, sh.y) > 0.f ? d.y : 0.f) - a1.y - (z.y - mu.y) * is.y * a2.y);
-            o.z = scs.z * ((fmaf(z.z, sc.z, sh.z) > 0.f ? d.z : 0.f) - a1.z - (z.z - mu.z) * is.z * a2.z);
-            o.w = scs.w * ((fmaf(z.w, sc.w, sh.w) > 0.f ? d.w : 0.f) - a1.w - (z.w - mu.w) * is.w * a2.w);
+    const long long last = p.M - 1;          // rev: rows are walked from the END (serpentine order against the previous kernel: its last rows are still in L2)
+    auto RV = [&](int r) -> long long { return p.rev_apply ? last - r : (long long)r; };
+    for (int cv = threadIdx.x; cv < cg; cv += blockDim.x) {
+        const int c0 = cv * CH;
+        // dz = scs * (dzhat - a1 - (z - mu) * is * a2) = scs * dzhat + kb * z + kc with the per-channel constants folded once
+        float sc[CH], scs[CH], sh[CH], kb[CH], kc[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) {
+            sc[j] = sv[c0 + j]; sh[j] = sv[p.C + c0 + j];
+            const float mu = sv[2 * p.C + c0 + j], is = sv[3 * p.C + c0 + j], a1 = k1[c0 + j], a2 = k2[c0 + j];
+            scs[j] = sc[j] * ss;                              // store_scale is a power of two: exact
+            kb[j] = -scs[j] * is * a2;
+            kc[j] = -scs[j] * a1 - kb[j] * mu;
+        }
+        auto dz_of = [&](const RowVec<H> &z, const RowVec<H> &d) {
+            RowVec<H> o;
+#pragma unroll
+            for (int j = 0; j < CH; j++)
+                o.v[j] = fmaf(scs[j], fmaf(z.v[j], sc[j], sh[j]) > 0.f ? d.v[j] : 0.f, fmaf(kb[j], z.v[j], kc[j]));
             return o;
         };
         const int stride = gridDim.x * blockDim.y;
@@ -498,89 +524,83 @@ __global__ void k_bn_bwd_apply(const VvBnBwd p) {
         if (FUSED) {                                         // fused 1x1 output conv backward: dY formed from the staged loss gradient
             const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
             const int oc = p.out_channels.v[g];
-            float4 w[3];
+            float w[3][CH];
 #pragma unroll
             for (int j = 0; j < 3; j++)
-                w[j] = j < oc ? *reinterpret_cast<const float4 *>(P + p.ow_off + j * p.C + c4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int c = 0; c < CH; c++) w[j][c] = j < oc ? P[p.ow_off + j * p.C + c0 + c] : 0.f;
             const float4 *DO = reinterpret_cast<const float4 *>(p.dout) + (long long)g * p.M;
             auto dy_of = [&](const float4 &dd) {
-                float4 d;
-                d.x = dd.x * w[0].x + dd.y * w[1].x + dd.z * w[2].x; d.y = dd.x * w[0].y + dd.y * w[1].y + dd.z * w[2].y;
-                d.z = dd.x * w[0].z + dd.y * w[1].z + dd.z * w[2].z; d.w = dd.x * w[0].w + dd.y * w[1].w + dd.z * w[2].w;
+                RowVec<H> d;
+#pragma unroll
+                for (int c = 0; c < CH; c++) d.v[c] = dd.x * w[0][c] + dd.y * w[1][c] + dd.z * w[2][c];
                 return d;
             };
-            for (; m + stride < p.M; m += 2 * stride) {
-                float4 z[2], dd[2];
+            for (; m + (UNR - 1) * stride < p.M; m += UNR * stride) {
+                RowVec<H> z[UNR];
+                float4 dd[UNR];
 #pragma unroll
-                for (int u = 0; u < 2; u++) {
-                    z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
-                    dd[u] = DO[m + u * stride];
+                for (int u = 0; u < UNR; u++) {
+                    z[u] = ldv<H>(p.Z, z0 + RV(m + u * stride) * p.C + c0);
+                    dd[u] = DO[RV(m + u * stride)];
                 }
 #pragma unroll
-                for (int u = 0; u < 2; u++) st4<H>(p.dZ, dz0 + (long long)(m + u * stride) * p.C + c4 * 4, dz_of(z[u], dy_of(dd[u])));
+                for (int u = 0; u < UNR; u++) stv<H>(p.dZ, dz0 + RV(m + u * stride) * p.C + c0, dz_of(z[u], dy_of(dd[u])));
             }
-            for (; m < p.M; m += stride) {
-                const float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-                st4<H>(p.dZ, dz0 + (long long)m * p.C + c4 * 4, dz_of(z, dy_of(DO[m])));
-            }
-        }
-        for (; m + stride < p.M; m += 2 * stride) {          // four independent 16-byte loads in flight per thread
-            float4 z[2], d[2];
+            for (; m < p.M; m += stride) stv<H>(p.dZ, dz0 + RV(m) * p.C + c0, dz_of(ldv<H>(p.Z, z0 + RV(m) * p.C + c0), dy_of(DO[RV(m)])));
+        } else {
+            for (; m + (UNR - 1) * stride < p.M; m += UNR * stride) {      // 2 * UNR independent 16-byte loads in flight per thread
+                RowVec<H> z[UNR], d[UNR];
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                z[u] = *reinterpret_cast<const float4 *>(Z + (long long)(m + u * stride) * p.C + c4 * 4);
-                d[u] = *reinterpret_cast<const float4 *>(dY + (long long)(m + u * stride) * p.ldy + p.dy_coff + c4 * 4);
-            }
+                for (int u = 0; u < UNR; u++) {
+                    z[u] = ldv<H>(p.Z, z0 + RV(m + u * stride) * p.C + c0);
+                    d[u] = ldv<H>(p.dY, dy0 + RV(m + u * stride) * p.ldy + c0);
+                }
 #pragma unroll
-            for (int u = 0; u < 2; u++) st4<H>(p.dZ, dz0 + (long long)(m + u * stride) * p.C + c4 * 4, dz_of(z[u], d[u]));
-        }
-        for (; m < p.M; m += stride) {
-            float4 z = *reinterpret_cast<const float4 *>(Z + (long long)m * p.C + c4 * 4);
-            float4 d = *reinterpret_cast<const float4 *>(dY + (long long)m * p.ldy + p.dy_coff + c4 * 4);
-            st4<H>(p.dZ, dz0 + (long long)m * p.C + c4 * 4, dz_of(z, d));
+                for (int u = 0; u < UNR; u++) stv<H>(p.dZ, dz0 + RV(m + u * stride) * p.C + c0, dz_of(z[u], d[u]));   // (dZ may alias dY: own rows only)
+            }
+            for (; m < p.M; m += stride)
+                stv<H>(p.dZ, dz0 + RV(m) * p.C + c0, dz_of(ldv<H>(p.Z, z0 + RV(m) * p.C + c0), ldv<H>(p.dY, dy0 + RV(m) * p.ldy + c0)));
         }
     }
 }
 
 // ---- MaxPool2d(2) backward: the gradient of each pooled element is added to the FIRST maximum of its 2x2 window in
-//      row-major order (ATen max_pool2d keeps the first index on ties, which are frequent after ReLU).
+//      row-major order (ATen max_pool2d keeps the first index on ties, which are frequent after ReLU).  H16: Y, dP and dY are fp16.
 template <bool H16>
-__global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ldy, int y_coff, const float *__restrict__ dP,
-                              long long dp_gs, float *__restrict__ dY, long long dy_gs, int lddy, int dy_coff, int B, int H, int W,
+__global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ldy, int y_coff, const void *__restrict__ dP,
+                              long long dp_gs, void *__restrict__ dY, long long dy_gs, int lddy, int dy_coff, int B, int H, int W,
                               int C) {
+    constexpr int CH = RowVec<H16>::CH;
     const int g = blockIdx.y;
-    const int Hp = H >> 1, Wp = W >> 1, cq = C >> 2;
-    const long long total = (long long)B * Hp * Wp * cq;
+    const int Hp = H >> 1, Wp = W >> 1, cg = C / CH;
+    const long long total = (long long)B * Hp * Wp * cg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c4 = (int)(i % cq);
-        int mp = (int)(i / cq);
+        const int c0 = (int)(i % cg) * CH;
+        const int mp = (int)(i / cg);
         int b, yp, xp;
         pix3(mp, Hp, Wp, b, yp, xp);
-        float4 dp = *reinterpret_cast<const float4 *>(dP + g * dp_gs + (long long)mp * C + c4 * 4);
-        float4 v[4];
+        const RowVec<H16> dp = ldv<H16>(dP, g * dp_gs + (long long)mp * C + c0);
+        RowVec<H16> v[4], cur[4];
         long long mi[4];
 #pragma unroll
         for (int w = 0; w < 4; w++) {
             mi[w] = ((long long)(b * H + 2 * yp + (w >> 1))) * W + 2 * xp + (w & 1);
-            v[w] = ld4<H16>(Y, g * y_gs + mi[w] * ldy + y_coff + c4 * 4);
-        }
-        int ax = 0, ay = 0, az = 0, aw = 0;
-        float bx = v[0].x, by = v[0].y, bz = v[0].z, bw = v[0].w;
-#pragma unroll
-        for (int w = 1; w < 4; w++) {
-            if (v[w].x > bx) { bx = v[w].x; ax = w; }
-            if (v[w].y > by) { by = v[w].y; ay = w; }
-            if (v[w].z > bz) { bz = v[w].z; az = w; }
-            if (v[w].w > bw) { bw = v[w].w; aw = w; }
+            v[w] = ldv<H16>(Y, g * y_gs + mi[w] * ldy + y_coff + c0);
+            cur[w] = ldv<H16>(dY, g * dy_gs + mi[w] * lddy + dy_coff + c0);
         }
 #pragma unroll
-        for (int w = 0; w < 4; w++) {
-            float *d = dY + g * dy_gs + mi[w] * lddy + dy_coff + c4 * 4;
-            float4 cur = *reinterpret_cast<float4 *>(d);
-            cur.x += (ax == w) ? dp.x : 0.f; cur.y += (ay == w) ? dp.y : 0.f;
-            cur.z += (az == w) ? dp.z : 0.f; cur.w += (aw == w) ? dp.w : 0.f;
-            *reinterpret_cast<float4 *>(d) = cur;
+        for (int j = 0; j < CH; j++) {
+            int arg = 0;
+            float best = v[0].v[j];
+#pragma unroll
+            for (int w = 1; w < 4; w++)
+                if (v[w].v[j] > best) { best = v[w].v[j]; arg = w; }
+#pragma unroll
+            for (int w = 0; w < 4; w++) cur[w].v[j] += (arg == w) ? dp.v[j] : 0.f;
         }
+#pragma unroll
+        for (int w = 0; w < 4; w++) stv<H16>(dY, g * dy_gs + mi[w] * lddy + dy_coff + c0, cur[w]);
     }
 }
 
@@ -588,25 +608,33 @@ __global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ld
 template <bool H>
 __global__ void k_colsum(const void *__restrict__ D, long long d_gs, int ld, int coff, int M, int C, float scale, float *__restrict__ grads,
                          VvIntG slot, long long slot_stride, long long off) {
+    constexpr int CH = RowVec<H>::CH;
     extern __shared__ float sm[];   // [blockDim.y][C]
     const int g = blockIdx.y;
-    const int cq = C >> 2;
-    for (int c4 = threadIdx.x; c4 < cq; c4 += blockDim.x) {
-        float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int cg = C / CH;
+    for (int cv = threadIdx.x; cv < cg; cv += blockDim.x) {
+        const int c0 = cv * CH;
+        float s[CH];
+#pragma unroll
+        for (int j = 0; j < CH; j++) s[j] = 0.f;
         const int stride = gridDim.x * blockDim.y;
         int m = blockIdx.x * blockDim.y + threadIdx.y;
         for (; m + 3 * stride < M; m += 4 * stride) {
-            float4 d[4];
+            RowVec<H> d[4];
 #pragma unroll
-            for (int u = 0; u < 4; u++) d[u] = ld4<H>(D, g * d_gs + (long long)(m + u * stride) * ld + coff + c4 * 4);
+            for (int u = 0; u < 4; u++) d[u] = ldv<H>(D, g * d_gs + (long long)(m + u * stride) * ld + coff + c0);
 #pragma unroll
-            for (int u = 0; u < 4; u++) { s.x += d[u].x; s.y += d[u].y; s.z += d[u].z; s.w += d[u].w; }
+            for (int u = 0; u < 4; u++)
+#pragma unroll
+                for (int j = 0; j < CH; j++) s[j] += d[u].v[j];
         }
         for (; m < M; m += stride) {
-            float4 d = ld4<H>(D, g * d_gs + (long long)m * ld + coff + c4 * 4);
-            s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+            const RowVec<H> d = ldv<H>(D, g * d_gs + (long long)m * ld + coff + c0);
+#pragma unroll
+            for (int j = 0; j < CH; j++) s[j] += d.v[j];
         }
-        *reinterpret_cast<float4 *>(sm + threadIdx.y * C + c4 * 4) = s;
+#pragma unroll
+        for (int j = 0; j < CH; j++) sm[threadIdx.y * C + c0 + j] = s[j];
     }
     __syncthreads();
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
@@ -700,7 +728,8 @@ __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
     const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
     float *G = p.grads + p.slot.v[g] * p.slot_param_stride;
     const long long u0 = g * p.u_gs;
-    float *dU = p.dU + g * p.du_gs;
+    const long long du0 = g * p.du_gs;
+    const float dus = p.du_scale;
     const int SS = p.S * p.S;
     const bool flow = p.target_is_flow.v[g] != 0;
     const float *ext = flow ? p.grad_of_out : p.grad_raw_out;      // external NCHW gradient, else the staged [m][4]
@@ -736,9 +765,9 @@ __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
             db[j] += d[j];
         }
         float4 o;
-        o.x = d[0] * w[0].x + d[1] * w[1].x + d[2] * w[2].x; o.y = d[0] * w[0].y + d[1] * w[1].y + d[2] * w[2].y;
-        o.z = d[0] * w[0].z + d[1] * w[1].z + d[2] * w[2].z; o.w = d[0] * w[0].w + d[1] * w[1].w + d[2] * w[2].w;
-        *reinterpret_cast<float4 *>(dU + (long long)m * F + 4 * q) = o;
+        o.x = (d[0] * w[0].x + d[1] * w[1].x + d[2] * w[2].x) * dus; o.y = (d[0] * w[0].y + d[1] * w[1].y + d[2] * w[2].y) * dus;
+        o.z = (d[0] * w[0].z + d[1] * w[1].z + d[2] * w[2].z) * dus; o.w = (d[0] * w[0].w + d[1] * w[1].w + d[2] * w[2].w) * dus;
+        st4<H>(p.dU, du0 + (long long)m * F + 4 * q, o);
     };
     const int stride = gridDim.x * npix;
     int m = blockIdx.x * npix + ps;
@@ -884,9 +913,10 @@ __global__ void k_cubes_to_tensors(const uint8_t *__restrict__ raw, const float 
     }
 }
 
-static inline dim3 row_block(int C, int &rows) {
-    int tx = C / 4;
+static inline dim3 row_block(int C, int ch, int &rows) {      // ch channels per thread
+    int tx = C / ch;
     if (tx > 64) tx = 64;
+    if (tx < 1) tx = 1;
     rows = 256 / tx;
     return dim3(tx, rows);
 }
@@ -948,10 +978,14 @@ int vv_prep_ct_w(const float *params, const VvIntG &slot, long long slot_stride,
 
 int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st) {
     int rows;
-    dim3 blk = row_block(p.C, rows);
+    VV_REQUIRE(p.C % 4 == 0, "bn_apply: channel count %d", p.C);
+    dim3 blk = row_block(p.C, 4, rows);
+    // ONE resident wave (148 SMs x 4 blocks) over all groups: every block pays a prologue (the per-channel BatchNorm constants, in
+    // double precision) and must amortise it over many rows -- with one block per 4 rows of work these passes ran at half of the HBM rate
     int work = p.pool ? p.M / 4 : p.M;
     int gx = vv_cdiv(work, rows * 4);
-    if (gx > 148 * 8) gx = 148 * 8;
+    const int cap = (148 * 4) / G > 0 ? (148 * 4) / G : 1;
+    if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     if (p.y_f16) k_bn_apply<true><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
     else k_bn_apply<false><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
@@ -961,17 +995,27 @@ int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st) {
 
 int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     int rows;
-    dim3 blk = row_block(p.C, rows);
+    VV_REQUIRE(p.C % 4 == 0, "bn_bwd: channel count %d", p.C);
+    dim3 blk = row_block(p.C, 4, rows);
+    const int cap = (148 * 4) / G > 0 ? (148 * 4) / G : 1;      // one resident wave over all groups (see vv_bn_apply)
     int gx = vv_cdiv(p.M, rows * 8);
-    if (gx > 148 * 4) gx = 148 * 4;
+    if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
     if (p.dout) VV_REQUIRE(p.C % 4 == 0 && p.params && p.grads, "bn_bwd: fused output-conv backward needs params / grads");
     VV_REQUIRE(!p.dz_f16 || (const void *)p.dZ != (const void *)p.dY, "bn_bwd: an fp16 dZ cannot alias dY");
-    if (p.dout) k_bn_bwd_reduce<true><<<dim3(gx, G), blk, (5 * rows * p.C + 4 * rows) * sizeof(float), st>>>(p);
-    else k_bn_bwd_reduce<false><<<dim3(gx, G), blk, 2 * rows * p.C * sizeof(float), st>>>(p);
+    VV_REQUIRE(p.z_f16 == p.dz_f16, "bn_bwd: Z and dZ are both fp16 (fp16 mode) or both fp32");
+    if (p.dout) {
+        const size_t smr = (5 * rows * p.C + 4 * rows) * sizeof(float);
+        if (p.z_f16) k_bn_bwd_reduce<true, true><<<dim3(gx, G), blk, smr, st>>>(p);
+        else k_bn_bwd_reduce<true, false><<<dim3(gx, G), blk, smr, st>>>(p);
+    } else {
+        const size_t smr = 2 * rows * p.C * sizeof(float);
+        if (p.z_f16) k_bn_bwd_reduce<false, true><<<dim3(gx, G), blk, smr, st>>>(p);
+        else k_bn_bwd_reduce<false, false><<<dim3(gx, G), blk, smr, st>>>(p);
+    }
     VV_CKL();
     int gx2 = vv_cdiv(p.M, rows * 4);
-    if (gx2 > 148 * 8) gx2 = 148 * 8;
+    if (gx2 > cap) gx2 = cap;
     if (gx2 < 1) gx2 = 1;
     const dim3 grid(gx2, G);
     const size_t sm = 2 * p.C * sizeof(float);
@@ -986,7 +1030,7 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     return 0;
 }
 
-int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
+int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const void *dP, long long dp_gs, void *dY, long long dy_gs,
                    int lddy, int dy_coff, int G, int B, int H, int W, int C, cudaStream_t st) {
     long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
     int gx = vv_cdiv(total, 256);
@@ -1000,7 +1044,7 @@ int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff
 int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M, int C, float scale, float *grads, const VvIntG &slot,
               long long slot_stride, long long off, int G, cudaStream_t st) {
     int rows;
-    dim3 blk = row_block(C, rows);
+    dim3 blk = row_block(C, 4, rows);
     int gx = vv_cdiv(M, rows * 16);
     if (gx > 148 * 2) gx = 148 * 2;
     if (gx < 1) gx = 1;

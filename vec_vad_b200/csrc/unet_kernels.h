@@ -9,10 +9,11 @@ struct VvIntG {
 };
 
 struct VvBnApply {
-    const float *Z;      long long z_gs;                  // [G][M][C] raw conv output
+    const void *Z;       long long z_gs;                  // [G][M][C] raw conv output: fp32, or fp16 when y_f16 (the fp16 mode stores both as fp16)
     void *Y;             long long y_gs;  int ldy, y_coff; // destination view (may live inside a concat buffer); fp32, or fp16 when y_f16
     void *P;             long long p_gs;                  // pooled destination [G][M/4][C] (pool != 0), same element type as Y
     int pool, y_f16;
+    int rev;                                              // walk the rows from the end (serpentine order for L2 reuse)
     int M, H, W, C;
     int training;
     const double *stats; long long stats_gs;              // [G][2][C] sums (training)
@@ -22,10 +23,11 @@ struct VvBnApply {
 };
 
 struct VvBnBwd {
-    const float *Z;      long long z_gs;
-    const float *dY;     long long dy_gs; int ldy, dy_coff;
+    const void *Z;       long long z_gs;  int z_f16;      // raw conv output, fp32 or fp16
+    const void *dY;      long long dy_gs; int ldy, dy_coff; // same element type as Z (the fp16 mode stores output gradients as fp16 too)
     void *dZ;            long long dz_gs;                 // dense [G][M][C]: fp32 (may alias dY when dY is dense) or fp16 (dz_f16; never aliases)
     int dz_f16;
+    int rev_reduce, rev_apply;                            // row order of the two passes (serpentine order for L2 reuse)
     float store_scale;                                    // dZ is multiplied by this when stored (the fp16 path's loss scale, applied once, at the last unit)
     float grad_unscale;                                   // d gamma / d beta are multiplied by this (1 / loss scale where dY already carries it)
     int M, C;
@@ -53,7 +55,8 @@ struct VvOutFwd {
 
 struct VvOutBwd {
     const void *U;       long long u_gs;  int u_f16;
-    float *dU;           long long du_gs;
+    void *dU;            long long du_gs;                 // same element type as U
+    float du_scale;                                       // dU is multiplied by this (the fp16 mode's loss scale)
     const float *params; float *grads; VvIntG slot; long long slot_param_stride, w_off, b_off;
     VvIntG out_channels, target_is_flow, out_slot;
     int M, S, F;
@@ -88,7 +91,7 @@ int vv_prep_ct_w(const float *params, const VvIntG &slot, long long slot_stride,
                  void *Wbf, long long wf_gs, void *Wbd, long long wd_gs, int w_f16, float *vec, long long vec_gs, int G, cudaStream_t st);
 int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st);
 int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st);
-int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const float *dP, long long dp_gs, float *dY, long long dy_gs,
+int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff, const void *dP, long long dp_gs, void *dY, long long dy_gs,
                    int lddy, int dy_coff, int G, int B, int H, int W, int C, cudaStream_t st);
 int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M, int C, float scale, float *grads, const VvIntG &slot,
               long long slot_stride, long long off, int G, cudaStream_t st);
