@@ -3,7 +3,7 @@ import sys, torch
 sys.path.insert(0, '.')
 from vec_vad_b200 import unet as vu, vad_datasets as vd, flow_ops as ops
 kw = dict(features_root=32, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
-for tc in (True, False):
+for tc in (2, 1, 0):          # fp16-operand tiles, tf32 tiles, fp32 SIMT tiles
     torch.manual_seed(0)
     m = vu.SelfCompleteNet4(use_tensor_cores=tc, **kw).cuda().train()
     m.init_adam()

@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
     constexpr int ROWB = F16 ? KS * 2 : KS * 4;              // bytes of one pixel row of a 32-channel slab
     constexpr int KSTEPS = F16 ? KS / 16 : KS / 8;           // MMAs per (tap, slab): 32 bytes of K each
     constexpr int B_TAP = BN * ROWB;                         // one (tap, slab) weight tile
-    constexpr int NBUF = (4 * BN <= 512 && BN < 128) ? 2 : 1; // accumulator double-buffering across pairs while TMEM allows it
+    constexpr int NBUF = (4 * BN <= 512) ? 2 : 1;              // accumulator double-buffering across pairs (BN = 128: all 512 TMEM columns)
     constexpr int TMEM_COLS = 2 * NBUF * BN < 32 ? 32 : 2 * NBUF * BN;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);

@@ -151,20 +151,22 @@ VvTaps taps2x2(int sign) {
 // algorithmic FLOPs of one contraction launch: 2 * pixels * N * K * taps over all groups
 double igemm_flops(int B, int H, int W, int N, int K, int taps, int G) { return 2.0 * B * H * W * (double)N * K * taps * G; }
 
-int run_igemm(bool want_tc, const VvIGemm &p, cudaStream_t st, int k_real = 0) {
+// k_real: real K per tap where the operand is channel-padded (first conv); flops > 0: the algorithmic count where the launch computes
+// structural zeros (the stride-2 transposed conv runs 16 tap-blocks for the 9 taps of its 3x3 kernel)
+int run_igemm(bool want_tc, const VvIGemm &p, cudaStream_t st, int k_real = 0, double flops = 0.0) {
     const bool tc = want_tc && vv_igemm_tc_supported(p);
     if (p.ab_f16 && !(tc && (vv_igemm_flat_supported(p) || vv_igemm_tc3_supported(p))))
         return vv_set_err(-3, "fp16-operand contraction %dx%d Kt=%d N=%d is not covered by the tcgen05 tiles (no fp32 fallback reads fp16)", p.H, p.W, p.Kt, p.N);
-    VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
+    VvProfScope ps(tc ? VV_PROF_IGEMM_TC : VV_PROF_IGEMM_SIMT, flops > 0.0 ? flops : igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_igemm_flat_supported(p)) return vv_launch_igemm_flat(p, st);
     if (tc && vv_igemm_tc3_supported(p)) return vv_launch_igemm_tc3(p, st);
     return vv_launch_igemm_simt(p, st);
 }
-int run_wgrad(bool want_tc, const VvWGrad &p, cudaStream_t st, int k_real = 0) {
+int run_wgrad(bool want_tc, const VvWGrad &p, cudaStream_t st, int k_real = 0, double flops = 0.0) {
     const bool tc = want_tc && vv_wgrad_tc_supported(p);
     if (p.ab_f16 && !(tc && (vv_wgrad_flat_supported(p) || vv_wgrad_tc2_supported(p))))
         return vv_set_err(-3, "fp16-operand weight gradient %dx%d Kt=%d N=%d is not covered by the tcgen05 tiles", p.H, p.W, p.Kt, p.N);
-    VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
+    VvProfScope ps(tc ? VV_PROF_WGRAD_TC : VV_PROF_WGRAD_SIMT, flops > 0.0 ? flops : igemm_flops(p.B, p.H, p.W, p.N, k_real ? k_real : p.Kt, p.taps.n, p.G), st);
     if (tc && vv_wgrad_flat_supported(p)) return vv_launch_wgrad_flat(p, st);
     if (tc && vv_wgrad_tc2_supported(p)) return vv_launch_wgrad_tc2(p, st);
     return vv_launch_wgrad_simt(p, st);
@@ -335,20 +337,39 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     // 1. weights into GEMM layouts (they change every optimiser step): one launch for all conv units when they tile by 32
     bool batched = true;
     for (int u = 0; u < NU; u++) batched = batched && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
+    // With the side stream only the first two units' weights (the 32x32 layers the forward starts with) are re-laid out on the
+    // critical path; the other twelve follow on the side stream while those layers run (the forward waits for them before unit 2).
+    cudaStream_t sP = n->use_side ? n->wg_stream : st;
+    cudaEvent_t w_ready = nullptr;
+    if (n->use_side) {
+        VV_CK(cudaEventRecord(n->ev[VV_NEV - 1], st));
+        VV_CK(cudaStreamWaitEvent(sP, n->ev[VV_NEV - 1], 0));
+    }
     if (batched) {
-        VvPrepAll all;
-        memset(&all, 0, sizeof(all));
-        all.n = NU;
-        for (int u = 0; u < NU; u++) {
-            VvPrepUnit &pu = all.u[u];
-            pu.w_off = c.conv_w[u]; pu.b_off = c.conv_b[u]; pu.g_off = c.bn_w[u]; pu.beta_off = c.bn_b[u];
-            pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
-            pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
-            pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
+        static int prep_side = -1;          // VECVAD_PREP_SIDE=1: units 2..13 re-laid out on the side stream (measured slower: default off)
+        if (prep_side < 0) { const char *e = getenv("VECVAD_PREP_SIDE"); prep_side = (e && e[0] == '1') ? 1 : 0; }
+        const int n_early = (n->use_side && prep_side) ? 2 : NU;
+        for (int part = 0; part < 2; part++) {
+            const int u0 = part ? n_early : 0, u1 = part ? NU : n_early;
+            if (u0 >= u1) continue;
+            VvPrepAll all;
+            memset(&all, 0, sizeof(all));
+            all.n = u1 - u0;
+            for (int u = u0; u < u1; u++) {
+                VvPrepUnit &pu = all.u[u - u0];
+                pu.w_off = c.conv_w[u]; pu.b_off = c.conv_b[u]; pu.g_off = c.bn_w[u]; pu.beta_off = c.bn_b[u];
+                pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
+                pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
+                pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
+            }
+            all.w_f16 = n->f16;
+            int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, part ? sP : st);
+            if (r) return r;
+            if (part && n->use_side) {
+                w_ready = n->ev[VV_NEV - 3];
+                VV_CK(cudaEventRecord(w_ready, sP));
+            }
         }
-        all.w_f16 = n->f16;
-        int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, st);
-        if (r) return r;
     } else {
         for (int u = 0; u < NU; u++) {
             int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
@@ -358,12 +379,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         }
     }
     // transposed-conv weights are first needed a third of the way into the forward: re-lay them out on the side stream meanwhile
-    cudaStream_t sP = n->use_side ? n->wg_stream : st;
     cudaEvent_t ct_ready = nullptr;
-    if (n->use_side) {
-        VV_CK(cudaEventRecord(n->ev[VV_NEV - 1], st));
-        VV_CK(cudaStreamWaitEvent(sP, n->ev[VV_NEV - 1], 0));
-    }
     for (int k = 0; k < NT; k++) {
         int r = vv_prep_ct_w(n->params, n->slot, c.slot_param_stride, c.up_w[k], c.up_b[k], n->tCi[k], n->tCo[k], n->tWf[k],
                              16LL * n->tCo[k] * n->tCi[k], n->tWd[k], 16LL * n->tCo[k] * n->tCi[k], n->f16, n->tvec[k], n->tCo[k], G, sP);
@@ -421,10 +437,14 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         p.O = (float *)o.p; p.o_gs = o.gs; p.ldo = o.ld; p.o_coff = o.coff; p.o_d2s = 1; p.o_f16 = n->f16;
         p.bias = n->tvec[k]; p.bias_gs = n->tCo[k];
         p.stats = nullptr; p.G = G;
-        return run_igemm(n->cfg.use_tensor_cores != 0, p, st);
+        // algorithmic FLOPs of ConvTranspose2d(k3, s2): 9 taps x Ci x Co per INPUT pixel
+        return run_igemm(n->cfg.use_tensor_cores != 0, p, st, 0, igemm_flops(B, n->tH[k], n->tH[k], n->tCo[k], n->tCi[k], 9, G));
     };
     int r;
-    for (int u = 0; u < 8; u++) if ((r = conv_unit(u))) return r;
+    for (int u = 0; u < 8; u++) {
+        if (u == 2 && w_ready) VV_CK(cudaStreamWaitEvent(st, w_ready, 0));
+        if ((r = conv_unit(u))) return r;
+    }
     for (int k = 0; k < 3; k++) {
         if (k == 0 && ct_ready) VV_CK(cudaStreamWaitEvent(st, ct_ready, 0));
         if ((r = convT(k))) return r;
@@ -632,7 +652,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         w.Gd = (const float *)dhalf.p; w.g_gs = dhalf.gs; w.ldg = dhalf.ld; w.g_coff = dhalf.coff; w.g_s2d = 1; w.N = 4 * Co;
         w.taps = t2f; w.dW = n->tdW[k]; w.dw_gs = 16LL * Co * Ci; w.G = G;
         if ((rr = fork())) return rr;
-        if ((rr = run_wgrad(c.use_tensor_cores != 0, w, sB))) return rr;
+        if ((rr = run_wgrad(c.use_tensor_cores != 0, w, sB, 0, igemm_flops(B, Hi, Hi, Co, Ci, 9, G)))) return rr;
         if ((rr = vv_scatter_ct_wgrad(n->tdW[k], w.dw_gs, Ci, Co, inv_LS, n->grads, n->slot, c.slot_param_stride, c.up_w[k], G, sB))) return rr;
         if ((rr = mark(nullptr))) return rr;
         VvIGemm p;
@@ -643,7 +663,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         p.O = (float *)ddeep.p; p.o_gs = ddeep.gs; p.ldo = ddeep.ld; p.o_coff = ddeep.coff; p.o_d2s = 0; p.o_f16 = f16;
         p.bias = nullptr; p.stats = nullptr; p.G = G;
         if ((rr = before_write(ddeep.p))) return rr;
-        return run_igemm(c.use_tensor_cores != 0, p, st);
+        return run_igemm(c.use_tensor_cores != 0, p, st, 0, igemm_flops(B, Hi, Hi, Co, Ci, 9, G));
     };
 
     // ---- decoder, deepest last.  GA holds dU3 now (external gradients), or nothing (fused: formed from DOUT on the fly).
