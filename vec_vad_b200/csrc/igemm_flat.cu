@@ -102,10 +102,6 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int i = threadIdx.x; i < BN; i += FL_THREADS) {
-        s_bias[i] = p.bias ? p.bias[g * p.bias_gs + n0 + i] : 0.f;
-        s_sum[i] = 0.f; s_sq[i] = 0.f;
-    }
     // zero what TMA never writes but the MMAs may read: the guard in front of stage 0 and the slack behind every box
     for (int i = threadIdx.x; i < FL_GUARD / 16; i += FL_THREADS) reinterpret_cast<uint4 *>(stage0 - FL_GUARD)[i] = make_uint4(0, 0, 0, 0);
     {
@@ -114,6 +110,11 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
             const int s = i / slack16, j = i - s * slack16;
             reinterpret_cast<uint4 *>(stage0 + s * p.stage_bytes + p.a_bytes)[j] = make_uint4(0, 0, 0, 0);
         }
+    }
+    vv_pdl_wait();                                           // set-up above overlaps the previous kernel's tail; global memory from here on
+    for (int i = threadIdx.x; i < BN; i += FL_THREADS) {
+        s_bias[i] = p.bias ? p.bias[g * p.bias_gs + n0 + i] : 0.f;
+        s_sum[i] = 0.f; s_sq[i] = 0.f;
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy zeros -> visible to the UMMA (async proxy) reads
     tc_fence_before();
@@ -369,7 +370,7 @@ int launch_flat(const CUtensorMap &tmA, const CUtensorMap &tmB, const FlatParams
         VV_CK(cudaFuncSetAttribute(k_igemm_flat<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, FL_SMEM_MAX));
         attr = true;
     }
-    k_igemm_flat<BN, F16><<<grid, FL_THREADS, smem, st>>>(tmA, tmB, fp);
+    vv_launch(k_igemm_flat<BN, F16>, dim3(grid), dim3(FL_THREADS), smem, st, tmA, tmB, fp);
     VV_CKL();
     if (fp.trace) {      // debugging aid: synchronous
         unsigned long long h[18];

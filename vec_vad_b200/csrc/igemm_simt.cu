@@ -32,6 +32,7 @@ __device__ __forceinline__ const float *a_addr(const float *A, int lda, int coff
 // ------------------------------------------------------------------------------------------------
 template <int TN>
 __global__ void __launch_bounds__(256) k_igemm_simt(const VvIGemm p) {
+    vv_pdl_wait();
     constexpr int BN = 16 * TN;
     constexpr int BS = BN + 4;
     __shared__ __align__(16) float As[2][BK][AS];
@@ -194,6 +195,7 @@ __global__ void __launch_bounds__(256) k_igemm_simt(const VvIGemm p) {
 // ------------------------------------------------------------------------------------------------
 constexpr int WK = 16;  // pixels per step
 __global__ void __launch_bounds__(256) k_wgrad_simt(const VvWGrad p, int nqt, int rows_per_split) {
+    vv_pdl_wait();
     __shared__ __align__(16) float Gs[2][WK][64 + 4];
     __shared__ __align__(16) float As[2][WK][64 + 4];
     const int g = blockIdx.z;
@@ -298,10 +300,10 @@ int vv_launch_igemm_simt(const VvIGemm &p, cudaStream_t st) {
     int M = p.B * p.H * p.W;
     if (p.N % 64 == 0 || p.N > 64) {
         dim3 grid(vv_cdiv(M, BM), vv_cdiv(p.N, 64), p.G);
-        k_igemm_simt<4><<<grid, 256, 0, st>>>(p);
+        vv_launch(k_igemm_simt<4>, dim3(grid), dim3(256), 0, st, p);
     } else {
         dim3 grid(vv_cdiv(M, BM), vv_cdiv(p.N, 32), p.G);
-        k_igemm_simt<2><<<grid, 256, 0, st>>>(p);
+        vv_launch(k_igemm_simt<2>, dim3(grid), dim3(256), 0, st, p);
     }
     VV_CKL();
     return 0;
@@ -323,7 +325,7 @@ int vv_launch_wgrad_simt(const VvWGrad &p, cudaStream_t st) {
     rows = (rows + WK - 1) / WK * WK;
     msplit = vv_cdiv(M, rows);
     dim3 grid(nqt * nnt, msplit, p.G);
-    k_wgrad_simt<<<grid, 256, 0, st>>>(p, nqt, rows);
+    vv_launch(k_wgrad_simt, dim3(grid), dim3(256), 0, st, p, nqt, rows);
     VV_CKL();
     return 0;
 }

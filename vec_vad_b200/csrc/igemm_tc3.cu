@@ -101,6 +101,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    vv_pdl_wait();                                           // set-up above overlaps the previous kernel's tail; global memory from here on
     for (int i = threadIdx.x; i < BN; i += T3_THREADS) {
         s_bias[i] = p.bias ? p.bias[g * p.bias_gs + (p.o_d2s ? (n0 + i) % (p.N >> 2) : (n0 + i))] : 0.f;
         s_sum[i] = 0.f; s_sq[i] = 0.f;
@@ -411,7 +412,7 @@ int launch3(const CUtensorMap &tmA, const CUtensorMap &tmB, const Tc3Params &tp,
         VV_CK(cudaFuncSetAttribute(k_igemm_tc3<BN, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, T3_SMEM_MAX));
         attr = true;
     }
-    k_igemm_tc3<BN, F16><<<grid, T3_THREADS, smem, st>>>(tmA, tmB, tp);
+    vv_launch(k_igemm_tc3<BN, F16>, dim3(grid), dim3(T3_THREADS), smem, st, tmA, tmB, tp);
     VV_CKL();
     if (tp.trace) {      // debugging aid: synchronous
         unsigned long long h[12];

@@ -22,6 +22,11 @@ int vv_set_err(int code, const char *fmt, ...) {
 extern "C" const char *vecvad_last_error(void) { return g_err; }
 extern "C" int vecvad_abi_version(void) { return VECVAD_ABI_VERSION; }
 unsigned long long g_vv_launches = 0;
+bool vv_pdl_enabled() {                      // VECVAD_PDL=0: plain stream-ordered launches (A/B baseline)
+    static int on = -1;
+    if (on < 0) { const char *e = getenv("VECVAD_PDL"); on = (e && e[0] == '0') ? 0 : 1; }
+    return on != 0;
+}
 extern "C" uint64_t vecvad_launch_count(void) { return g_vv_launches; }
 
 namespace {

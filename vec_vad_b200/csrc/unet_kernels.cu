@@ -52,6 +52,7 @@ __device__ __forceinline__ void pix3(int m, int H, int W, int &b, int &y, int &x
 template <bool H>
 __global__ void k_prep_input(const float *__restrict__ x, void *__restrict__ X0, int B, int T, int S, int cinp, int padding,
                              VvIntG erase) {
+    vv_pdl_wait();
     const int g = blockIdx.y;
     const int M = B * S * S;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -83,6 +84,7 @@ __global__ void k_prep_input(const float *__restrict__ x, void *__restrict__ X0,
 __global__ void k_prep_conv_w(const float *__restrict__ params, VvIntG slot, long long slot_stride, long long w_off, long long b_off,
                               long long g_off, long long beta_off, int N, int C, int Cp, void *__restrict__ Wf, long long wf_gs,
                               void *__restrict__ Wd, long long wd_gs, int w_f16, float *__restrict__ vec, long long vec_gs) {
+    vv_pdl_wait();
     const int g = blockIdx.y;
     const float *P = params + slot.v[g] * slot_stride;
     const int total = 9 * N * Cp;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(256) k_prep_conv_w_tiled(const float *__restri
                                                            long long w_off, long long b_off, long long g_off, long long beta_off, int N,
                                                            int C, int Cp, void *__restrict__ Wf, long long wf_gs, void *__restrict__ Wd,
                                                            long long wd_gs, int w_f16, float *__restrict__ vec, long long vec_gs) {
+    vv_pdl_wait();
     __shared__ float tile[32][32 * 9 + 1];
     const int g = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const float *P = params + slot.v[g] * slot_stride;
@@ -146,6 +149,7 @@ __device__ __forceinline__ int find_unit(const VvPrepAll &all, int blk) {
 }
 __global__ void __launch_bounds__(256) k_prep_conv_w_all(const float *__restrict__ params, VvIntG slot, long long slot_stride,
                                                          const VvPrepAll all) {
+    vv_pdl_wait();
     __shared__ float tile[32][32 * 9 + 1];
     const int ui = find_unit(all, blockIdx.x);
     const VvPrepUnit &U = all.u[ui];
@@ -179,6 +183,7 @@ __global__ void __launch_bounds__(256) k_prep_conv_w_all(const float *__restrict
 }
 __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_all(float *__restrict__ grads, VvIntG slot, long long slot_stride,
                                                                 const VvPrepAll all) {
+    vv_pdl_wait();
     __shared__ float tile[32][32 * 9 + 1];
     const int ui = find_unit(all, blockIdx.x);
     const VvPrepUnit &U = all.u[ui];
@@ -205,6 +210,7 @@ __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_all(float *__restric
 __global__ void k_prep_ct_w(const float *__restrict__ params, VvIntG slot, long long slot_stride, long long w_off, long long b_off,
                             int Ci, int Co, void *__restrict__ Wbf, long long wf_gs, void *__restrict__ Wbd, long long wd_gs, int w_f16,
                             float *__restrict__ vec, long long vec_gs) {
+    vv_pdl_wait();
     const int g = blockIdx.y;
     const float *P = params + slot.v[g] * slot_stride;
     const int total = 4 * 4 * Co * Ci;
@@ -276,6 +282,7 @@ __device__ __forceinline__ void stv(void *base, long long idx, const RowVec<H> &
 // operands of the next contraction; rounded once, here, exactly as the tf32 path rounds them on their way into shared memory)
 template <bool H>
 __global__ void __launch_bounds__(256, 4) k_bn_apply(const VvBnApply p) {
+    vv_pdl_wait();
     constexpr int CH = RowVec<H>::CH;
     constexpr int UNR = 4;                 // rows in flight per thread: these passes are bound by bytes in flight
     extern __shared__ float sm[];          // scale[C], shift[C]
@@ -352,6 +359,7 @@ __global__ void __launch_bounds__(256, 4) k_bn_apply(const VvBnApply p) {
 //      own weight / bias gradients are reduced alongside: dW_out[j][c] += dout[m][j] * relu(bn(z))[m][c]
 template <bool FUSED, bool H>
 __global__ void __launch_bounds__(256, FUSED ? 2 : 4) k_bn_bwd_reduce(const VvBnBwd p) {
+    vv_pdl_wait();
     constexpr int CH = RowVec<H>::CH;
     constexpr int UNR = 4;
     extern __shared__ float sm[];   // [2][blockDim.y][C] partials (+ FUSED: [3][blockDim.y][C] + [blockDim.y][4])
@@ -473,6 +481,7 @@ __global__ void __launch_bounds__(256, FUSED ? 2 : 4) k_bn_bwd_reduce(const VvBn
 //      H: Z, dY and dZ are fp16
 template <bool FUSED, bool H>
 __global__ void __launch_bounds__(256, FUSED ? 3 : 4) k_bn_bwd_apply(const VvBnBwd p) {
+    vv_pdl_wait();
     constexpr int CH = RowVec<H>::CH;
     constexpr int UNR = 4;
     extern __shared__ float sm[];   // k1[C], k2[C]
@@ -571,6 +580,7 @@ template <bool H16>
 __global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ldy, int y_coff, const void *__restrict__ dP,
                               long long dp_gs, void *__restrict__ dY, long long dy_gs, int lddy, int dy_coff, int B, int H, int W,
                               int C) {
+    vv_pdl_wait();
     constexpr int CH = RowVec<H16>::CH;
     const int g = blockIdx.y;
     const int Hp = H >> 1, Wp = W >> 1, cg = C / CH;
@@ -608,6 +618,7 @@ __global__ void k_maxpool_bwd(const void *__restrict__ Y, long long y_gs, int ld
 template <bool H>
 __global__ void k_colsum(const void *__restrict__ D, long long d_gs, int ld, int coff, int M, int C, float scale, float *__restrict__ grads,
                          VvIntG slot, long long slot_stride, long long off) {
+    vv_pdl_wait();
     constexpr int CH = RowVec<H>::CH;
     extern __shared__ float sm[];   // [blockDim.y][C]
     const int g = blockIdx.y;
@@ -650,6 +661,7 @@ __global__ void k_colsum(const void *__restrict__ D, long long d_gs, int ld, int
 //      deterministic in-CTA reduction.  U [G][B*S*S][F];  out NCHW;  dout [G][B*S*S][4].
 template <bool H>
 __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
+    vv_pdl_wait();
     extern __shared__ float sm[];   // tile [256][F+1], w [4][F], b[4]
     const int g = blockIdx.y, b = blockIdx.x;
     const int F = p.F, SS = p.S * p.S;
@@ -720,6 +732,7 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
 // flight; the weight / bias gradients are reduced in shared memory and flushed with one atomic per element per block.
 template <bool H>
 __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
+    vv_pdl_wait();
     extern __shared__ float sm_ob[];            // dW partial [3][F], db partial [4]
     const int g = blockIdx.y;
     const int F = p.F, FQ = F >> 2;
@@ -801,6 +814,7 @@ __global__ void __launch_bounds__(256) k_outconv_bwd(const VvOutBwd p) {
 // ---- gradient re-layout back to PyTorch's parameter layouts
 __global__ void k_scatter_conv_wgrad(const float *__restrict__ dWf, long long gs, int N, int C, int Cp, float *__restrict__ grads,
                                      VvIntG slot, long long slot_stride, long long w_off) {
+    vv_pdl_wait();
     const int g = blockIdx.y;
     const int total = N * C * 9;
     int i = blockIdx.x * blockDim.x + threadIdx.x;   // i indexes the PyTorch layout [n][c][t] (coalesced writes)
@@ -813,6 +827,7 @@ __global__ void k_scatter_conv_wgrad(const float *__restrict__ dWf, long long gs
 __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_tiled(const float *__restrict__ dWf, long long gs, int N, int C, int Cp,
                                                                   float *__restrict__ grads, VvIntG slot, long long slot_stride,
                                                                   long long w_off) {
+    vv_pdl_wait();
     __shared__ float tile[32][32 * 9 + 1];
     const int g = blockIdx.z, n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
     const int cw = min(32, C - c0);
@@ -831,6 +846,7 @@ __global__ void __launch_bounds__(256) k_scatter_conv_wgrad_tiled(const float *_
 
 __global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, int Ci, int Co, float scale, float *__restrict__ grads,
                                    VvIntG slot, long long slot_stride, long long w_off) {
+    vv_pdl_wait();
     const int g = blockIdx.y;
     const int total = Ci * Co * 9;
     int i = blockIdx.x * blockDim.x + threadIdx.x;   // PyTorch layout [ci][co][ky][kx]
@@ -845,6 +861,7 @@ __global__ void k_scatter_ct_wgrad(const float *__restrict__ dWb, long long gs, 
 
 // ---- losses from the per-cube SSE buffer: mean over B * ch * S * S (train.py:385-392)
 __global__ void k_losses(const float *__restrict__ sse, int G, int B, VvIntG is_flow, float inv_raw, float inv_of, float *__restrict__ out) {
+    vv_pdl_wait();
     __shared__ double r[2][256];
     double a = 0.0, b = 0.0;
     for (int i = threadIdx.x; i < G * B; i += 256) {
@@ -863,6 +880,7 @@ __global__ void k_losses(const float *__restrict__ sse, int G, int B, VvIntG is_
 // ---- Adam (torch.optim.Adam, amsgrad=False, maximize=False): train.py:376
 __global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
                        float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+    vv_pdl_wait();
     long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 pp = *reinterpret_cast<float4 *>(p + i);
@@ -895,6 +913,7 @@ __global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float
 // ---- cube staging: uint8 [N,T,S,S,3] -> x [N,3T,S,S] (/255), flow [N,To,S,S,2] -> x_of [N,2To,S,S]   (vad_datasets.py:153-165)
 __global__ void k_cubes_to_tensors(const uint8_t *__restrict__ raw, const float *__restrict__ flow, float *__restrict__ x,
                                    float *__restrict__ x_of, int n, int T, int To, int S) {
+    vv_pdl_wait();
     const long long SS = (long long)S * S;
     const long long nraw = (long long)n * T * 3 * SS, nof = flow ? (long long)n * To * 2 * SS : 0;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nraw + nof; i += (long long)gridDim.x * blockDim.x) {
@@ -928,8 +947,8 @@ static inline dim3 row_block(int C, int ch, int &rows) {      // ch channels per
 // ------------------------------------------------------------------------------------------------
 int vv_prep_input(const float *x, void *X0, int x0_f16, int G, int B, int T, int S, int cinp, int padding, const VvIntG &erase, cudaStream_t st) {
     int M = B * S * S;
-    if (x0_f16) k_prep_input<true><<<dim3(vv_cdiv(M, 256), G), 256, 0, st>>>(x, X0, B, T, S, cinp, padding, erase);
-    else k_prep_input<false><<<dim3(vv_cdiv(M, 256), G), 256, 0, st>>>(x, X0, B, T, S, cinp, padding, erase);
+    if (x0_f16) vv_launch(k_prep_input<true>, dim3(vv_cdiv(M, 256), G), dim3(256), 0, st, x, X0, B, T, S, cinp, padding, erase);
+    else vv_launch(k_prep_input<false>, dim3(vv_cdiv(M, 256), G), dim3(256), 0, st, x, X0, B, T, S, cinp, padding, erase);
     VV_CKL();
     return 0;
 }
@@ -938,10 +957,10 @@ int vv_prep_conv_w(const float *params, const VvIntG &slot, long long slot_strid
                    long long beta_off, int N, int C, int Cp, void *Wf, long long wf_gs, void *Wd, long long wd_gs, int w_f16, float *vec,
                    long long vec_gs, int G, cudaStream_t st) {
     if (N % 32 == 0 && Cp % 32 == 0)
-        k_prep_conv_w_tiled<<<dim3(N / 32, Cp / 32, G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C, Cp, Wf,
+        vv_launch(k_prep_conv_w_tiled, dim3(N / 32, Cp / 32, G), dim3(256), 0, st, params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C, Cp, Wf,
                                                                     wf_gs, Wd, wd_gs, w_f16, vec, vec_gs);
     else
-        k_prep_conv_w<<<dim3(vv_cdiv(9LL * N * Cp, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C,
+        vv_launch(k_prep_conv_w, dim3(vv_cdiv(9LL * N * Cp, 256), G), dim3(256), 0, st, params, slot, slot_stride, w_off, b_off, g_off, beta_off, N, C,
                                                                          Cp, Wf, wf_gs, Wd, wd_gs, w_f16, vec, vec_gs);
     VV_CKL();
     return 0;
@@ -957,20 +976,20 @@ static void layout_blocks(VvPrepAll &all) {
 }
 int vv_prep_conv_w_all(const float *params, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st) {
     layout_blocks(all);
-    k_prep_conv_w_all<<<dim3(all.total_blocks, 1, G), 256, 0, st>>>(params, slot, slot_stride, all);
+    vv_launch(k_prep_conv_w_all, dim3(all.total_blocks, 1, G), dim3(256), 0, st, params, slot, slot_stride, all);
     VV_CKL();
     return 0;
 }
 int vv_scatter_conv_wgrad_all(float *grads, const VvIntG &slot, long long slot_stride, VvPrepAll &all, int G, cudaStream_t st) {
     layout_blocks(all);
-    k_scatter_conv_wgrad_all<<<dim3(all.total_blocks, 1, G), 256, 0, st>>>(grads, slot, slot_stride, all);
+    vv_launch(k_scatter_conv_wgrad_all, dim3(all.total_blocks, 1, G), dim3(256), 0, st, grads, slot, slot_stride, all);
     VV_CKL();
     return 0;
 }
 
 int vv_prep_ct_w(const float *params, const VvIntG &slot, long long slot_stride, long long w_off, long long b_off, int Ci, int Co,
                  void *Wbf, long long wf_gs, void *Wbd, long long wd_gs, int w_f16, float *vec, long long vec_gs, int G, cudaStream_t st) {
-    k_prep_ct_w<<<dim3(vv_cdiv(16LL * Co * Ci, 256), G), 256, 0, st>>>(params, slot, slot_stride, w_off, b_off, Ci, Co, Wbf, wf_gs, Wbd,
+    vv_launch(k_prep_ct_w, dim3(vv_cdiv(16LL * Co * Ci, 256), G), dim3(256), 0, st, params, slot, slot_stride, w_off, b_off, Ci, Co, Wbf, wf_gs, Wbd,
                                                                      wd_gs, w_f16, vec, vec_gs);
     VV_CKL();
     return 0;
@@ -987,8 +1006,8 @@ int vv_bn_apply(const VvBnApply &p, int G, cudaStream_t st) {
     const int cap = (148 * 4) / G > 0 ? (148 * 4) / G : 1;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    if (p.y_f16) k_bn_apply<true><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
-    else k_bn_apply<false><<<dim3(gx, G), blk, 2 * p.C * sizeof(float), st>>>(p);
+    if (p.y_f16) vv_launch(k_bn_apply<true>, dim3(gx, G), dim3(blk), 2 * p.C * sizeof(float), st, p);
+    else vv_launch(k_bn_apply<false>, dim3(gx, G), dim3(blk), 2 * p.C * sizeof(float), st, p);
     VV_CKL();
     return 0;
 }
@@ -1006,12 +1025,12 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     VV_REQUIRE(p.z_f16 == p.dz_f16, "bn_bwd: Z and dZ are both fp16 (fp16 mode) or both fp32");
     if (p.dout) {
         const size_t smr = (5 * rows * p.C + 4 * rows) * sizeof(float);
-        if (p.z_f16) k_bn_bwd_reduce<true, true><<<dim3(gx, G), blk, smr, st>>>(p);
-        else k_bn_bwd_reduce<true, false><<<dim3(gx, G), blk, smr, st>>>(p);
+        if (p.z_f16) vv_launch(k_bn_bwd_reduce<true, true>, dim3(gx, G), dim3(blk), smr, st, p);
+        else vv_launch(k_bn_bwd_reduce<true, false>, dim3(gx, G), dim3(blk), smr, st, p);
     } else {
         const size_t smr = 2 * rows * p.C * sizeof(float);
-        if (p.z_f16) k_bn_bwd_reduce<false, true><<<dim3(gx, G), blk, smr, st>>>(p);
-        else k_bn_bwd_reduce<false, false><<<dim3(gx, G), blk, smr, st>>>(p);
+        if (p.z_f16) vv_launch(k_bn_bwd_reduce<false, true>, dim3(gx, G), dim3(blk), smr, st, p);
+        else vv_launch(k_bn_bwd_reduce<false, false>, dim3(gx, G), dim3(blk), smr, st, p);
     }
     VV_CKL();
     int gx2 = vv_cdiv(p.M, rows * 4);
@@ -1020,11 +1039,11 @@ int vv_bn_bwd(const VvBnBwd &p, int G, cudaStream_t st) {
     const dim3 grid(gx2, G);
     const size_t sm = 2 * p.C * sizeof(float);
     if (p.dout) {
-        if (p.dz_f16) k_bn_bwd_apply<true, true><<<grid, blk, sm, st>>>(p);
-        else k_bn_bwd_apply<true, false><<<grid, blk, sm, st>>>(p);
+        if (p.dz_f16) vv_launch(k_bn_bwd_apply<true, true>, dim3(grid), dim3(blk), sm, st, p);
+        else vv_launch(k_bn_bwd_apply<true, false>, dim3(grid), dim3(blk), sm, st, p);
     } else {
-        if (p.dz_f16) k_bn_bwd_apply<false, true><<<grid, blk, sm, st>>>(p);
-        else k_bn_bwd_apply<false, false><<<grid, blk, sm, st>>>(p);
+        if (p.dz_f16) vv_launch(k_bn_bwd_apply<false, true>, dim3(grid), dim3(blk), sm, st, p);
+        else vv_launch(k_bn_bwd_apply<false, false>, dim3(grid), dim3(blk), sm, st, p);
     }
     VV_CKL();
     return 0;
@@ -1035,8 +1054,8 @@ int vv_maxpool_bwd(const void *Y, int y_f16, long long y_gs, int ldy, int y_coff
     long long total = (long long)B * (H / 2) * (W / 2) * (C / 4);
     int gx = vv_cdiv(total, 256);
     if (gx > 148 * 16) gx = 148 * 16;
-    if (y_f16) k_maxpool_bwd<true><<<dim3(gx, G), 256, 0, st>>>(Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
-    else k_maxpool_bwd<false><<<dim3(gx, G), 256, 0, st>>>(Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
+    if (y_f16) vv_launch(k_maxpool_bwd<true>, dim3(gx, G), dim3(256), 0, st, Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
+    else vv_launch(k_maxpool_bwd<false>, dim3(gx, G), dim3(256), 0, st, Y, y_gs, ldy, y_coff, dP, dp_gs, dY, dy_gs, lddy, dy_coff, B, H, W, C);
     VV_CKL();
     return 0;
 }
@@ -1048,8 +1067,8 @@ int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M,
     int gx = vv_cdiv(M, rows * 16);
     if (gx > 148 * 2) gx = 148 * 2;
     if (gx < 1) gx = 1;
-    if (d_f16) k_colsum<true><<<dim3(gx, G), blk, rows * C * sizeof(float), st>>>(D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
-    else k_colsum<false><<<dim3(gx, G), blk, rows * C * sizeof(float), st>>>(D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
+    if (d_f16) vv_launch(k_colsum<true>, dim3(gx, G), dim3(blk), rows * C * sizeof(float), st, D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
+    else vv_launch(k_colsum<false>, dim3(gx, G), dim3(blk), rows * C * sizeof(float), st, D, d_gs, ld, coff, M, C, scale, grads, slot, slot_stride, off);
     VV_CKL();
     return 0;
 }
@@ -1063,8 +1082,8 @@ int vv_outconv_fwd(const VvOutFwd &p, int G, cudaStream_t st) {
         VV_CK(cudaFuncSetAttribute(k_outconv_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
         attr_set = true;
     }
-    if (p.u_f16) k_outconv_fwd<true><<<dim3(p.B, G), 256, smem, st>>>(p);
-    else k_outconv_fwd<false><<<dim3(p.B, G), 256, smem, st>>>(p);
+    if (p.u_f16) vv_launch(k_outconv_fwd<true>, dim3(p.B, G), dim3(256), smem, st, p);
+    else vv_launch(k_outconv_fwd<false>, dim3(p.B, G), dim3(256), smem, st, p);
     VV_CKL();
     return 0;
 }
@@ -1075,8 +1094,8 @@ int vv_outconv_bwd(const VvOutBwd &p, int G, cudaStream_t st) {
     int gx = vv_cdiv(p.M, npix * 8);
     if (gx > 148 * 8) gx = 148 * 8;
     if (gx < 1) gx = 1;
-    if (p.u_f16) k_outconv_bwd<true><<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
-    else k_outconv_bwd<false><<<dim3(gx, G), 256, (3 * p.F + 4) * sizeof(float), st>>>(p);
+    if (p.u_f16) vv_launch(k_outconv_bwd<true>, dim3(gx, G), dim3(256), (3 * p.F + 4) * sizeof(float), st, p);
+    else vv_launch(k_outconv_bwd<false>, dim3(gx, G), dim3(256), (3 * p.F + 4) * sizeof(float), st, p);
     VV_CKL();
     return 0;
 }
@@ -1084,22 +1103,22 @@ int vv_outconv_bwd(const VvOutBwd &p, int G, cudaStream_t st) {
 int vv_scatter_conv_wgrad(const float *dWf, long long gs, int N, int C, int Cp, float *grads, const VvIntG &slot, long long slot_stride,
                           long long w_off, int G, cudaStream_t st) {
     if (N % 32 == 0 && Cp % 32 == 0)
-        k_scatter_conv_wgrad_tiled<<<dim3(N / 32, Cp / 32, G), 256, 0, st>>>(dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
+        vv_launch(k_scatter_conv_wgrad_tiled, dim3(N / 32, Cp / 32, G), dim3(256), 0, st, dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
     else
-        k_scatter_conv_wgrad<<<dim3(vv_cdiv(9LL * N * C, 256), G), 256, 0, st>>>(dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
+        vv_launch(k_scatter_conv_wgrad, dim3(vv_cdiv(9LL * N * C, 256), G), dim3(256), 0, st, dWf, gs, N, C, Cp, grads, slot, slot_stride, w_off);
     VV_CKL();
     return 0;
 }
 
 int vv_scatter_ct_wgrad(const float *dWb, long long gs, int Ci, int Co, float scale, float *grads, const VvIntG &slot, long long slot_stride,
                         long long w_off, int G, cudaStream_t st) {
-    k_scatter_ct_wgrad<<<dim3(vv_cdiv(9LL * Ci * Co, 256), G), 256, 0, st>>>(dWb, gs, Ci, Co, scale, grads, slot, slot_stride, w_off);
+    vv_launch(k_scatter_ct_wgrad, dim3(vv_cdiv(9LL * Ci * Co, 256), G), dim3(256), 0, st, dWb, gs, Ci, Co, scale, grads, slot, slot_stride, w_off);
     VV_CKL();
     return 0;
 }
 
 int vv_losses(const float *sse, int G, int B, const VvIntG &is_flow, float inv_raw, float inv_of, float *out, cudaStream_t st) {
-    k_losses<<<1, 256, 0, st>>>(sse, G, B, is_flow, inv_raw, inv_of, out);
+    vv_launch(k_losses, dim3(1), dim3(256), 0, st, sse, G, B, is_flow, inv_raw, inv_of, out);
     VV_CKL();
     return 0;
 }
@@ -1112,7 +1131,7 @@ extern "C" int vecvad_adam_step(float *params, const float *grads, float *exp_av
     double bc1 = 1.0 - pow((double)beta1, (double)step);
     double bc2 = 1.0 - pow((double)beta2, (double)step);
     long long nthr = (n + 3) / 4;
-    k_adam<<<vv_cdiv(nthr, 256), 256, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
+    vv_launch(k_adam, dim3(vv_cdiv(nthr, 256)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
                                                                (float)bc1, (float)sqrt(bc2), grad_scale);
     VV_CKL();
     return 0;
@@ -1125,13 +1144,14 @@ extern "C" int vecvad_cubes_to_tensors(const uint8_t *raw, const float *flow, fl
     long long total = (long long)n * patch * patch * (3 * t_raw + (flow ? 2 * t_of : 0));
     int gx = vv_cdiv(total, 256);
     if (gx > 148 * 16) gx = 148 * 16;
-    k_cubes_to_tensors<<<gx, 256, 0, (cudaStream_t)stream>>>(raw, flow, x, x_of, n, t_raw, t_of, patch);
+    vv_launch(k_cubes_to_tensors, dim3(gx), dim3(256), 0, (cudaStream_t)stream, raw, flow, x, x_of, n, t_raw, t_of, patch);
     VV_CKL();
     return 0;
 }
 
 namespace {
 __global__ void k_f32_to_f16(const float *__restrict__ src, int ld, int cols, long long rows, __half *__restrict__ dst) {
+    vv_pdl_wait();
     const int cq = cols >> 2;
     const long long total = rows * cq;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -1145,6 +1165,7 @@ __global__ void k_f32_to_f16(const float *__restrict__ src, int ld, int cols, lo
 
 namespace {
 __global__ void k_f16_to_f32(const __half *__restrict__ src, long long n, float *__restrict__ dst) {
+    vv_pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = __half2float(src[i]);
 }
 }  // namespace
@@ -1153,7 +1174,7 @@ int vv_f16_to_f32(const void *src, long long n, float *dst, cudaStream_t st) {
     int gx = vv_cdiv(n, 256);
     if (gx > 148 * 16) gx = 148 * 16;
     if (gx < 1) gx = 1;
-    k_f16_to_f32<<<gx, 256, 0, st>>>((const __half *)src, n, dst);
+    vv_launch(k_f16_to_f32, dim3(gx), dim3(256), 0, st, (const __half *)src, n, dst);
     VV_CKL();
     return 0;
 }
@@ -1164,7 +1185,7 @@ int vv_f32_to_f16(const float *src, int ld, int cols, long long rows, void *dst,
     int gx = vv_cdiv(total, 256);
     if (gx > 148 * 16) gx = 148 * 16;
     if (gx < 1) gx = 1;
-    k_f32_to_f16<<<gx, 256, 0, st>>>(src, ld, cols, rows, (__half *)dst);
+    vv_launch(k_f32_to_f16, dim3(gx), dim3(256), 0, st, src, ld, cols, rows, (__half *)dst);
     VV_CKL();
     return 0;
 }

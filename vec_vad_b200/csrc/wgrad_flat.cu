@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_flat(const __grid_constant__ C
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    vv_pdl_wait();                                           // set-up above overlaps the previous kernel's tail; global memory from here on
 
     if (ntiles > 0) {
         if (warp == 0 && lane == 0) {
@@ -286,8 +287,8 @@ int vv_launch_wgrad_flat(const VvWGrad &p, cudaStream_t st) {
         VV_CK(cudaFuncSetAttribute(k_wgrad_flat<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WGF_SMEM_MAX));
         attr = true;
     }
-    if (p.ab_f16) k_wgrad_flat<true><<<grid, 128, smem, st>>>(tmA, tmG, wp);
-    else k_wgrad_flat<false><<<grid, 128, smem, st>>>(tmA, tmG, wp);
+    if (p.ab_f16) vv_launch(k_wgrad_flat<true>, dim3(grid), dim3(128), smem, st, tmA, tmG, wp);
+    else vv_launch(k_wgrad_flat<false>, dim3(grid), dim3(128), smem, st, tmA, tmG, wp);
     VV_CKL();
     if (wp.trace) {      // debugging aid: synchronous
         unsigned long long h[5];

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_tc2(const __grid_constant__ CU
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    vv_pdl_wait();                                           // set-up above overlaps the previous kernel's tail; global memory from here on
 
     if (ntiles > 0) {
         if (warp == 0) {
@@ -211,7 +212,7 @@ int launch_wg2(const CUtensorMap &tmA, const CUtensorMap &tmG, const Wg2Params &
         VV_CK(cudaFuncSetAttribute(k_wgrad_tc2<NT, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG2_SMEM_MAX));
         attr = true;
     }
-    k_wgrad_tc2<NT, F16><<<grid, 128, smem, st>>>(tmA, tmG, wp);
+    vv_launch(k_wgrad_tc2<NT, F16>, dim3(grid), dim3(128), smem, st, tmA, tmG, wp);
     VV_CKL();
     return 0;
 }
