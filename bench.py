@@ -24,10 +24,12 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
 
-# DRAM traffic of the contraction kernel classes over ONE train step (batch 128, 5raw1of), from the ncu pass whose raw output is
-# committed as profiles/r01_v5_step_metrics.csv, tabulated in profiles/r01_v5_step.txt (dram__bytes_read.sum + dram__bytes_write.sum
-# summed over the class's launches: k_igemm_flat + k_igemm_tc3, k_wgrad_flat + k_wgrad_tc2)
-NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': (1.876e9 + 0.604e9, 33), 'wgrad_tcgen05': (1.924e9 + 0.002e9, 17)}
+# DRAM traffic of the contraction kernel classes over ONE train step (batch 128, 5raw1of): dram__bytes_read.sum + dram__bytes_write.sum
+# summed over the class's launches (k_igemm_flat + k_igemm_tc3, k_wgrad_flat + k_wgrad_tc2) in the per-launch ncu pass committed under
+# profiles/ (NCU_SOURCE; tabulated by profiles/step_table.py): {class: {operand type: (bytes per step, launches per step)}}
+NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': {'tf32': (1.876e9 + 0.604e9, 33), 'f16': (0.320e9 + 0.706e9, 33)},
+                           'wgrad_tcgen05': {'tf32': (1.924e9 + 0.002e9, 17), 'f16': (0.673e9 + 0.272e9, 17)}}
+NCU_SOURCE = 'profiles/r01_v5_step_metrics.csv (tf32), profiles/r02_f16_step_metrics.csv (f16)'
 
 METRIC = 'STCs/sec (train step, device-timed)'       # BASELINE.json's metric; both arms print the same string
 
@@ -85,7 +87,7 @@ class ClockSampler:
                 'samples': len(sm)}
 
 
-def cpu_reference_steps(net, batch, steps, warmup, threads):
+def cpu_reference_steps(net, batch, steps, warmup, threads, pool=1):
     """The reference algorithm (oracle port of model/unet.py + train.py:383-402) on the host cores. -> (STC/s, s/step)"""
     import torch
     from oracle import unet_oracle as orc
@@ -94,15 +96,23 @@ def cpu_reference_steps(net, batch, steps, warmup, threads):
     torch.manual_seed(0)
     m = orc.CompletionNetOracle(kind, **kw).train()
     opt = orc.make_adam(m)
-    raw_u8, flow = orc.synthetic_cubes(batch, t_of=t_of, seed=1234)
-    x, x_of = orc.cubes_to_tensors(raw_u8, flow)
-    for _ in range(warmup):
-        orc.train_step(m, opt, x, x_of)
+    data = []
+    for i in range(max(1, pool)):
+        raw_u8, flow = orc.synthetic_cubes(batch, t_of=t_of, seed=1234 + i)
+        data.append(orc.cubes_to_tensors(raw_u8, flow))
+    for i in range(warmup):
+        orc.train_step(m, opt, *data[i % len(data)])
     t0 = time.perf_counter()
-    for _ in range(steps):
-        orc.train_step(m, opt, x, x_of)
+    for i in range(steps):
+        orc.train_step(m, opt, *data[(warmup + i) % len(data)])
     dt = (time.perf_counter() - t0) / steps
     return batch / dt, dt
+
+
+def config_of(net, batch, world, pool):
+    """The workload description both arms print: identical key for key (the driver compares them)."""
+    return {'workload': WORKLOAD[net], 'net': net, 'batch_per_gpu': batch, 'global_batch': world * batch, 'input_pool_batches': pool,
+            'l2': 'per-step working set (activations + gradients, >3 GB at batch 128) exceeds the 126 MB L2; inputs rotate over %d batches' % pool}
 
 
 def run_reference(args):
@@ -111,19 +121,20 @@ def run_reference(args):
         return
     threads = os.cpu_count() or 1
     batch = args.batch
-    v, dt = cpu_reference_steps(args.net, batch, args.steps, args.warmup, threads)
+    v, dt = cpu_reference_steps(args.net, batch, args.steps, args.warmup, threads, args.pool)
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'STC/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': batch, 'global_batch': batch,
-                       'timing': 'host wall clock on rank 0 only (the CPU arm has no device): each step is one batch of the same workload'},
+            'config': config_of(args.net, batch, 1, args.pool),
+            'details': {'timing': 'host wall clock on rank 0 only (the CPU arm has no device): each step is one batch of the same workload'},
             'cpu_baseline': {'value': v, 'unit': 'STC/s', 'cores': threads, 'kind': 'port',
                              'sample': '%d train steps of batch %d (oracle port of model/unet.py + train.py:383-402, torch CPU fp32)' % (args.steps, batch)},
             'e2e': {'value': v, 'unit': 'STC/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line))
 
 
-def run_ours(args):
+def measure_net(args, net, steps, warmup, with_e2e, sample_clocks):
+    """Device-timed (and optionally end-to-end) train steps of one UNet set on this rank's GPU.  Collective when WORLD_SIZE > 1."""
     import torch
     import torch.distributed as dist
     from vec_vad_b200 import _lib, unet as vu, vad_datasets as vd
@@ -131,11 +142,8 @@ def run_ours(args):
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
-    kind, kw, t_of = NET_KW[args.net]
+    kind, kw, t_of = NET_KW[net]
     cls = {'net4': vu.SelfCompleteNet4, 'full': vu.SelfCompleteNetFull}[kind]
     torch.manual_seed(0)
     prec = 0 if args.simt else {'tf32': 1, 'f16': 2}[args.precision]
@@ -150,9 +158,11 @@ def run_ours(args):
     losses = torch.zeros(2, device=dev)
     reduce = None
     if world > 1:
-        def reduce(flat):
-            dist.all_reduce(flat)          # NCCL sum over NVLink/NVSwitch on the current stream; Adam applies 1/world
-            return 1.0 / world
+        # NCCL sum over NVLink/NVSwitch, 1/world folded into Adam.  overlap: each gradient phase (decoder / deepest encoder block /
+        # rest) is exchanged on a side stream as soon as the backward has produced it; --no-overlap: one all-reduce of the flat
+        # buffer after the backward
+        from vec_vad_b200 import ddp
+        reduce = ddp.GradReducer(overlap=not args.no_overlap)
 
     def step_dev(i):
         x, x_of = vd.cubes_to_device_tensors(dev_raw[i % P], dev_flow[i % P])
@@ -188,15 +198,15 @@ def run_ours(args):
         return ms / steps, (_lib.lib().vecvad_launch_count() - n0) // steps
 
     clk = ClockSampler(local)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         clk.start()
-    ms_dev, launches = timed(step_dev, args.steps, args.warmup)
-    clocks = clk.stop() if rank == 0 else None
-    ms_e2e, _ = timed(step_e2e, args.steps, max(3, args.warmup // 2))
+    ms_dev, launches = timed(step_dev, steps, warmup)
+    clocks = clk.stop() if (rank == 0 and sample_clocks) else None
+    ms_e2e = timed(step_e2e, steps, max(3, warmup // 2))[0] if with_e2e else None
     final_loss = losses.cpu().tolist()
     # ---- per-kernel-class breakdown (separate, untimed pass; CUDA events on the launch stream around every launch)
     prof = None
-    psteps = min(5, args.steps)
+    psteps = min(5, steps)
     if rank == 0:
         _lib.profile_begin()
     for i in range(psteps):            # every rank steps (the gradient all-reduce is collective); rank 0 records
@@ -204,38 +214,108 @@ def run_ours(args):
     if rank == 0:
         prof = {k: (ms / psteps, fl / psteps, la // psteps) for k, (ms, fl, la) in _lib.profile_end().items()}
     barrier()
+    out = dict(ms_dev=ms_dev, launches=int(launches), ms_e2e=ms_e2e, final_loss=final_loss, prof=prof, clocks=clocks,
+               h2d=int(host_raw[0].numel() + 4 * host_flow[0].numel()), world=world, batch=B)
+    del model
+    torch.cuda.empty_cache()
+    return out
+
+
+def operand_peak(args, pk):
+    """Tensor-pipe peak of the operand type the tiles run in: fp16 operands run at the bf16 rate (MEASURED_PEAKS.json, sustained);
+    tf32 at the tf32 cuBLAS rate measured the same way on this pool's B200 (profiles/r02_tf32_peak.json, scratch/measure_tf32_peak.py)."""
+    peak16 = pk['bf16_tflops_sustained'] if 'bf16_tflops_sustained' in pk else pk['bf16_tflops']
+    if args.simt or args.precision == 'f16':
+        return peak16, peak16, 'bf16/fp16 rate'
+    tf = os.path.join(REPO, 'profiles', 'r02_tf32_peak.json')
+    tf32 = json.load(open(tf))['tf32_tflops_sustained'] if os.path.exists(tf) else peak16 / 2
+    return peak16, tf32, 'tf32 rate measured with cuBLAS (profiles/r02_tf32_peak.json)'
+
+
+def roofline_of(args, net, m, pk, src):
+    prof = m['prof']
+    world, B = m['world'], m['batch']
+    value = world * B / (m['ms_dev'] * 1e-3)
+    step_tf = value * FLOPS_PER_STC[net] / 1e12 / world           # per-GPU rate of the step's contractions over the WHOLE step
+    peak16, peak_op, peak_how = operand_peak(args, pk)
+    dom = max((k for k in prof if prof[k][1] > 0), key=lambda k: prof[k][0])
+    dom_ms, dom_fl, dom_n = prof[dom]
+    dom_tf = dom_fl / (dom_ms * 1e-3) / 1e12
+    traffic = None
+    if dom in NCU_DRAM_BYTES_PER_STEP and net == 'net4' and B == 128 and not args.simt and args.precision in NCU_DRAM_BYTES_PER_STEP[dom]:
+        tot, n = NCU_DRAM_BYTES_PER_STEP[dom][args.precision]
+        traffic = tot / n
+    return {'bound': 'tensor', 'kernel': dom, 'achieved': dom_tf, 'peak': peak16, 'unit': 'TFLOP/s', 'frac': dom_tf / peak16,
+            'traffic': traffic, 'traffic_note': 'mean DRAM bytes per launch of this kernel class (ncu, %s)' % NCU_SOURCE,
+            'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / m['ms_dev'],
+            'peak_of_operand_type': peak_op, 'frac_of_operand_type_peak': dom_tf / peak_op, 'operand_peak_is': peak_how,
+            'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak16,
+            'note': 'achieved = ALGORITHMIC conv FLOPs of the dominant kernel class (transposed convs counted at their 9 taps) / its '
+                    'CUDA-event time (sum over its launches in one step, measured live in a separate pass); peak = %s sustained bf16 '
+                    'cuBLAS (%s); the weight-gradient tiles run concurrently on a side stream, so class times overlap and include '
+                    'their mutual contention' % (src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md fallback')}
+
+
+def flow_secondary(pk):
+    """BASELINE.json configs[4] (FlowNet2 correlation + warp, 1024x436 pairs) beside the headline: bench_flow.py's rows, HBM roofline."""
+    import bench_flow
+    rows = []
+    for batch in (1, 8):
+        for r in bench_flow.run(batch, 10, with_reference=False):
+            rows.append({'workload': 'FlowNet2 %s, 1024x436 synthetic pairs, batch %d (BASELINE.json configs[4])' % (r['op'], batch),
+                         'metric': 'pairs/sec', 'value': r['pairs_per_s'], 'unit': 'pairs/s', 'us_per_launch': r['us'],
+                         'roofline': {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                                      'frac': r['frac_of_hbm_peak'], 'traffic': None, 'algorithmic_bytes': r['algorithmic_bytes'],
+                                      'tflops_fp32': r.get('tflops_fp32')}})
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    m = measure_net(args, args.net, args.steps, args.warmup, with_e2e=True, sample_clocks=True)
+    B, P = args.batch, args.pool
     if rank == 0:
         pk, src = peaks()
-        value = world * B / (ms_dev * 1e-3)
-        step_tf = value * FLOPS_PER_STC[args.net] / 1e12 / world      # per-GPU rate of the step's contractions over the WHOLE step
-        peak = pk['bf16_tflops_sustained'] if 'bf16_tflops_sustained' in pk else pk['bf16_tflops']
-        dom = max((k for k in prof if prof[k][1] > 0), key=lambda k: prof[k][0])
-        dom_ms, dom_fl, dom_n = prof[dom]
-        dom_tf = dom_fl / (dom_ms * 1e-3) / 1e12
-        tf32 = not args.simt
+        value = world * B / (m['ms_dev'] * 1e-3)
         line = {'metric': METRIC, 'value': value, 'unit': 'STC/s', 'n_gpus': world, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-                'dtype': (args.precision if tf32 else 'f32'), 'data': 'synthetic',
-                'config': {'workload': WORKLOAD[args.net], 'net': args.net, 'batch_per_gpu': B, 'global_batch': world * B,
-                           'parallelism': 'dp%d' % world, 'input_pool_batches': P,
-                           'l2': 'per-step working set (activations + gradients, >3 GB at batch 128) exceeds the 126 MB L2; inputs rotate over %d batches' % P,
-                           'final_losses': final_loss},
-                'clocks': clocks, 'gpu_launches': int(launches),
-                'e2e': {'value': world * B / (ms_e2e * 1e-3), 'unit': 'STC/s', 'ms_per_step': ms_e2e,
-                        'h2d_bytes_per_step': int(host_raw[0].numel() + 4 * host_flow[0].numel()), 'd2h_bytes_per_step': 8},
-                'roofline': {'bound': 'tensor', 'kernel': dom, 'achieved': dom_tf, 'peak': peak, 'unit': 'TFLOP/s', 'frac': dom_tf / peak,
-                             'traffic': (NCU_DRAM_BYTES_PER_STEP[dom][0] / NCU_DRAM_BYTES_PER_STEP[dom][1]
-                                         if (dom in NCU_DRAM_BYTES_PER_STEP and args.net == 'net4' and B == 128) else None),
-                             'traffic_note': 'mean DRAM bytes per launch of this kernel class (ncu, profiles/r01_v5_step_metrics.csv)',
-                             'launches_per_step': int(dom_n), 'ms_per_step': dom_ms, 'share_of_step': dom_ms / ms_dev,
-                             'peak_tf32': peak / 2 if tf32 else None, 'frac_of_tf32_peak': dom_tf / (peak / 2) if tf32 else None,
-                             'whole_step_tflops': step_tf, 'whole_step_frac': step_tf / peak,
-                             'note': 'achieved = algorithmic conv FLOPs of the dominant kernel class / its CUDA-event time (sum over its '
-                                     'launches in one step, measured live in a separate pass); peak = %s sustained bf16 cuBLAS (%s); the '
-                                     'tiles are kind::tf32 whose hardware rate is half the bf16 rate (peak_tf32); the weight-gradient tiles run '
-                                     'concurrently on a side stream, so class times overlap and include their mutual contention'
-                                     % (src, 'MEASURED_PEAKS.json' if src == 'measured' else 'B200_PROFILING.md fallback')},
-                'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in prof.items() if v[2] > 0}}
+                'warmup': args.warmup, 'ms_per_step': m['ms_dev'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': ('f32' if args.simt else args.precision), 'data': 'synthetic',
+                'config': config_of(args.net, B, world, P),
+                'details': {'parallelism': 'dp%d' % world,
+                            'grad_exchange': ('none' if world == 1 else 'one all-reduce after backward' if args.no_overlap
+                                              else 'three gradient phases exchanged while the backward runs'),
+                            'operands': ('fp32 SIMT' if args.simt else 'tcgen05 kind::%s operands, fp32 accumulation; BatchNorm, losses, 1x1 output '
+                                         'conv and Adam in fp32' % args.precision),
+                            'final_losses': m['final_loss']},
+                'clocks': m['clocks'], 'gpu_launches': m['launches'],
+                'e2e': {'value': world * B / (m['ms_e2e'] * 1e-3), 'unit': 'STC/s', 'ms_per_step': m['ms_e2e'],
+                        'h2d_bytes_per_step': m['h2d'], 'd2h_bytes_per_step': 8},
+                'roofline': roofline_of(args, args.net, m, pk, src),
+                'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in m['prof'].items() if v[2] > 0}}
+    # ---- secondary workloads (BASELINE.json configs[2] and configs[4]) so the driver's record carries them; 1 GPU only
+    if world == 1 and not args.no_secondary:
+        sec = []
+        if args.net != 'full':
+            m2 = measure_net(args, 'full', min(args.steps, 20), 5, with_e2e=False, sample_clocks=False)
+            sec.append({'workload': WORKLOAD['full'] + ', batch %d per GPU (BASELINE.json configs[2] is 2 x this)' % B, 'metric': METRIC,
+                        'value': B / (m2['ms_dev'] * 1e-3), 'unit': 'STC/s', 'ms_per_step': m2['ms_dev'], 'gpu_launches': m2['launches'],
+                        'roofline': roofline_of(args, 'full', m2, pk, src),
+                        'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in m2['prof'].items() if v[2] > 0}})
+        try:
+            sec += flow_secondary(pk)
+        except Exception as e:                                  # the headline line must still print
+            sec.append({'workload': 'FlowNet2 ops', 'error': repr(e)})
+        line['secondary'] = sec
+    if rank == 0:
         if world == 1 and not args.no_cpu:
             threads = os.cpu_count() or 1
             v, dt = cpu_reference_steps(args.net, B, 4, 1, threads)
@@ -258,6 +338,8 @@ def main():
     ap.add_argument('--simt', action='store_true', help='fp32 SIMT tiles instead of tcgen05 tiles')
     ap.add_argument('--precision', default='f16', choices=['tf32', 'f16'], help='operand type of the tcgen05 tiles (fp32 accumulation either way)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the secondary workloads (5raw5of set, FlowNet2 ops)')
+    ap.add_argument('--no-overlap', action='store_true', help='N>1: one all-reduce after the backward instead of the phased, overlapped exchange')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -14,23 +14,20 @@ REPO = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, REPO)
 
 
-def main():
+def run(batch, iters, with_reference=True, device=0):
+    """-> one dict per op (ours, then the recompiled reference kernels when oracle/_ref is present and with_reference)."""
     import torch
     from vec_vad_b200 import flow_ops as ops
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--batch', type=int, default=1)
-    ap.add_argument('--iters', type=int, default=20)
-    a = ap.parse_args()
     pk = json.load(open(os.path.join(REPO, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(REPO, 'MEASURED_PEAKS.json')) else {'hbm_gbs': 6650.0}
-    dev = torch.device('cuda', 0)
+    dev = torch.device('cuda', device)
     g = torch.Generator().manual_seed(0)
-    B = a.batch
+    B = batch
     f1 = torch.randn(B, 256, 55, 128, generator=g).to(dev)
     f2 = torch.randn(B, 256, 55, 128, generator=g).to(dev)
     img0 = torch.rand(B, 3, 436, 1024, generator=g).to(dev)
     img1 = torch.rand(B, 3, 436, 1024, generator=g).to(dev)
     flow = (torch.randn(B, 2, 436, 1024, generator=g) * 4).to(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device=dev)          # > 126 MB L2
     corr = ops.Correlation(20, 1, 20, 1, 2, 1)
     warp = ops.Resample2d()
 
@@ -38,7 +35,9 @@ def main():
         for _ in range(3):
             fn()
         ts = []
-        for _ in range(a.iters):
+        for _ in range(iters):
+            # the 512 MiB memset flushes L2 AND keeps the GPU busy (~150 us) while the host queues the events and the op behind it,
+            # so the interval between the events is device time of the op, not host launch latency
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -55,11 +54,13 @@ def main():
     ]
     # the stated bar of SURVEY.md section 2.2: the reference's own kernels, recompiled unmodified for sm_100a (oracle/_ref,
     # test infrastructure -- timed here as the baseline beside ours, never part of the product path)
-    try:
-        from oracle import ref_ops
-        have_ref = ref_ops.available()
-    except ImportError:
-        have_ref = False
+    have_ref = False
+    if with_reference:
+        try:
+            from oracle import ref_ops
+            have_ref = ref_ops.available()
+        except ImportError:
+            have_ref = False
     if have_ref:
         scratch = torch.empty(ref_ops.lib().ref_correlation_scratch_floats(B, 256, 55, 128, 20), device=dev)
         rows += [
@@ -68,12 +69,24 @@ def main():
             ('reference_warp_diff_norm_chain', lambda: ref_ops.channelnorm_forward((img0 - ref_ops.resample2d_forward(img1, flow)).contiguous()),
              rows[2][2], 0.0),
         ]
+    out = []
     for name, fn, nbytes, flops in rows:
         t = timed(fn)
         line = {'op': name, 'batch': B, 'us': t * 1e6, 'pairs_per_s': B / t, 'algorithmic_bytes': nbytes, 'achieved_gbs': nbytes / t / 1e9,
-                'hbm_peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': nbytes / t / 1e9 / pk['hbm_gbs'], 'l2': 'flushed (256 MiB memset) before every timed launch'}
+                'hbm_peak_gbs': pk['hbm_gbs'], 'frac_of_hbm_peak': nbytes / t / 1e9 / pk['hbm_gbs'], 'l2': 'flushed (512 MiB memset) before every timed launch'}
         if flops:
             line['tflops_fp32'] = flops / t / 1e12
+        out.append(line)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--batch', type=int, default=1)
+    ap.add_argument('--iters', type=int, default=20)
+    ap.add_argument('--no-reference', action='store_true', help='skip the recompiled reference kernels (oracle/_ref)')
+    a = ap.parse_args()
+    for line in run(a.batch, a.iters, with_reference=not a.no_reference):
         print(json.dumps(line))
 
 

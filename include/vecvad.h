@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 4
+#define VECVAD_ABI_VERSION 5
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -169,6 +169,16 @@ int vecvad_net_forward(vecvad_net *net, const float *x, const float *x_of, int x
  * NULL to use the fused MSE gradient staged by vecvad_net_forward(..., sse != NULL).
  * Writes (overwrites) every gradient of the executed UNets into the bound `grads` buffer. */
 int vecvad_net_backward(vecvad_net *net, const float *grad_raw_out, const float *grad_of_out, vecvad_stream stream);
+
+/* Gradient phases (overlapping the data-parallel gradient exchange with the backward; replaces the reduce-add onto GPU 0 that
+ * nn.DataParallel performs after the whole backward, train.py:375,399).  The parameter gradients of every slot become final
+ * in three contiguous ranges of the slot, in this order: phase 0 = the decoder (conv units 8..13, transposed convs, output conv),
+ * phase 1 = the deepest encoder block (units 6, 7), phase 2 = the rest.
+ * vecvad_net_grad_phase_ranges: [begin[p], end[p]) in floats relative to the start of a slot (same for every slot).
+ * vecvad_net_grad_phase_wait:   makes `stream` wait (cudaStreamWaitEvent) until phase p of the LAST vecvad_net_backward call is
+ *                               complete; call it after vecvad_net_backward returned (the backward itself is asynchronous). */
+int vecvad_net_grad_phase_ranges(const vecvad_net *net, int64_t *begin, int64_t *end);
+int vecvad_net_grad_phase_wait(vecvad_net *net, int phase, vecvad_stream stream);
 
 /* fp16-operand mode only: the power-of-two loss scale the backward applies to the dZ operands it stores as fp16 (and removes again
  * from every parameter gradient it writes).  scale <= 0 (default): derived per step from the MSE-gradient coefficients of the last

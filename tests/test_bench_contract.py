@@ -25,6 +25,7 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d['impl'] == 'reference' and d['metric'] == bench.METRIC and d['unit'] == 'STC/s' and d['higher_is_better'] is True
     assert d['value'] > 0 and d['ms_per_step'] > 0 and d['steps'] == 1 and d['n_gpus'] == 1
     assert d['config']['workload'] == bench.WORKLOAD['net4'] and d['config']['batch_per_gpu'] == 4
+    assert d['config'] == bench.config_of('net4', 4, 1, 8)          # key for key what the GPU arm prints at N = 1 (bench.run_ours)
     cb = d['cpu_baseline']
     assert cb['kind'] == 'port' and cb['cores'] >= 1 and cb['value'] == d['value'] and 'sample' in cb
     assert d['e2e'] == {'value': d['value'], 'unit': 'STC/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}

@@ -167,3 +167,62 @@ def test_ragged_global_batches_weighted_gradient_equals_global_batch_gradient():
         (mse(raw_t, raw_o) + mse(of_t, of_o)).backward()
         want = torch.cat([p.grad.reshape(-1) for p in m.parameters()]).numpy()
         np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-7)
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# overlapped (phased) gradient exchange: GradReducer.reduce_phased against the plain whole-buffer sum
+class _PhasedStandIn:
+    """What reduce_phased needs from CompletionNet (unet.py grad_phase_views / wait_grad_phase), on a CPU buffer: 3 slots of 40
+    floats, phases = [24, 40), [16, 24), [0, 16) of every slot."""
+    def __init__(self, flat):
+        self.flat_grads = flat
+        self.waited = []
+
+    def grad_phase_views(self):
+        rng = [(24, 40), (16, 24), (0, 16)]
+        return [[self.flat_grads[s * 40 + b:s * 40 + e] for s in range(3)] for (b, e) in rng]
+
+    def wait_grad_phase(self, phase, stream=None):
+        self.waited.append(phase)
+
+
+def _worker_phased(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    ddp.init_from_env('gloo')
+    g = torch.Generator().manual_seed(7 + rank)
+    flat = torch.randn(120, generator=g)
+    want = flat.clone()
+    dist.all_reduce(want)
+    out = {}
+    for tag, local_n, global_n in (('even', 4, 8), ('ragged', 3 if rank == 0 else 2, 5)):
+        red = ddp.GradReducer(overlap=True)
+        red.set_batch(local_n, global_n)
+        m = _PhasedStandIn(flat.clone())
+        scale = red.reduce_phased(m)
+        ref = flat.clone()
+        scale_ref = ddp.GradReducer(overlap=False)
+        scale_ref.set_batch(local_n, global_n)
+        s2 = scale_ref(ref)
+        out[tag] = (torch.equal(m.flat_grads, ref), scale, s2, m.waited)
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_phased_reduction_equals_whole_buffer_reduction():
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_phased, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for tag in ('even', 'ragged'):
+        same, scale, scale_ref, waited = out[tag]
+        assert same, tag
+        assert scale == scale_ref
+        assert waited == [0, 1, 2]

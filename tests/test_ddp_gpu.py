@@ -1,0 +1,84 @@
+"""Overlapped (phased) gradient exchange on real GPUs: two NCCL ranks that are fed the SAME cubes must end a train step with
+exactly twice the single-process gradient in every parameter (sum all-reduce) -- a phase that was exchanged too early, too late or
+not at all shows up as a factor-of-two error in its range.  Skipped below two visible GPUs (the driver's 1-GPU tier); run with
+``gpurun --gpus 2 -- python -m pytest tests/test_ddp_gpu.py -m gpu``."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+KW = dict(features_root=32, tot_raw_num=5, tot_of_num=1, border_mode='predict', rawRange=None, useFlow=True, padding=False)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _one_step(prec, reducer, steps=2):
+    from vec_vad_b200 import unet as vu
+    torch.manual_seed(3)
+    m = vu.SelfCompleteNet4(use_tensor_cores=prec, **KW).cuda().train()
+    m.init_adam()
+    g = torch.Generator().manual_seed(11)
+    x = torch.rand(16, 15, 32, 32, generator=g).cuda()
+    x_of = torch.randn(16, 2, 32, 32, generator=g).cuda()
+    grads = []
+    for _ in range(steps):
+        m.train_step(x, x_of, reduce_grads=reducer)
+        torch.cuda.synchronize()
+        grads.append(m.flat_grads.clone())
+    return grads, m.flat_params.clone()
+
+
+def _worker(rank, world, port, prec, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    import torch.distributed as dist
+    from vec_vad_b200 import ddp
+    ddp.init_from_env('nccl')
+    out = {}
+    for overlap in (True, False):
+        red = ddp.GradReducer(overlap=overlap)
+        grads, params = _one_step(prec, red)
+        out[overlap] = ([g.cpu() for g in grads], params.cpu())
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs')
+@pytest.mark.parametrize('prec', [2, 0])
+def test_phased_exchange_sums_every_gradient_once(prec):
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, prec, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=600)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    single, params1 = _one_step(prec, None)
+    for overlap in (True, False):
+        grads, params = out[overlap]
+        for step, (g2, g1) in enumerate(zip(grads, single)):
+            g1 = g1.cpu()
+            # both ranks computed the same gradient up to the order of fp32 atomics: the sum is 2 g
+            err = (g2 - 2 * g1).norm() / (2 * g1).norm()
+            assert err < 1e-4, (overlap, step, float(err))
+            # and no range was left un-summed: compare range by range (a stale range would sit at relative error 0.5)
+            for lo in range(0, g1.numel(), 65536):
+                a, b = g2[lo:lo + 65536], 2 * g1[lo:lo + 65536]
+                if float(b.norm()) > 0:
+                    assert float((a - b).norm() / b.norm()) < 5e-2, (overlap, step, lo)
+        # Adam with grad_scale 1/2 on the summed gradient == the single-process update
+        assert float((params - params1.cpu()).abs().max()) < 2e-3

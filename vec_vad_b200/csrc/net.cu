@@ -76,6 +76,10 @@ struct vecvad_net {
     cudaStream_t wg_stream;
     cudaEvent_t ev[VV_NEV];
     int ev_next, use_side;
+    // gradient phases (vecvad_net_grad_phase_*): the parameter gradients of a slot become final in three contiguous ranges, in
+    // this order: [unit 8, end) after the decoder, [unit 6, unit 8) after the deepest encoder block, [0, unit 6) at the end
+    cudaEvent_t ev_phase[3];
+    int have_phase_ev, phases_recorded;
 };
 
 namespace {
@@ -284,12 +288,18 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
                 if (cudaEventCreateWithFlags(&n->ev[i], cudaEventDisableTiming) != cudaSuccess) n->use_side = 0;
         }
     }
+    n->have_phase_ev = 1;
+    for (int i = 0; i < 3; i++)
+        if (cudaEventCreateWithFlags(&n->ev_phase[i], cudaEventDisableTiming) != cudaSuccess) { n->have_phase_ev = 0; break; }
+    n->phases_recorded = 0;
     *out = n;
     return 0;
 }
 
 extern "C" void vecvad_net_destroy(vecvad_net *net) {
     if (!net) return;
+    if (net->have_phase_ev)
+        for (int i = 0; i < 3; i++) cudaEventDestroy(net->ev_phase[i]);
     if (net->use_side) {
         cudaStreamSynchronize(net->wg_stream);
         for (int i = 0; i < VV_NEV; i++) cudaEventDestroy(net->ev[i]);
@@ -539,7 +549,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
     cudaStream_t sB = n->use_side ? n->wg_stream : st;
     constexpr int NPEND = 6;
     const void *pend_ptr[NPEND] = {n->GA, n->GB, n->HZ[0], n->HZ[1], n->HZ[2], n->HZ[3]};
-    cudaEvent_t pend[NPEND] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}, last_wg = nullptr;
+    cudaEvent_t pend[NPEND] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     n->ev_next = 0;
     auto next_ev = [&]() { return n->ev[(n->ev_next++) % VV_NEV]; };
     auto pend_slot = [&](const void *ptr) -> int {
@@ -568,7 +578,6 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         VV_CK(cudaEventRecord(e, sB));
         const int i = pend_slot(reads);
         if (i >= 0) pend[i] = e;
-        last_wg = e;
         return 0;
     };
     int hz_next = 0;
@@ -671,6 +680,37 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         return run_igemm(c.use_tensor_cores != 0, p, st, 0, igemm_flops(B, Hi, Hi, Co, Ci, 9, G));
     };
 
+    // conv weight gradients of units [u0, u1) back to PyTorch's layout (one launch) on stream s
+    auto scatter_units = [&](int u0, int u1, cudaStream_t s) -> int {
+        VvPrepAll all;
+        memset(&all, 0, sizeof(all));
+        all.n = u1 - u0;
+        all.scale = inv_LS;
+        for (int u = u0; u < u1; u++) {
+            VvPrepUnit &pu = all.u[u - u0];
+            pu.w_off = c.conv_w[u]; pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
+            pu.dWf = n->dWf[u]; pu.wf_gs = 9LL * n->uN[u] * n->uCp[u];
+        }
+        return vv_scatter_conv_wgrad_all(n->grads, n->slot, c.slot_param_stride, all, G, s);
+    };
+    // gradient phase ph is final once everything issued so far on BOTH streams has run: the side stream (which carries the weight
+    // gradients of the phase and their scatter) waits for the main stream's share (BatchNorm / bias / output-conv gradients)
+    // and records the phase event.  Nothing on the main stream waits for it.
+    n->phases_recorded = 0;
+    auto phase_done = [&](int ph, int u0, int u1) -> int {
+        int rr;
+        if (batched_scatter && (rr = scatter_units(u0, u1, sB))) return rr;
+        if (!n->have_phase_ev) return 0;
+        if (n->use_side) {
+            cudaEvent_t e = next_ev();
+            VV_CK(cudaEventRecord(e, st));
+            VV_CK(cudaStreamWaitEvent(sB, e, 0));
+        }
+        VV_CK(cudaEventRecord(n->ev_phase[ph], sB));
+        n->phases_recorded = ph + 1;
+        return 0;
+    };
+
     // ---- decoder, deepest last.  GA holds dU3 now (external gradients), or nothing (fused: formed from DOUT on the fly).
     void *ga = n->GA, *gb = n->GB;
     for (int k = 2; k >= 0; k--) {
@@ -684,8 +724,10 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         View ddeep = mk(ga, B, H / 2, C, 0, C);                  // d(X4 / U1 / U2): [B,(H/2)^2, C]
         if ((r = convT_bwd(k, ddeep))) return r;
     }
+    if ((r = phase_done(0, 8, NU))) return r;                  // decoder (units 8..13, transposed convs, output conv) complete
     // ---- encoder.  ga holds dX4.
     for (int k = 3; k >= 0; k--) {
+        if (k == 2 && (r = phase_done(1, 6, 8))) return r;     // deepest encoder block (units 6, 7) complete
         const int u2 = 2 * k + 1, u1 = 2 * k;
         const int H = n->uH[u1], N = n->uN[u2];
         View dy2;
@@ -712,19 +754,35 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
                 return r;
         }
     }
-    if (n->use_side && last_wg) VV_CK(cudaStreamWaitEvent(st, last_wg, 0));      // join: every weight gradient is complete
-    if (batched_scatter) {
-        VvPrepAll all;
-        memset(&all, 0, sizeof(all));
-        all.n = NU;
-        all.scale = inv_LS;
-        for (int u = 0; u < NU; u++) {
-            VvPrepUnit &pu = all.u[u];
-            pu.w_off = c.conv_w[u]; pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
-            pu.dWf = n->dWf[u]; pu.wf_gs = 9LL * n->uN[u] * n->uCp[u];
+    if ((r = phase_done(2, 0, 6))) return r;                   // the rest; its scatter runs on the side stream like the others
+    if (n->use_side) {                                         // join: every weight gradient and scatter is complete
+        if (n->have_phase_ev) VV_CK(cudaStreamWaitEvent(st, n->ev_phase[2], 0));
+        else {
+            cudaEvent_t e = next_ev();
+            VV_CK(cudaEventRecord(e, sB));
+            VV_CK(cudaStreamWaitEvent(st, e, 0));
         }
-        if ((r = vv_scatter_conv_wgrad_all(n->grads, n->slot, c.slot_param_stride, all, G, st))) return r;
     }
+    return 0;
+}
+
+extern "C" int vecvad_net_grad_phase_ranges(const vecvad_net *n, int64_t *begin, int64_t *end) {
+    VV_REQUIRE(n && begin && end, "grad_phase_ranges: null argument");
+    const vecvad_net_config &c = n->cfg;
+    begin[0] = c.conv_w[8]; end[0] = c.slot_param_stride;
+    begin[1] = c.conv_w[6]; end[1] = c.conv_w[8];
+    begin[2] = 0;           end[2] = c.conv_w[6];
+    // the phases rely on the slot layout of vec_vad_b200/unet.py slot_layout(): units in execution order, then the transposed
+    // convs, then the output conv
+    for (int u = 1; u < NU; u++) VV_REQUIRE(c.conv_w[u] > c.conv_w[u - 1], "grad_phase_ranges: conv units are not laid out in execution order");
+    VV_REQUIRE(c.up_w[0] > c.conv_w[NU - 1] && c.out_w > c.up_w[0], "grad_phase_ranges: transposed / output convs do not follow the conv units");
+    return 0;
+}
+
+extern "C" int vecvad_net_grad_phase_wait(vecvad_net *n, int phase, vecvad_stream stream) {
+    VV_REQUIRE(n && phase >= 0 && phase < 3, "grad_phase_wait: phase %d out of range", phase);
+    VV_REQUIRE(n->have_phase_ev && n->phases_recorded > phase, "grad_phase_wait: phase %d was not recorded by the last backward", phase);
+    VV_CK(cudaStreamWaitEvent((cudaStream_t)stream, n->ev_phase[phase], 0));
     return 0;
 }
 

@@ -8,6 +8,7 @@ global-batch gradient is the average of the rank gradients = sum-all-reduce foll
 ``grad_scale``, include/vecvad.h vecvad_adam_step).  Rank 0's running statistics are the ones saved (DataParallel keeps
 replica 0's).
 """
+import contextlib
 import os
 
 import torch
@@ -71,15 +72,30 @@ def init_from_env(backend=None):
     return rank, local, world
 
 
+def _all_reduce_views(views, group=None):
+    """Sum every tensor of ``views`` over the ranks, asynchronously on the current stream, in ONE coalesced collective where the
+    backend offers it (NCCL: one ncclGroupStart/End, one kernel) and one collective per view otherwise.  -> list of work handles."""
+    try:
+        from torch.distributed.distributed_c10d import _coalescing_manager
+        with _coalescing_manager(group=group, async_ops=True) as cm:
+            for v in views:
+                dist.all_reduce(v, group=group)
+        return [cm]
+    except (ImportError, RuntimeError, TypeError, AttributeError):
+        return [dist.all_reduce(v, group=group, async_op=True) for v in views]
+
+
 class GradReducer:
     """Callable handed to ``CompletionNet.train_step(reduce_grads=...)``: sums the flat gradient buffer over the ranks
     in place on the current stream and returns the scale Adam must apply (1/world)."""
 
-    def __init__(self, group=None, bucket_bytes=0):
+    def __init__(self, group=None, bucket_bytes=0, overlap=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = bucket_bytes // 4
         self.pre_weight = None
+        self.overlap = overlap
+        self._comm = None                 # side stream the phase exchanges are queued behind (created on first use)
 
     def set_batch(self, local_n, global_n):
         """Tell the reducer how this step's global batch was split.  The global-batch mean gradient is
@@ -95,6 +111,39 @@ class GradReducer:
             flat.mul_(pre)
         scale = 1.0 / self.world if pre is None else 1.0
         return self._sum(flat, scale)
+
+    def reduce_phased(self, model):
+        """Called by ``CompletionNet.train_step`` right after the (asynchronous) backward was queued: exchange every gradient
+        phase as soon as the backward has produced it, while the rest of the backward still runs.
+
+        ``model.grad_phase_views()`` gives, per phase, one contiguous view of the flat gradient buffer per UNet slot;
+        ``model.wait_grad_phase(p, stream)`` makes a stream wait for phase p.  Each phase's views are summed over the ranks in one
+        coalesced NCCL call queued behind a side stream that waits for the phase; the caller's stream finally waits for all
+        three.  Returns the scale Adam must apply, like ``__call__``.  Without overlap (``overlap=False``) or with one rank this
+        is ``__call__`` on the flat buffer."""
+        if self.world == 1:
+            return 1.0
+        if not self.overlap:
+            return self(model.flat_grads)
+        pre = self.pre_weight
+        on_gpu = model.flat_grads.is_cuda          # (the CPU / gloo tests drive the same code with a stand-in model)
+        if on_gpu:
+            cur = torch.cuda.current_stream()
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=model.flat_grads.device)
+        works = []
+        for ph, views in enumerate(model.grad_phase_views()):
+            with (torch.cuda.stream(self._comm) if on_gpu else contextlib.nullcontext()):
+                model.wait_grad_phase(ph, self._comm)
+                if pre is not None:
+                    for v in views:
+                        v.mul_(pre)
+                works.extend(_all_reduce_views(views, self.group))
+        for w in works:
+            w.wait()                       # NCCL: the caller's stream waits for the collective, the host does not block
+        if on_gpu:
+            cur.wait_stream(self._comm)
+        return 1.0 / self.world if pre is None else 1.0
 
     def _sum(self, flat, scale):
         if self.bucket_elems and flat.numel() > self.bucket_elems:

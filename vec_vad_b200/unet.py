@@ -188,6 +188,7 @@ class CompletionNet(nn.Module):
         # ---- flat buffers (CPU at construction like any nn.Module; moved by .cuda()/.to())
         self._pflat = torch.zeros(nslots * self._pstride)
         self._gflat = None
+        self._phase_views = None
         self._sflat = torch.zeros(nslots * self._sstride)
         self._nbt = torch.zeros(nslots * _lib.N_UNITS, dtype=torch.long)
         self._init_reference_order()          # seeded-init parity with the reference constructors
@@ -379,6 +380,7 @@ class CompletionNet(nn.Module):
         nbt = fn(self._nbt)
         self._nbt = nbt.long() if nbt.dtype != torch.long else nbt
         self._gflat = None
+        self._phase_views = None
         self._release_engine()
         self._rebind()
         return self
@@ -632,7 +634,12 @@ class CompletionNet(nn.Module):
         self._run_backward(None, None)
         scale = 1.0
         if reduce_grads is not None:
-            scale = float(reduce_grads(self._gflat))
+            # a reducer with ``reduce_phased`` exchanges each gradient phase as soon as the backward has produced it (the rest of
+            # the backward is still running); anything else gets the whole flat buffer once the backward is complete
+            if hasattr(reduce_grads, 'reduce_phased') and len(self._parts) == 1:
+                scale = float(reduce_grads.reduce_phased(self))
+            else:
+                scale = float(reduce_grads(self._gflat))
         a = self._adam
         a['step'] += 1
         _lib.check(L.vecvad_adam_step(_lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(a['m']), _lib.ptr(a['v']),
@@ -657,6 +664,24 @@ class CompletionNet(nn.Module):
                                                self._pflat.numel(), a['lr'], a['b1'], a['b2'], a['eps'], a['wd'], a['step'], scale,
                                                _lib.cur_stream()), 'adam_step')
         return torch.zeros(2, dtype=torch.float32, device=self._pflat.device)
+
+    # ------------------------------------------------------------------ gradient phases (overlapped data-parallel exchange)
+    def grad_phase_views(self):
+        """[[contiguous 1-D views of the flat gradient buffer] per phase], in the order the backward completes them: phase 0 the
+        decoder, phase 1 the deepest encoder block, phase 2 the rest -- one view per UNet slot (include/vecvad.h
+        vecvad_net_grad_phase_ranges).  Together the views cover every parameter gradient exactly once."""
+        if self._phase_views is None:
+            self._engine(max(1, self._ws_batch))
+            b, e = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+            _lib.check(_lib.lib().vecvad_net_grad_phase_ranges(self._parts[0]['net'], b, e), 'grad_phase_ranges')
+            self._phase_views = [[self._gflat[s * self._pstride + b[ph]:s * self._pstride + e[ph]] for s in range(len(self._slots))]
+                                 for ph in range(3)]
+        return self._phase_views
+
+    def wait_grad_phase(self, phase, stream=None):
+        """Make ``stream`` (default: the current stream) wait until phase ``phase`` of the backward queued last is complete."""
+        st = torch.cuda.current_stream() if stream is None else stream
+        _lib.check(_lib.lib().vecvad_net_grad_phase_wait(self._parts[0]['net'], int(phase), C.c_void_p(st.cuda_stream)), 'grad_phase_wait')
 
     @property
     def flat_params(self):
