@@ -238,6 +238,18 @@ int vecvad_convt3x3s2_dgrad(const float *grad_out, int ld, int coff, const float
 int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int coff, float *dw, float *scratch, int batch, int h,
                             int wd, int ci, int co, int use_tc, vecvad_stream stream);
 
+/* get_foreground on the device (vad_datasets.py:70-93): crop every box out of each of n_frames frames and resize the crop to
+ * patch x patch with the arithmetic of cv2.resize(.., INTER_LINEAR), bit-exact for uint8 and float32 frames alike (copy when the
+ * crop already has the size, 2x2 box average when it is exactly twice as large, fixed-point / unfused float bilinear otherwise).
+ * frames: device, uint8 (is_f32 = 0) or float32 (is_f32 = 1), addressed as [t][c][y][x] through the four ELEMENT strides, so cv2's
+ *         [T,H,W,C] frames (stride_c = 1) and the reference's [T,C,H,W] stacks both pass unchanged.
+ * boxes : device int32 [n_boxes][4] = x_min, y_min, x_max, y_max, the ceil'ed bbox edges exactly as the reference computes them on the
+ *         host (np.ceil -> int); every box must satisfy 0 <= min < max <= extent (checked by the host wrapper).
+ * out   : device [n_boxes][n_frames][channels][patch][patch], same element type as frames; patch <= 32. */
+int vecvad_crop_resize(const void *frames, int is_f32, int n_frames, int channels, int height, int width, int64_t stride_t,
+                       int64_t stride_c, int64_t stride_h, int64_t stride_w, const int32_t *boxes, int n_boxes, int patch, void *out,
+                       vecvad_stream stream);
+
 /* cube staging: uint8 cubes [N,T,S,S,3] (+ float flow [N,T_of,S,S,2]) -> x [N,3T,S,S] float /255, x_of [N,2*T_of,S,S]
  * == cube_to_train_dataset + ToTensor + collate (vad_datasets.py:130-168). */
 int vecvad_cubes_to_tensors(const uint8_t *raw, const float *flow, float *x, float *x_of, int n, int t_raw, int t_of, int patch,

@@ -26,6 +26,7 @@ SYMBOLS = [
     'vecvad_net_grad_phase_ranges', 'vecvad_net_grad_phase_wait',
     'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
     'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
+    'vecvad_crop_resize',
 ]
 
 
@@ -91,6 +92,7 @@ def lib():
     L.vecvad_convt3x3s2_dgrad.argtypes = [p, i, i, p, p, p, i, i, i, i, i, i, p]
     L.vecvad_convt3x3s2_wgrad.argtypes = [p, p, i, i, p, p, i, i, i, i, i, i, p]
     L.vecvad_cubes_to_tensors.argtypes = [p, p, p, p, i, i, i, i, p]
+    L.vecvad_crop_resize.argtypes = [p, i, i, i, i, i, i64, i64, i64, i64, p, i, i, p, p]
     if L.vecvad_abi_version() != ABI_VERSION:
         raise RuntimeError('vec_vad_b200: libvecvad.so ABI %d != binding ABI %d -- rebuild' % (L.vecvad_abi_version(), ABI_VERSION))
     _lib = L

@@ -160,6 +160,10 @@ def _cube_datasets(cfg, all_bboxes):
     ds2 = vd.unified_dataset_interface(cfg.dataset_name, os.path.join('optical_flow', cfg.dataset_name),
                                        context_frame_num=cfg.context_of_num, mode=cfg.mode, border_mode=cfg.border_mode,
                                        all_bboxes=all_bboxes, patch_size=cfg.patch_size, file_format='.npy')
+    # crop + resize of the foreground boxes on the GPU (bit-identical to cv2.resize, csrc/crop_resize.cu); VECVAD_DEVICE_FOREGROUND=0
+    # keeps the host path
+    if torch.cuda.is_available() and os.environ.get('VECVAD_DEVICE_FOREGROUND', '1') != '0':
+        ds.foreground_device = ds2.foreground_device = torch.device('cuda', torch.cuda.current_device())
     return ds, ds2
 
 

@@ -62,7 +62,7 @@ def img_batch_tensor2numpy(img_batch):
         axes = [0, 3, 1, 2] if img_batch.ndim == 4 else [0, 1, 4, 2, 3]
         return torch.from_numpy(np.transpose(img_batch, axes))
     axes = [0, 2, 3, 1] if img_batch.dim() == 4 else [0, 1, 3, 4, 2]
-    return np.transpose(img_batch, axes).numpy()
+    return np.transpose(img_batch.cpu(), axes).numpy()
 
 
 def _bbox_to_slices(box):
@@ -200,6 +200,7 @@ class _frame_folder_dataset(Dataset):
         self.context_frame_num, self.border_mode = context_frame_num, border_mode
         self.file_format, self.all_bboxes, self.patch_size = file_format, all_bboxes, patch_size
         self.return_gt = False
+        self.foreground_device = None          # a CUDA device: __getitem__ crops + resizes the boxes on the GPU (get_foreground_device)
         if mode not in ('train', 'test'):
             raise NotImplementedError
         self.dataset_init()
@@ -234,9 +235,14 @@ class _frame_folder_dataset(Dataset):
             img = np.transpose(get_inputs(self.all_frame_addr[indice]), [2, 0, 1])
         else:
             img = np.array([np.transpose(get_inputs(self.all_frame_addr[i]), [2, 0, 1]) for i in self.context_range(indice)])
-        if self.all_bboxes is not None:
-            img = get_foreground(img=img, bboxes=self.all_bboxes[indice], patch_size=self.patch_size)
-        img = torch.from_numpy(img)
+        if self.all_bboxes is not None and self.foreground_device is not None:
+            # device path (f4): upload the frame stack once, crop + resize every box on the GPU (bit-identical patches)
+            img = get_foreground_device(torch.from_numpy(np.ascontiguousarray(img)).to(self.foreground_device), self.all_bboxes[indice],
+                                        self.patch_size)
+        else:
+            if self.all_bboxes is not None:
+                img = get_foreground(img=img, bboxes=self.all_bboxes[indice], patch_size=self.patch_size)
+            img = torch.from_numpy(img)
         if self.mode == 'test' and self.return_gt:
             return img, torch.from_numpy(self._gt(indice))
         return img, torch.zeros(1)
@@ -342,6 +348,47 @@ def unified_dataset_interface(dataset_name, dir, mode='train', context_frame_num
 
 
 # ------------------------------------------------------------------------------------------ device feed
+def get_foreground_device(img, bboxes, patch_size, layout='CHW'):
+    """``get_foreground`` (vad_datasets.py:70-93) on the GPU: same boxes -> the same patches, bit for bit (uint8 AND float32).
+
+    img    : CUDA tensor, uint8 or float32.  layout 'CHW': [C,H,W] or [T,C,H,W] as the reference passes it; layout 'HWC': [H,W,C]
+             or [T,H,W,C] as cv2.imread / np.load deliver frames (no host transpose needed).
+    bboxes : host array [N,4] (x_min, y_min, x_max, y_max) as loaded from bboxes_*.npy; the ceil -> int of every edge is done on
+             the host in numpy exactly as the reference does it (the integer path stays the reference's own arithmetic).
+    -> CUDA tensor [N,C,ps,ps] (3-D input) or [N,T,C,ps,ps] (4-D input), dtype of img.
+    """
+    _lib.require_cuda(img)
+    if img.dtype not in (torch.uint8, torch.float32):
+        raise TypeError('get_foreground_device: frames must be uint8 or float32, got %s' % img.dtype)
+    if layout not in ('CHW', 'HWC'):
+        raise ValueError("layout must be 'CHW' or 'HWC'")
+    single = img.dim() == 3
+    if img.dim() not in (3, 4):
+        raise ValueError('img must be 3-D or 4-D, got %s' % (tuple(img.shape),))
+    v = img[None] if single else img
+    if layout == 'HWC':
+        v = v.permute(0, 3, 1, 2)                            # a view: the kernel walks the frames through element strides
+    T, Cn, H, W = v.shape
+    boxes = np.asarray(bboxes)
+    n = len(boxes)
+    ib = np.empty((n, 4), dtype=np.int32)
+    for k in range(n):
+        ys, xs = _bbox_to_slices(boxes[k])
+        # numpy slicing clips silently; the reference then hands cv2 whatever is left (an empty crop raises there)
+        y0, y1, _ = ys.indices(H)
+        x0, x1, _ = xs.indices(W)
+        if y1 <= y0 or x1 <= x0:
+            raise ValueError('get_foreground_device: box %d (%s) is empty after ceil / clipping to the %dx%d frame' % (k, boxes[k], H, W))
+        ib[k] = (x0, y0, x1, y1)
+    out = torch.empty((n, T, Cn, patch_size, patch_size), dtype=img.dtype, device=img.device)
+    if n:
+        dev_boxes = torch.from_numpy(ib).to(img.device, non_blocking=False)
+        st = v.stride()
+        _lib.check(_lib.lib().vecvad_crop_resize(_lib.ptr(v), int(img.dtype == torch.float32), T, Cn, H, W, st[0], st[1], st[2], st[3],
+                                                 _lib.ptr(dev_boxes), n, int(patch_size), _lib.ptr(out), _lib.cur_stream()), 'crop_resize')
+    return out[:, 0] if single else out
+
+
 def cubes_to_device_tensors(raw_u8, flow=None):
     """uint8 cubes [N,T,S,S,3] (+ float32 flow [N,T_of,S,S,2]) on the GPU -> (x [N,3T,S,S] float32 in [0,1], x_of [N,2T_of,S,S]).
 
