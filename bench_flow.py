@@ -80,12 +80,42 @@ def run(batch, iters, with_reference=True, device=0):
     return out
 
 
+def run_flownet2(batch=1, iters=10, height=384, width=512, device=0):
+    """The whole FlowNet2 stack (vec_vad_b200/flownet2.py) on the frame size calc_optical_flow.py:49-54 feeds it (512x384), random
+    weights: ms per pair and the fp32 FMA rate over the algorithmic conv FLOPs.  Compute-bound on the fp32 pipe (SIMT tiles)."""
+    import torch
+    from vec_vad_b200 import flownet2 as fn
+    dev = torch.device('cuda', device)
+    torch.manual_seed(0)
+    net = fn.FlowNet2().to(dev).eval()
+    x = torch.rand(batch, 3, 2, height, width, device=dev) * 255
+    for _ in range(2):
+        net(x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        net(x)
+    e1.record()
+    torch.cuda.synchronize()
+    t = e0.elapsed_time(e1) * 1e-3 / iters
+    flops = batch * fn.conv_flops(height, width)
+    return {'op': 'flownet2_forward', 'batch': batch, 'frame': '%dx%d' % (width, height), 'ms': t * 1e3, 'pairs_per_s': batch / t,
+            'algorithmic_gflop': flops / 1e9, 'tflops_fp32': flops / t / 1e12,
+            'note': 'inputs (%d x 3 x 2 x %d x %d fp32) larger than nothing cached between iterations: 162.5 M parameters (650 MB) and '
+                    'all activations stream through L2 every pass' % (batch, height, width)}
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--flownet2', action='store_true', help='time the whole FlowNet2 stack instead of the three ops')
     ap.add_argument('--batch', type=int, default=1)
     ap.add_argument('--iters', type=int, default=20)
     ap.add_argument('--no-reference', action='store_true', help='skip the recompiled reference kernels (oracle/_ref)')
     a = ap.parse_args()
+    if a.flownet2:
+        print(json.dumps(run_flownet2(a.batch, a.iters)))
+        return
     for line in run(a.batch, a.iters, with_reference=not a.no_reference):
         print(json.dumps(line))
 

@@ -238,6 +238,29 @@ int vecvad_convt3x3s2_dgrad(const float *grad_out, int ld, int coff, const float
 int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int coff, float *dw, float *scratch, int batch, int h,
                             int wd, int ci, int co, int use_tc, vecvad_stream stream);
 
+/* ---- FlowNet2 inference graph (FlowNet2_src/models/flownet2.py:65-149, components/FlowNet{C,S,SD,Fusion}.py, misc.py:6-45): the layers
+ * that are not the three native ops.  NCHW fp32; every tensor argument is a CHANNEL SLICE of a possibly larger buffer (pointer to the
+ * slice's first channel + the batch stride, in elements, of the buffer it lives in), so the reference's torch.cat calls never run.
+ * fn_conv2d        nn.Conv2d(c_in, c_out, ksize, stride, padding=(ksize-1)/2, bias) [+ LeakyReLU(0.1) when leaky]   (misc.py:6-27,41-45)
+ *                  w [c_out][c_in][k][k] (PyTorch layout), bias nullable.
+ * fn_deconv4x4s2   nn.ConvTranspose2d(c_in, c_out, 4, 2, 1, bias) [+ LeakyReLU(0.1)]                              (misc.py:30-38)
+ *                  w_phases [4][c_out][c_in*4]: the weight [c_in][c_out][4][4] re-laid out once per output parity phase
+ *                  (py, px) = (ph >> 1, ph & 1), tap (a, b) -> kernel element (k[py*2+a], k[px*2+b]) with k from fn_deconv_taps.
+ * fn_normalize_pair ims [B,3,2,H,W] -> x [B,6,H,W] = (ims - mean over both frames per colour) / rgb_max        (flownet2.py:66-72)
+ *                  scratch: 3*B doubles.
+ * fn_upsample4     nn.Upsample(scale_factor=4, mode = 0 'bilinear' (align_corners False) | 1 'nearest'), times mul.
+ * fn_scale_copy    out slice = mul * in slice, then LeakyReLU(leaky_slope) if leaky_slope >= 0. */
+int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias, float *out,
+                     int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch, vecvad_stream stream);
+int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w_phases, const float *bias,
+                          float *out, int64_t out_batch_stride, int c_out, int leaky, int batch, vecvad_stream stream);
+int vecvad_fn_deconv_taps(int *k_of_parity_tap);
+int vecvad_fn_normalize_pair(const float *ims, float *x, double *scratch, int batch, int height, int width, float rgb_max, vecvad_stream stream);
+int vecvad_fn_upsample4(const float *in, int64_t in_batch_stride, int channels, int h, int w, float *out, int64_t out_batch_stride, int mode,
+                        float mul, int batch, vecvad_stream stream);
+int vecvad_fn_scale_copy(const float *in, int64_t in_batch_stride, float *out, int64_t out_batch_stride, int64_t elems_per_image, float mul,
+                         float leaky_slope, int batch, vecvad_stream stream);
+
 /* get_foreground on the device (vad_datasets.py:70-93): crop every box out of each of n_frames frames and resize the crop to
  * patch x patch with the arithmetic of cv2.resize(.., INTER_LINEAR), bit-exact for uint8 and float32 frames alike (copy when the
  * crop already has the size, 2x2 box average when it is exactly twice as large, fixed-point / unfused float bilinear otherwise).

@@ -27,6 +27,7 @@ SYMBOLS = [
     'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
     'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
     'vecvad_crop_resize',
+    'vecvad_fn_conv2d', 'vecvad_fn_deconv4x4s2', 'vecvad_fn_deconv_taps', 'vecvad_fn_normalize_pair', 'vecvad_fn_upsample4', 'vecvad_fn_scale_copy',
 ]
 
 
@@ -93,6 +94,12 @@ def lib():
     L.vecvad_convt3x3s2_wgrad.argtypes = [p, p, i, i, p, p, i, i, i, i, i, i, p]
     L.vecvad_cubes_to_tensors.argtypes = [p, p, p, p, i, i, i, i, p]
     L.vecvad_crop_resize.argtypes = [p, i, i, i, i, i, i64, i64, i64, i64, p, i, i, p, p]
+    L.vecvad_fn_conv2d.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, i, i, p]
+    L.vecvad_fn_deconv4x4s2.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, p]
+    L.vecvad_fn_deconv_taps.argtypes = [ip]
+    L.vecvad_fn_normalize_pair.argtypes = [p, p, p, i, i, i, f, p]
+    L.vecvad_fn_upsample4.argtypes = [p, i64, i, i, i, p, i64, i, f, i, p]
+    L.vecvad_fn_scale_copy.argtypes = [p, i64, p, i64, i64, f, f, i, p]
     if L.vecvad_abi_version() != ABI_VERSION:
         raise RuntimeError('vec_vad_b200: libvecvad.so ABI %d != binding ABI %d -- rebuild' % (L.vecvad_abi_version(), ABI_VERSION))
     _lib = L

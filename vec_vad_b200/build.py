@@ -7,7 +7,7 @@ PKG = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, 'csrc')
 LIB = os.path.join(PKG, 'libvecvad.so')
-SOURCES = ['net.cu', 'single_ops.cu', 'unet_kernels.cu', 'igemm_simt.cu', 'tc_support.cu', 'igemm_flat.cu', 'igemm_tc3.cu', 'wgrad_tc2.cu', 'wgrad_flat.cu', 'flow_ops.cu', 'corr_tma.cu', 'prof.cu', 'crop_resize.cu']
+SOURCES = ['net.cu', 'single_ops.cu', 'unet_kernels.cu', 'igemm_simt.cu', 'tc_support.cu', 'igemm_flat.cu', 'igemm_tc3.cu', 'wgrad_tc2.cu', 'wgrad_flat.cu', 'flow_ops.cu', 'corr_tma.cu', 'prof.cu', 'crop_resize.cu', 'flownet_ops.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '-Xcompiler', '-fPIC',
               '-I' + os.path.join(REPO, 'include'), '-I' + CSRC]
 

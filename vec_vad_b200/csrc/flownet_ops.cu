@@ -1,0 +1,326 @@
+// Kernels of the FlowNet2 inference graph (reference: FlowNet2_src/models/flownet2.py:65-149 and
+// components/FlowNetC.py, FlowNetS.py, FlowNetSD.py, FlowNetFusion.py, misc.py:6-45) that are not the three native ops
+// (correlation / resample2d / channelnorm live in corr_tma.cu / flow_ops.cu).
+//
+// Layout: NCHW fp32 like the reference, but every tensor argument is a CHANNEL SLICE of a possibly larger buffer: a pointer to
+// the slice's first channel plus the batch stride of the buffer it lives in.  torch.cat([...], 1) of the reference is therefore
+// never executed: the producers write their channels straight into the concat buffer.
+//
+//   k_fn_conv<TN>   Conv2d (k in {1,3,5,7}, stride 1/2, pad (k-1)/2) and ConvTranspose2d(4, 2, 1) as ONE gather-GEMM:
+//                   out[b, co, gy*o_mul + o_off, ..] = bias[co] + sum_{ci, t} in[b, ci, gy*i_mul + ty[t], gx*i_mul + tx[t]] * w[co][ci*ntaps + t]
+//                   (+ LeakyReLU(0.1), misc.py:25-26).  The transposed conv runs as its four output-parity phases, each a 2x2-tap
+//                   gather with the phase's weights re-laid out once at load time.  fp32 FMA tiles: 128 pixels x TN channels per
+//                   CTA, K staged through shared memory in chunks of 16 with a register prefetch of the next chunk.
+//                   Arithmetic is exact fp32 (the reference runs these layers in fp32 cuDNN); summation order differs.
+//   k_fn_mean / k_fn_normalize   per-(image, colour) mean over both frames, (x - mean) / rgb_max, frames concatenated on channels
+//                   (flownet2.py:66-72).
+//   k_fn_upsample4  nn.Upsample(scale_factor=4, 'bilinear' | 'nearest') times a constant (flownet2.py:28,34,41-42,76,90,105,122).
+//   k_fn_scale_copy slice -> slice copy with a scale and an optional LeakyReLU (concat members that are not conv outputs,
+//                   the correlation's activation FlowNetC.py:33,91).
+#include "common.h"
+
+namespace {
+
+constexpr int FN_TM = 128, FN_KC = 16, FN_MAXTAPS = 49;
+
+struct FnConv {
+    const float *in;   long long in_bs;  int Cin, IH, IW;
+    const float *w;                                      // [Co][K], K = Cin * ntaps
+    const float *bias;                                   // nullable
+    float *out;        long long out_bs; int Co, OH, OW;
+    int GH, GW;                                          // pixel grid of this launch
+    int o_mul, o_off_y, o_off_x;                         // output pixel = g * o_mul + o_off
+    int i_mul;                                           // input pixel  = g * i_mul + tap offset
+    int ntaps;
+    signed char ty[FN_MAXTAPS], tx[FN_MAXTAPS];
+    int B, act;                                          // act: LeakyReLU(0.1)
+};
+
+template <int TN>
+__global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
+    constexpr int CN = TN / 16;                          // output channels per thread
+    __shared__ float As[2][FN_KC][FN_TM + 4];
+    __shared__ float Bs[2][FN_KC][TN + 4];
+    __shared__ signed char s_ty[FN_MAXTAPS], s_tx[FN_MAXTAPS];
+    vv_pdl_wait();
+    const int tid = threadIdx.x;
+    if (tid < p.ntaps) { s_ty[tid] = p.ty[tid]; s_tx[tid] = p.tx[tid]; }
+    const int K = p.Cin * p.ntaps;
+    const long long M = (long long)p.B * p.GH * p.GW;
+    const long long m0 = (long long)blockIdx.x * FN_TM;
+    const int n0 = blockIdx.y * TN;
+    // ---- loader roles.  A: thread owns pixel (tid % 128) and 8 consecutive k of the chunk; B: channel (tid / 4 ... ) and 4 k.
+    const int a_m = tid & 127, a_k0 = (tid >> 7) * 8;
+    const long long am = m0 + a_m;
+    const bool a_ok = am < M;
+    int ab = 0, agy = 0, agx = 0;
+    if (a_ok) {
+        ab = (int)(am / ((long long)p.GH * p.GW));
+        const int r = (int)(am - (long long)ab * p.GH * p.GW);
+        agy = r / p.GW; agx = r - agy * p.GW;
+    }
+    const float *a_base = p.in + (long long)ab * p.in_bs;
+    const int iy0 = agy * p.i_mul, ix0 = agx * p.i_mul;
+    const long long IHW = (long long)p.IH * p.IW;
+    constexpr int BPT = TN * FN_KC / 256;                // B elements per thread: 4 (TN = 64) or 1 (TN = 16)
+    const int b_n = (tid * BPT) / FN_KC, b_k0 = (tid * BPT) % FN_KC;
+    const bool b_ok = n0 + b_n < p.Co;
+    const float *b_base = p.w + (long long)(n0 + b_n) * K;
+    __syncthreads();                                     // tap tables visible
+
+    float ra[8], rb[BPT];
+    auto load = [&](int k0) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int kg = k0 + a_k0 + j;
+            float v = 0.f;
+            if (a_ok && kg < K) {
+                const int ci = kg / p.ntaps, t = kg - ci * p.ntaps;
+                const int iy = iy0 + s_ty[t], ix = ix0 + s_tx[t];
+                if (iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW) v = __ldg(a_base + ci * IHW + (long long)iy * p.IW + ix);
+            }
+            ra[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < BPT; j++) {
+            const int kg = k0 + b_k0 + j;
+            rb[j] = (b_ok && kg < K) ? __ldg(b_base + kg) : 0.f;
+        }
+    };
+    auto stage = [&](int buf) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) As[buf][a_k0 + j][a_m] = ra[j];
+#pragma unroll
+        for (int j = 0; j < BPT; j++) Bs[buf][b_k0 + j][b_n] = rb[j];
+    };
+    // ---- compute roles: 16 x 16 threads, thread (tm, tn) owns pixels tm + 16 i (i < 8) and channels tn * CN + j
+    const int tm = tid & 15, tn = tid >> 4;
+    float acc[8][CN];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < CN; j++) acc[i][j] = 0.f;
+
+    load(0);
+    stage(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += FN_KC) {
+        const bool more = k0 + FN_KC < K;
+        if (more) load(k0 + FN_KC);                       // global loads of the next chunk in flight during the FMAs
+#pragma unroll
+        for (int k = 0; k < FN_KC; k++) {
+            float a[8], b[CN];
+#pragma unroll
+            for (int i = 0; i < 8; i++) a[i] = As[buf][k][tm + 16 * i];
+#pragma unroll
+            for (int j = 0; j < CN; j++) b[j] = Bs[buf][k][tn * CN + j];
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < CN; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            stage(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+    // ---- epilogue: bias, LeakyReLU, NCHW store (16 consecutive pixels per (i, channel) across the half-warp)
+    const long long OHW = (long long)p.OH * p.OW;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long long m = m0 + tm + 16 * i;
+        if (m >= M) continue;
+        const int b = (int)(m / ((long long)p.GH * p.GW));
+        const int r = (int)(m - (long long)b * p.GH * p.GW);
+        const int gy = r / p.GW, gx = r - gy * p.GW;
+        float *o = p.out + (long long)b * p.out_bs + (long long)(gy * p.o_mul + p.o_off_y) * p.OW + (gx * p.o_mul + p.o_off_x);
+#pragma unroll
+        for (int j = 0; j < CN; j++) {
+            const int co = n0 + tn * CN + j;
+            if (co < p.Co) {
+                float v = acc[i][j] + (p.bias ? __ldg(p.bias + co) : 0.f);
+                if (p.act) v = v > 0.f ? v : 0.1f * v;
+                o[co * OHW] = v;
+            }
+        }
+    }
+}
+
+int launch_conv(const FnConv &p, cudaStream_t st) {
+    const long long M = (long long)p.B * p.GH * p.GW;
+    cudaError_t e;
+    if (p.Co <= 16) e = vv_launch(k_fn_conv<16>, dim3(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, 16)), dim3(256), 0, st, p);
+    else e = vv_launch(k_fn_conv<64>, dim3(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, 64)), dim3(256), 0, st, p);
+    VV_CK(e);
+    VV_CKL();
+    return 0;
+}
+
+// sums[b * 3 + c] += sum over this block's share of the 2 * H * W values of colour c of image pair b  (ims: [B,3,2,H,W])
+__global__ void k_fn_mean(const float *__restrict__ ims, double *__restrict__ sums, long long per) {
+    vv_pdl_wait();
+    const int bc = blockIdx.y;
+    const float *src = ims + (long long)bc * per;
+    double s = 0.0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per; i += (long long)gridDim.x * blockDim.x) s += (double)src[i];
+    __shared__ double red[256];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) atomicAdd(sums + bc, red[0]);
+}
+// x[b, f*3 + c, y, x] = (ims[b, c, f, y, x] - mean[b, c]) / rgb_max
+__global__ void k_fn_normalize(const float *__restrict__ ims, const double *__restrict__ sums, float *__restrict__ x, long long HW, float rgb_max) {
+    vv_pdl_wait();
+    const int bc = blockIdx.y, b = bc / 3, c = bc - 3 * b;
+    const float mean = (float)(sums[bc] / (double)(2 * HW));
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < 2 * HW; i += (long long)gridDim.x * blockDim.x) {
+        const int f = i >= HW;
+        const long long pix = i - f * HW;
+        x[((long long)b * 6 + f * 3 + c) * HW + pix] = (ims[(long long)bc * 2 * HW + i] - mean) / rgb_max;
+    }
+}
+
+// out[b, c, Y, X] = mul * upsample4(in)[b, c, Y, X];  mode 0: bilinear, align_corners = False (F.interpolate's default, which is
+// what nn.Upsample(scale_factor=4, mode='bilinear') resolves to in PyTorch >= 0.4); mode 1: nearest
+__global__ void k_fn_upsample4(const float *__restrict__ in, long long in_bs, int C, int h, int w, float *__restrict__ out, long long out_bs,
+                               int mode, float mul, int B) {
+    vv_pdl_wait();
+    const int H = 4 * h, W = 4 * w;
+    const long long total = (long long)B * C * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int X = (int)(i % W);
+        long long r = i / W;
+        const int Y = (int)(r % H); r /= H;
+        const int c = (int)(r % C), b = (int)(r / C);
+        const float *src = in + (long long)b * in_bs + (long long)c * h * w;
+        float v;
+        if (mode == 1) {
+            v = src[(Y >> 2) * w + (X >> 2)];
+        } else {
+            float sy = 0.25f * ((float)Y + 0.5f) - 0.5f, sx = 0.25f * ((float)X + 0.5f) - 0.5f;
+            sy = sy < 0.f ? 0.f : sy; sx = sx < 0.f ? 0.f : sx;
+            const int y0 = (int)sy, x0 = (int)sx;
+            const int y1 = y0 + (y0 < h - 1), x1 = x0 + (x0 < w - 1);
+            const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+            v = hy * (hx * src[y0 * w + x0] + lx * src[y0 * w + x1]) + ly * (hx * src[y1 * w + x0] + lx * src[y1 * w + x1]);
+        }
+        out[(long long)b * out_bs + ((long long)c * H + Y) * W + X] = mul * v;
+    }
+}
+
+// out slice = act(mul * in slice); slope < 0: no activation
+__global__ void k_fn_scale_copy(const float *__restrict__ in, long long in_bs, float *__restrict__ out, long long out_bs, long long per,
+                                float mul, float slope, int B) {
+    vv_pdl_wait();
+    const long long total = (long long)B * per;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(i / per);
+        const long long r = i - (long long)b * per;
+        float v = mul * in[(long long)b * in_bs + r];
+        if (slope >= 0.f) v = v > 0.f ? v : slope * v;
+        out[(long long)b * out_bs + r] = v;
+    }
+}
+
+}  // namespace
+
+extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias,
+                                float *out, int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch,
+                                vecvad_stream stream) {
+    VV_REQUIRE(in && w && out, "fn_conv2d: null pointer");
+    VV_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "fn_conv2d: kernel size %d not in {1,3,5,7}", ksize);
+    VV_REQUIRE(stride == 1 || stride == 2, "fn_conv2d: stride %d not in {1,2}", stride);
+    VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_conv2d: bad shape");
+    const int pad = (ksize - 1) / 2;
+    FnConv p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
+    p.w = w; p.bias = bias;
+    p.OH = (in_h + 2 * pad - ksize) / stride + 1; p.OW = (in_w + 2 * pad - ksize) / stride + 1;
+    p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
+    p.GH = p.OH; p.GW = p.OW; p.o_mul = 1; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = stride;
+    p.ntaps = ksize * ksize;
+    for (int ky = 0; ky < ksize; ky++)
+        for (int kx = 0; kx < ksize; kx++) { p.ty[ky * ksize + kx] = (signed char)(ky - pad); p.tx[ky * ksize + kx] = (signed char)(kx - pad); }
+    p.B = batch; p.act = leaky;
+    return launch_conv(p, (cudaStream_t)stream);
+}
+
+// w_phases: [4][c_out][c_in * 4] -- phase (py, px) = (ph >> 1, ph & 1), tap t = a * 2 + b with the (ky, kx) pairs of
+// vecvad_fn_deconv_taps(); prepared once from the ConvTranspose2d weight [c_in][c_out][4][4] (vec_vad_b200/flownet2.py)
+extern "C" int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w_phases,
+                                     const float *bias, float *out, int64_t out_batch_stride, int c_out, int leaky, int batch,
+                                     vecvad_stream stream) {
+    VV_REQUIRE(in && w_phases && out, "fn_deconv4x4s2: null pointer");
+    VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_deconv4x4s2: bad shape");
+    for (int ph = 0; ph < 4; ph++) {
+        const int py = ph >> 1, px = ph & 1;
+        FnConv p;
+        memset(&p, 0, sizeof(p));
+        p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
+        p.w = w_phases + (long long)ph * c_out * c_in * 4; p.bias = bias;
+        p.OH = 2 * in_h; p.OW = 2 * in_w;
+        p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
+        p.GH = in_h; p.GW = in_w; p.o_mul = 2; p.o_off_y = py; p.o_off_x = px; p.i_mul = 1;
+        p.ntaps = 4;
+        // output row 2y + py receives input row y + dy through kernel row ky (oy = 2 iy - 1 + ky):
+        //   py = 0: (ky, dy) = (1, 0), (3, -1);   py = 1: (ky, dy) = (0, +1), (2, 0)
+        const int dys[2][2] = {{0, -1}, {1, 0}};
+        for (int a = 0; a < 2; a++)
+            for (int b = 0; b < 2; b++) { p.ty[a * 2 + b] = (signed char)dys[py][a]; p.tx[a * 2 + b] = (signed char)dys[px][b]; }
+        p.B = batch; p.act = leaky;
+        int r = launch_conv(p, (cudaStream_t)stream);
+        if (r) return r;
+    }
+    return 0;
+}
+
+// the kernel rows / columns that feed output parity 0 and 1, in tap order (see above): parity 0 -> k = 1, 3; parity 1 -> k = 0, 2
+extern "C" int vecvad_fn_deconv_taps(int *k_of_parity_tap) {
+    VV_REQUIRE(k_of_parity_tap, "fn_deconv_taps: null pointer");
+    const int k[4] = {1, 3, 0, 2};
+    for (int i = 0; i < 4; i++) k_of_parity_tap[i] = k[i];
+    return 0;
+}
+
+extern "C" int vecvad_fn_normalize_pair(const float *ims, float *x, double *scratch, int batch, int height, int width, float rgb_max,
+                                        vecvad_stream stream) {
+    VV_REQUIRE(ims && x && scratch && batch >= 1 && height >= 1 && width >= 1 && rgb_max > 0.f, "fn_normalize_pair: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long HW = (long long)height * width;
+    VV_CK(cudaMemsetAsync(scratch, 0, sizeof(double) * 3 * batch, st));
+    const int gx = (int)((2 * HW + 256 * 8 - 1) / (256 * 8));
+    VV_CK(vv_launch(k_fn_mean, dim3(gx < 1 ? 1 : gx, 3 * batch), dim3(256), 0, st, ims, scratch, 2 * HW));
+    VV_CKL();
+    VV_CK(vv_launch(k_fn_normalize, dim3(gx < 1 ? 1 : gx, 3 * batch), dim3(256), 0, st, ims, (const double *)scratch, x, HW, rgb_max));
+    VV_CKL();
+    return 0;
+}
+
+extern "C" int vecvad_fn_upsample4(const float *in, int64_t in_batch_stride, int channels, int h, int w, float *out, int64_t out_batch_stride,
+                                   int mode, float mul, int batch, vecvad_stream stream) {
+    VV_REQUIRE(in && out && channels >= 1 && h >= 1 && w >= 1 && batch >= 1 && (mode == 0 || mode == 1), "fn_upsample4: bad argument");
+    const long long total = (long long)batch * channels * 16 * h * w;
+    const int gx = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    VV_CK(vv_launch(k_fn_upsample4, dim3(gx), dim3(256), 0, (cudaStream_t)stream, in, (long long)in_batch_stride, channels, h, w, out,
+                    (long long)out_batch_stride, mode, mul, batch));
+    VV_CKL();
+    return 0;
+}
+
+extern "C" int vecvad_fn_scale_copy(const float *in, int64_t in_batch_stride, float *out, int64_t out_batch_stride, int64_t elems_per_image,
+                                    float mul, float leaky_slope, int batch, vecvad_stream stream) {
+    VV_REQUIRE(in && out && elems_per_image >= 1 && batch >= 1, "fn_scale_copy: bad argument");
+    const long long total = (long long)batch * elems_per_image;
+    const int gx = (int)((total + 255) / 256 > 148 * 16 ? 148 * 16 : (total + 255) / 256);
+    VV_CK(vv_launch(k_fn_scale_copy, dim3(gx), dim3(256), 0, (cudaStream_t)stream, in, (long long)in_batch_stride, out,
+                    (long long)out_batch_stride, (long long)elems_per_image, mul, leaky_slope, batch));
+    VV_CKL();
+    return 0;
+}

@@ -87,9 +87,14 @@ def _all_reduce_views(views, group=None):
 
 class GradReducer:
     """Callable handed to ``CompletionNet.train_step(reduce_grads=...)``: sums the flat gradient buffer over the ranks
-    in place on the current stream and returns the scale Adam must apply (1/world)."""
+    in place on the current stream and returns the scale Adam must apply (1/world).
 
-    def __init__(self, group=None, bucket_bytes=0, overlap=True):
+    overlap=True exchanges the three gradient phases while the backward still runs (``reduce_phased``).  Measured on 2 x B200
+    (profiles/r02_ddp_overlap_n2.txt) it buys nothing at NCCL's default channel count -- the step keeps every SM busy, so the
+    collective's SM time is paid either way (2.61 ms overlapped vs 2.60 ms after the backward, 2.46 ms on one GPU) -- and wins
+    only when the collective is throttled to few CTAs (NCCL_MAX_CTAS <= 16); hence off by default."""
+
+    def __init__(self, group=None, bucket_bytes=0, overlap=False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.bucket_elems = bucket_bytes // 4
