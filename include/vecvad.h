@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 5
+#define VECVAD_ABI_VERSION 6
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -249,11 +249,15 @@ int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int 
  * fn_normalize_pair ims [B,3,2,H,W] -> x [B,6,H,W] = (ims - mean over both frames per colour) / rgb_max        (flownet2.py:66-72)
  *                  scratch: 3*B doubles.
  * fn_upsample4     nn.Upsample(scale_factor=4, mode = 0 'bilinear' (align_corners False) | 1 'nearest'), times mul.
- * fn_scale_copy    out slice = mul * in slice, then LeakyReLU(leaky_slope) if leaky_slope >= 0. */
+ * fn_scale_copy    out slice = mul * in slice, then LeakyReLU(leaky_slope) if leaky_slope >= 0.
+ * scratch (fn_conv2d / fn_deconv4x4s2): caller-owned device floats (may be NULL): launches whose pixel grid is too small to fill the
+ *                  GPU split the contraction over more CTAs and pass their partial sums through it (used size <= scratch_floats). */
 int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias, float *out,
-                     int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch, vecvad_stream stream);
+                     int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch, float *scratch,
+                     int64_t scratch_floats, vecvad_stream stream);
 int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w_phases, const float *bias,
-                          float *out, int64_t out_batch_stride, int c_out, int leaky, int batch, vecvad_stream stream);
+                          float *out, int64_t out_batch_stride, int c_out, int leaky, int batch, float *scratch, int64_t scratch_floats,
+                          vecvad_stream stream);
 int vecvad_fn_deconv_taps(int *k_of_parity_tap);
 int vecvad_fn_normalize_pair(const float *ims, float *x, double *scratch, int batch, int height, int width, float rgb_max, vecvad_stream stream);
 int vecvad_fn_upsample4(const float *in, int64_t in_batch_stride, int channels, int h, int w, float *out, int64_t out_batch_stride, int mode,

@@ -69,8 +69,9 @@ def test_conv2d_kernel_matches_torch(cin, cout, k, s, h, w, leaky):
     from vec_vad_b200 import _lib
     sv, dv = fn.View(src_buf.cuda(), 2, 2 + cin), fn.View(dst_buf, 1, 1 + cout)
     wc, bc = wt.cuda(), bias.cuda()
+    sc = fn._scratch(wc.device)                                                   # small grids split the contraction through it
     _lib.check(_lib.lib().vecvad_fn_conv2d(sv.ptr, sv.bs, cin, h, w, _lib.ptr(wc), _lib.ptr(bc), dv.ptr, dv.bs, cout, k, s, leaky, B,
-                                           _lib.cur_stream()), 'fn_conv2d')
+                                           _lib.ptr(sc), sc.numel(), _lib.cur_stream()), 'fn_conv2d')
     got = dst_buf.cpu()
     assert torch.allclose(got[:, 1:1 + cout].double(), want, rtol=1e-4, atol=1e-5), float((got[:, 1:1 + cout].double() - want).abs().max())
     assert bool((got[:, 0] == 7.0).all()) and bool((got[:, 1 + cout:] == 7.0).all())
@@ -148,3 +149,30 @@ def test_flownet2_stack_matches_reference_fixture(gold):
         m(torch.zeros(1, 3, 2, 100, 128).cuda())
     with pytest.raises(RuntimeError):
         m(gold['inputs'])                                                          # CPU tensor: no fallback
+
+
+@pytest.mark.gpu
+def test_calc_optical_flow_stage_writes_the_flow_modality(tmp_path, monkeypatch):
+    """calc_optical_flow.py:12-88 on a tiny on-disk dataset: one .npy per frame in the raw_datasets layout, frame-sized [H,W,2] float32,
+    computed from the first two entries of the clamped window at a video's borders and from (current, next) elsewhere."""
+    import cv2
+    from tests import _synthetic_dataset as syn
+    from vec_vad_b200 import optical_flow as of, vad_datasets as vd
+    from vec_vad_b200.flownet2 import FlowNet2
+    root = syn.make(str(tmp_path / 'ws'), n_train=(3,), n_test=(2,))
+    monkeypatch.chdir(root)
+    torch.manual_seed(1)
+    net = FlowNet2().cuda().eval()
+    ds = vd.unified_dataset_interface(dataset_name='UCSDped2', dir=os.path.join('raw_datasets', 'UCSDped2'), context_frame_num=1, mode='train',
+                                      border_mode='hard')
+    of.calc_optical_flow(ds, net=net, of_root_dir='./of_out', verbose=False)
+    frames = [cv2.imread(a) for a in ds.all_frame_addr]
+    assert len(frames) == 3
+    # windows [0,0,1] / [0,1,2] / [1,2,2]: a border window feeds its FIRST two entries (frame 0 against itself at the very start,
+    # calc_optical_flow.py:44-56), every other window its last two
+    for idx, pair in ((0, (0, 0)), (1, (1, 2)), (2, (1, 2))):
+        saved = np.load(os.path.join('of_out', 'UCSDped2', 'Train', 'Train001', '%03d.npy' % (idx + 1)))
+        assert saved.shape == (240, 360, 2) and saved.dtype == np.float32
+        ims = np.array([[cv2.resize(frames[pair[0]], (512, 384)), cv2.resize(frames[pair[1]], (512, 384))]]).transpose((0, 4, 1, 2, 3))
+        want = cv2.resize(net(torch.from_numpy(ims.astype(np.float32)).cuda())[0].cpu().numpy().transpose((1, 2, 0)), (360, 240))
+        assert np.allclose(saved, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()))

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -94,8 +94,8 @@ def lib():
     L.vecvad_convt3x3s2_wgrad.argtypes = [p, p, i, i, p, p, i, i, i, i, i, i, p]
     L.vecvad_cubes_to_tensors.argtypes = [p, p, p, p, i, i, i, i, p]
     L.vecvad_crop_resize.argtypes = [p, i, i, i, i, i, i64, i64, i64, i64, p, i, i, p, p]
-    L.vecvad_fn_conv2d.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, i, i, p]
-    L.vecvad_fn_deconv4x4s2.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, p]
+    L.vecvad_fn_conv2d.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, i, i, p, i64, p]
+    L.vecvad_fn_deconv4x4s2.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, p, i64, p]
     L.vecvad_fn_deconv_taps.argtypes = [ip]
     L.vecvad_fn_normalize_pair.argtypes = [p, p, p, i, i, i, f, p]
     L.vecvad_fn_upsample4.argtypes = [p, i64, i, i, i, p, i64, i, f, i, p]

@@ -34,18 +34,21 @@ struct FnConv {
     int ntaps;
     signed char ty[FN_MAXTAPS], tx[FN_MAXTAPS];
     int B, act;                                          // act: LeakyReLU(0.1)
+    int ksplit, kper;                                    // split-K: blockIdx.z handles k in [z * kper, (z + 1) * kper); kper % 16 == 0
+    float *partial;                                      // ksplit > 1: raw partial sums [ksplit][Co][M], finished by k_fn_conv_finish
 };
 
 template <int TN>
 __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
     constexpr int CN = TN / 16;                          // output channels per thread
-    __shared__ float As[2][FN_KC][FN_TM + 4];
-    __shared__ float Bs[2][FN_KC][TN + 4];
+    __shared__ __align__(16) float As[2][FN_KC][FN_TM + 4];
+    __shared__ __align__(16) float Bs[2][FN_KC][TN + 4];
     __shared__ signed char s_ty[FN_MAXTAPS], s_tx[FN_MAXTAPS];
     vv_pdl_wait();
     const int tid = threadIdx.x;
     if (tid < p.ntaps) { s_ty[tid] = p.ty[tid]; s_tx[tid] = p.tx[tid]; }
-    const int K = p.Cin * p.ntaps;
+    const int Kall = p.Cin * p.ntaps;
+    const int kbeg = blockIdx.z * p.kper, K = min(Kall, kbeg + p.kper);     // this CTA's share of the contraction
     const long long M = (long long)p.B * p.GH * p.GW;
     const long long m0 = (long long)blockIdx.x * FN_TM;
     const int n0 = blockIdx.y * TN;
@@ -65,26 +68,27 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
     constexpr int BPT = TN * FN_KC / 256;                // B elements per thread: 4 (TN = 64) or 1 (TN = 16)
     const int b_n = (tid * BPT) / FN_KC, b_k0 = (tid * BPT) % FN_KC;
     const bool b_ok = n0 + b_n < p.Co;
-    const float *b_base = p.w + (long long)(n0 + b_n) * K;
+    const float *b_base = p.w + (long long)(n0 + b_n) * Kall;
     __syncthreads();                                     // tap tables visible
 
     float ra[8], rb[BPT];
     auto load = [&](int k0) {
+        int kg = k0 + a_k0;
+        int ci = kg / p.ntaps, t = kg - ci * p.ntaps;    // one division per chunk; the 8 consecutive k walk (ci, t) incrementally
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int kg = k0 + a_k0 + j;
+        for (int j = 0; j < 8; j++, kg++) {
             float v = 0.f;
             if (a_ok && kg < K) {
-                const int ci = kg / p.ntaps, t = kg - ci * p.ntaps;
                 const int iy = iy0 + s_ty[t], ix = ix0 + s_tx[t];
                 if (iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW) v = __ldg(a_base + ci * IHW + (long long)iy * p.IW + ix);
             }
             ra[j] = v;
+            if (++t == p.ntaps) { t = 0; ci++; }
         }
 #pragma unroll
         for (int j = 0; j < BPT; j++) {
-            const int kg = k0 + b_k0 + j;
-            rb[j] = (b_ok && kg < K) ? __ldg(b_base + kg) : 0.f;
+            const int kb = k0 + b_k0 + j;
+            rb[j] = (b_ok && kb < K) ? __ldg(b_base + kb) : 0.f;
         }
     };
     auto stage = [&](int buf) {
@@ -93,7 +97,8 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
 #pragma unroll
         for (int j = 0; j < BPT; j++) Bs[buf][b_k0 + j][b_n] = rb[j];
     };
-    // ---- compute roles: 16 x 16 threads, thread (tm, tn) owns pixels tm + 16 i (i < 8) and channels tn * CN + j
+    // ---- compute roles: 16 x 16 threads, thread (tm, tn) owns pixels 4 tm .. 4 tm + 3 and 64 + 4 tm .. + 3 (two 16-byte shared-memory
+    // reads per k instead of eight scalar ones) and channels tn * CN + j
     const int tm = tid & 15, tn = tid >> 4;
     float acc[8][CN];
 #pragma unroll
@@ -101,20 +106,20 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
 #pragma unroll
         for (int j = 0; j < CN; j++) acc[i][j] = 0.f;
 
-    load(0);
+    load(kbeg);
     stage(0);
     __syncthreads();
     int buf = 0;
-    for (int k0 = 0; k0 < K; k0 += FN_KC) {
+    for (int k0 = kbeg; k0 < K; k0 += FN_KC) {
         const bool more = k0 + FN_KC < K;
         if (more) load(k0 + FN_KC);                       // global loads of the next chunk in flight during the FMAs
 #pragma unroll
         for (int k = 0; k < FN_KC; k++) {
             float a[8], b[CN];
-#pragma unroll
-            for (int i = 0; i < 8; i++) a[i] = As[buf][k][tm + 16 * i];
-#pragma unroll
-            for (int j = 0; j < CN; j++) b[j] = Bs[buf][k][tn * CN + j];
+            *reinterpret_cast<float4 *>(a) = *reinterpret_cast<const float4 *>(&As[buf][k][4 * tm]);
+            *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[buf][k][64 + 4 * tm]);
+            if constexpr (CN == 4) *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tn]);
+            else b[0] = Bs[buf][k][tn];
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
@@ -126,12 +131,20 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
             buf ^= 1;
         }
     }
-    // ---- epilogue: bias, LeakyReLU, NCHW store (16 consecutive pixels per (i, channel) across the half-warp)
+    // ---- epilogue: bias, LeakyReLU, NCHW store (a half-warp covers 64 consecutive pixels of a channel); split-K: raw partials
     const long long OHW = (long long)p.OH * p.OW;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const long long m = m0 + tm + 16 * i;
+        const long long m = m0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + i - 4);
         if (m >= M) continue;
+        if (p.ksplit > 1) {
+#pragma unroll
+            for (int j = 0; j < CN; j++) {
+                const int co = n0 + tn * CN + j;
+                if (co < p.Co) p.partial[((long long)blockIdx.z * p.Co + co) * M + m] = acc[i][j];
+            }
+            continue;
+        }
         const int b = (int)(m / ((long long)p.GH * p.GW));
         const int r = (int)(m - (long long)b * p.GH * p.GW);
         const int gy = r / p.GW, gx = r - gy * p.GW;
@@ -148,13 +161,51 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
     }
 }
 
-int launch_conv(const FnConv &p, cudaStream_t st) {
+// out = act(bias + sum over the splits of the partial sums)
+__global__ void k_fn_conv_finish(const FnConv p) {
+    vv_pdl_wait();
+    const long long M = (long long)p.B * p.GH * p.GW, total = M * p.Co;
+    const long long OHW = (long long)p.OH * p.OW;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int co = (int)(i / M);
+        const long long m = i - (long long)co * M;
+        float v = p.bias ? __ldg(p.bias + co) : 0.f;
+        for (int z = 0; z < p.ksplit; z++) v += p.partial[((long long)z * p.Co + co) * M + m];
+        if (p.act) v = v > 0.f ? v : 0.1f * v;
+        const int b = (int)(m / ((long long)p.GH * p.GW));
+        const int r = (int)(m - (long long)b * p.GH * p.GW);
+        const int gy = r / p.GW, gx = r - gy * p.GW;
+        p.out[(long long)b * p.out_bs + co * OHW + (long long)(gy * p.o_mul + p.o_off_y) * p.OW + (gx * p.o_mul + p.o_off_x)] = v;
+    }
+}
+
+// Launches with few CTAs (small images, deep layers: the contraction is long and the pixel grid tiny) split the contraction over
+// blockIdx.z so that ~4 CTAs per SM are in flight; the partial sums go through the caller's scratch buffer.
+int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t st) {
     const long long M = (long long)p.B * p.GH * p.GW;
-    cudaError_t e;
-    if (p.Co <= 16) e = vv_launch(k_fn_conv<16>, dim3(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, 16)), dim3(256), 0, st, p);
-    else e = vv_launch(k_fn_conv<64>, dim3(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, 64)), dim3(256), 0, st, p);
+    const int tn = p.Co <= 16 ? 16 : 64;
+    const long long base = (long long)vv_cdiv(M, FN_TM) * vv_cdiv(p.Co, tn);
+    const int K = p.Cin * p.ntaps;
+    int ksplit = 1;
+    if (scratch && base < 296) {
+        ksplit = (int)(592 / base);
+        if (ksplit > K / 64) ksplit = K / 64;
+        while (ksplit > 1 && (long long)ksplit * p.Co * M > scratch_floats) ksplit--;
+        if (ksplit < 1) ksplit = 1;
+    }
+    p.ksplit = ksplit;
+    p.kper = ksplit > 1 ? vv_cdiv(vv_cdiv(K, ksplit), FN_KC) * FN_KC : ((K + FN_KC - 1) / FN_KC) * FN_KC;
+    if (ksplit > 1) p.ksplit = ksplit = vv_cdiv(K, p.kper);          // rounding kper up may leave the last split empty: drop it
+    p.partial = scratch;
+    const dim3 grid(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, tn), ksplit);
+    cudaError_t e = tn == 16 ? vv_launch(k_fn_conv<16>, grid, dim3(256), 0, st, p) : vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p);
     VV_CK(e);
     VV_CKL();
+    if (ksplit > 1) {
+        const long long total = M * p.Co;
+        VV_CK(vv_launch(k_fn_conv_finish, dim3((unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256)), dim3(256), 0, st, p));
+        VV_CKL();
+    }
     return 0;
 }
 
@@ -232,7 +283,7 @@ __global__ void k_fn_scale_copy(const float *__restrict__ in, long long in_bs, f
 
 extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias,
                                 float *out, int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch,
-                                vecvad_stream stream) {
+                                float *scratch, int64_t scratch_floats, vecvad_stream stream) {
     VV_REQUIRE(in && w && out, "fn_conv2d: null pointer");
     VV_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "fn_conv2d: kernel size %d not in {1,3,5,7}", ksize);
     VV_REQUIRE(stride == 1 || stride == 2, "fn_conv2d: stride %d not in {1,2}", stride);
@@ -249,14 +300,14 @@ extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_
     for (int ky = 0; ky < ksize; ky++)
         for (int kx = 0; kx < ksize; kx++) { p.ty[ky * ksize + kx] = (signed char)(ky - pad); p.tx[ky * ksize + kx] = (signed char)(kx - pad); }
     p.B = batch; p.act = leaky;
-    return launch_conv(p, (cudaStream_t)stream);
+    return launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
 }
 
 // w_phases: [4][c_out][c_in * 4] -- phase (py, px) = (ph >> 1, ph & 1), tap t = a * 2 + b with the (ky, kx) pairs of
 // vecvad_fn_deconv_taps(); prepared once from the ConvTranspose2d weight [c_in][c_out][4][4] (vec_vad_b200/flownet2.py)
 extern "C" int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w_phases,
                                      const float *bias, float *out, int64_t out_batch_stride, int c_out, int leaky, int batch,
-                                     vecvad_stream stream) {
+                                     float *scratch, int64_t scratch_floats, vecvad_stream stream) {
     VV_REQUIRE(in && w_phases && out, "fn_deconv4x4s2: null pointer");
     VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_deconv4x4s2: bad shape");
     for (int ph = 0; ph < 4; ph++) {
@@ -275,7 +326,7 @@ extern "C" int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, i
         for (int a = 0; a < 2; a++)
             for (int b = 0; b < 2; b++) { p.ty[a * 2 + b] = (signed char)dys[py][a]; p.tx[a * 2 + b] = (signed char)dys[px][b]; }
         p.B = batch; p.act = leaky;
-        int r = launch_conv(p, (cudaStream_t)stream);
+        int r = launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
         if (r) return r;
     }
     return 0;

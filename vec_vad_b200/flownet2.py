@@ -147,6 +147,18 @@ def upsample4(src, dst, mode, mul):
                                               float(mul), src.B, _lib.cur_stream()), 'fn_upsample4')
 
 
+_SCRATCH = {}
+
+
+def _scratch(device):
+    """Split-K partial sums of the layers whose pixel grid is too small to fill the GPU (csrc/flownet_ops.cu launch_conv): one
+    16 MB buffer per device, reused by every layer (all launches are ordered on the caller's stream)."""
+    key = (device.type, device.index)
+    if key not in _SCRATCH:
+        _SCRATCH[key] = torch.empty(4 << 20, dtype=torch.float32, device=device)
+    return _SCRATCH[key]
+
+
 class _SubNet(nn.Module):
     """One of FlowNetC / FlowNetS / FlowNetSD / FlowNetFusion: the parameter tree (reference attribute names and order) plus the
     interpreter helpers."""
@@ -169,8 +181,10 @@ class _SubNet(nn.Module):
         if dst is None:
             dst = View(src.t.new_empty((src.B, cout, oh, ow)))
         assert dst.C == cout and dst.H == oh and dst.W == ow, (name, dst.C, dst.H, dst.W)
+        sc = _scratch(src.t.device)
         _lib.check(_lib.lib().vecvad_fn_conv2d(src.ptr, src.bs, cin, src.H, src.W, _lib.ptr(layer.weight), _lib.ptr(layer.bias), dst.ptr,
-                                               dst.bs, cout, k, s, int(lk == 'conv'), src.B, _lib.cur_stream()), 'fn_conv2d ' + name)
+                                               dst.bs, cout, k, s, int(lk == 'conv'), src.B, _lib.ptr(sc), sc.numel(), _lib.cur_stream()),
+                   'fn_conv2d ' + name)
         return dst
 
     def _phase_weights(self, name, layer):
@@ -198,8 +212,10 @@ class _SubNet(nn.Module):
             dst = View(src.t.new_empty((src.B, cout, 2 * src.H, 2 * src.W)))
         assert dst.C == cout and dst.H == 2 * src.H and dst.W == 2 * src.W, name
         wp = self._phase_weights(name, layer)
+        sc = _scratch(src.t.device)
         _lib.check(_lib.lib().vecvad_fn_deconv4x4s2(src.ptr, src.bs, cin, src.H, src.W, _lib.ptr(wp), _lib.ptr(layer.bias), dst.ptr, dst.bs,
-                                                    cout, int(lk == 'deconv'), src.B, _lib.cur_stream()), 'fn_deconv4x4s2 ' + name)
+                                                    cout, int(lk == 'deconv'), src.B, _lib.ptr(sc), sc.numel(), _lib.cur_stream()),
+                   'fn_deconv4x4s2 ' + name)
         return dst
 
     # -- the shared refinement: levels 5..2 of FlowNetC / S / SD (FlowNetC.py:104-127, FlowNetS.py:68-91, FlowNetSD.py:64-98)
