@@ -71,7 +71,10 @@ def test_correlation_backward(case):
     np.testing.assert_allclose(tb.grad.cpu().numpy(), g2, rtol=2e-4, atol=2e-5)
 
 
-@pytest.mark.parametrize('shape,amp', [((2, 3, 24, 40), 4.0), ((1, 2, 17, 19), 30.0), ((1, 3, 436, 1024), 4.0)])
+# the last three run the shared-memory-tiled kernel (width >= 64): ragged tiles, flow far beyond the staged +-12 px window (global
+# fallback inside the tiled kernel), one / two / three channels
+@pytest.mark.parametrize('shape,amp', [((2, 3, 24, 40), 4.0), ((1, 2, 17, 19), 30.0), ((1, 3, 436, 1024), 4.0), ((2, 3, 70, 150), 30.0),
+                                       ((1, 2, 100, 64), 8.0), ((3, 1, 33, 129), 12.0)])
 def test_resample2d_forward(shape, amp):
     b, c, h, w = shape
     rng = np.random.RandomState(h)
@@ -110,8 +113,13 @@ def test_channelnorm_forward_backward():
 def test_warp_diff_norm_fused():
     rng = np.random.RandomState(10)
     b, c, h, w = 2, 3, 30, 50
+    _fused_case(rng, b, c, h, w, 5)
+    _fused_case(rng, 2, 3, 75, 200, 9)            # the tiled kernel (width >= 64), some samples beyond its staged window
+
+
+def _fused_case(rng, b, c, h, w, amp):
     img0, img1 = rng.rand(b, c, h, w).astype(np.float32), rng.rand(b, c, h, w).astype(np.float32)
-    flow = (rng.randn(b, 2, h, w) * 5).astype(np.float32)
+    flow = (rng.randn(b, 2, h, w) * amp).astype(np.float32)
     warped, diff, norm = ops.warp_diff_norm(_t(img0), _t(img1), _t(flow))
     w_, d_, n_ = fo.warp_diff_norm(img0, img1, flow)
     np.testing.assert_allclose(warped.cpu().numpy(), w_, rtol=1e-6, atol=1e-7)

@@ -235,6 +235,55 @@ __global__ void k_resample2d(const float *__restrict__ img, const float *__restr
     if (norm) norm[(long long)b * OHW + (long long)y * OW + x] = sqrtf(ss);
 }
 
+// Fixed-channel-count variant (C = 1..3, what FlowNet2 uses: images and flows).  The four double weights of the reference's arithmetic --
+// each tap's weight product in double, the running value rounded to float after every tap (Resample2d_kernel.cu:53-63) -- are formed
+// ONCE per pixel instead of once per (channel, tap) and the channel loop is unrolled: same results bit for bit, 1.3x faster
+// (profiles/r02_resample_variants.txt).  What bounds it on BASELINE.json configs[4]'s per-pixel N(0, 4 px) flow is the gather itself: a
+// warp's 32 flow vectors point into ~20 different 128-byte lines per load instruction (L1 wavefronts), so even float arithmetic only
+// reaches 0.30 of the HBM rate; staging the neighbourhood in shared memory was measured slower (same file) and dropped.
+template <int C>
+__global__ void __launch_bounds__(128) k_resample2d_c(const float *__restrict__ img, const float *__restrict__ flow, float *__restrict__ out,
+                                                      const float *__restrict__ img0, float *__restrict__ diff, float *__restrict__ norm, int IH,
+                                                      int IW, int OH, int OW) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+    if (x >= OW) return;
+    const long long OHW = (long long)OH * OW, IHW = (long long)IH * IW, pix = (long long)y * OW + x;
+    const float dx = flow[((long long)b * 2 + 0) * OHW + pix], dy = flow[((long long)b * 2 + 1) * OHW + pix];
+    const Bilin w = bilin(dx, dy, x, y, OW, OH);
+    const long long oTL = (long long)w.yT * IW + w.xL, oTR = (long long)w.yT * IW + w.xR, oBL = (long long)w.yB * IW + w.xL,
+                    oBR = (long long)w.yB * IW + w.xR;
+    const double wTL = (1. - w.alpha) * (1. - w.beta), wTR = (w.alpha) * (1. - w.beta), wBL = (1. - w.alpha) * (w.beta), wBR = (w.alpha) * (w.beta);
+    float ss = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        const float *im = img + ((long long)b * C + c) * IHW;
+        const float tl = __ldg(im + oTL), tr = __ldg(im + oTR), bl = __ldg(im + oBL), br = __ldg(im + oBR);
+        float v = 0.f;
+        v += wTL * tl; v += wTR * tr; v += wBL * bl; v += wBR * br;       // as bilin_sample: double product + sum, float after every tap
+        const long long o = ((long long)b * C + c) * OHW + pix;
+        if (out) out[o] = v;
+        if (img0) {
+            const float d = img0[o] - v;
+            if (diff) diff[o] = d;
+            ss += d * d;
+        }
+    }
+    if (norm) norm[(long long)b * OHW + pix] = sqrtf(ss);
+}
+
+int launch_resample(const float *img, const float *flow, float *out, const float *img0, float *diff, float *norm, int B, int C, int IH, int IW,
+                    int OH, int OW, cudaStream_t st) {
+    static int generic = -1;                   // VECVAD_RESAMPLE_GENERIC=1: the any-channel-count kernel everywhere (bit-identical A/B baseline)
+    if (generic < 0) { const char *g = getenv("VECVAD_RESAMPLE_GENERIC"); generic = (g && g[0] == '1') ? 1 : 0; }
+    const dim3 grid(vv_cdiv(OW, 128), OH, B);
+    if (!generic && C == 1) k_resample2d_c<1><<<grid, 128, 0, st>>>(img, flow, out, img0, diff, norm, IH, IW, OH, OW);
+    else if (!generic && C == 2) k_resample2d_c<2><<<grid, 128, 0, st>>>(img, flow, out, img0, diff, norm, IH, IW, OH, OW);
+    else if (!generic && C == 3) k_resample2d_c<3><<<grid, 128, 0, st>>>(img, flow, out, img0, diff, norm, IH, IW, OH, OW);
+    else k_resample2d<<<grid, 128, 0, st>>>(img, flow, out, img0, diff, norm, B, C, IH, IW, OH, OW);
+    VV_CKL();
+    return 0;
+}
+
 // backward wrt the image: scatter-add (Resample2d_kernel.cu:69-116; weights use xf - int(xf), i.e. truncation, as there)
 __global__ void k_resample2d_bwd_img(const float *__restrict__ flow, const float *__restrict__ gout, float *__restrict__ gimg, int B, int C,
                                      int IH, int IW, int OH, int OW) {
@@ -405,10 +454,7 @@ extern "C" int vecvad_resample2d_forward(const float *img, const float *flow, fl
     VV_REQUIRE(kernel_size == 1, "resample2d: only kernel_size 1 is supported (the only value any caller uses: modules/resample2d.py:8)");
     VV_REQUIRE(out_h <= img_h && out_w <= img_w, "resample2d: flow larger than the image reads out of bounds in the reference; unsupported");
     VV_REQUIRE(out_h <= 65535 && batch <= 65535, "resample2d: tensor too large");
-    k_resample2d<<<dim3(vv_cdiv(out_w, 128), out_h, batch), 128, 0, (cudaStream_t)stream>>>(img, flow, out, nullptr, nullptr, nullptr, batch,
-                                                                                        channels, img_h, img_w, out_h, out_w);
-    VV_CKL();
-    return 0;
+    return launch_resample(img, flow, out, nullptr, nullptr, nullptr, batch, channels, img_h, img_w, out_h, out_w, (cudaStream_t)stream);
 }
 
 extern "C" int vecvad_resample2d_backward(const float *img, const float *flow, const float *grad_out, float *grad_img, float *grad_flow,
@@ -451,8 +497,5 @@ extern "C" int vecvad_warp_diff_norm(const float *img0, const float *img1, const
                                      int batch, int channels, int h, int w, vecvad_stream stream) {
     VV_REQUIRE(img0 && img1 && flow, "warp_diff_norm: null pointer");
     VV_REQUIRE(h <= 65535 && batch <= 65535, "warp_diff_norm: tensor too large");
-    k_resample2d<<<dim3(vv_cdiv(w, 128), h, batch), 128, 0, (cudaStream_t)stream>>>(img1, flow, warped, img0, diff, norm, batch, channels, h, w,
-                                                                                h, w);
-    VV_CKL();
-    return 0;
+    return launch_resample(img1, flow, warped, img0, diff, norm, batch, channels, h, w, h, w, (cudaStream_t)stream);
 }
