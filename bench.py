@@ -256,16 +256,28 @@ def roofline_of(args, net, m, pk, src):
 
 
 def flow_secondary(pk):
-    """BASELINE.json configs[4] (FlowNet2 correlation + warp, 1024x436 pairs) beside the headline: bench_flow.py's rows, HBM roofline."""
+    """BASELINE.json configs[4] (FlowNet2 correlation + warp, 1024x436 pairs) beside the headline: bench_flow.py's rows.  The warp
+    kernels are judged against the HBM roofline over their algorithmic bytes; the correlation (59 FLOP/B) against the fp32 FMA rate
+    (148 SMs x 128 lanes x 2 x SM clock: no fp32 peak is in MEASURED_PEAKS.json); then the whole FlowNet2 stack on a 512x384 pair."""
     import bench_flow
+    fp32_peak = 148 * 128 * 2 * pk.get('sm_max_mhz', 1965.0) * 1e6 / 1e12
     rows = []
     for batch in (1, 8):
         for r in bench_flow.run(batch, 10, with_reference=False):
+            roof = {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': r['frac_of_hbm_peak'],
+                    'traffic': None, 'algorithmic_bytes': r['algorithmic_bytes']}
+            if r.get('tflops_fp32'):
+                roof = {'bound': 'fp32', 'achieved': r['tflops_fp32'], 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': r['tflops_fp32'] / fp32_peak,
+                        'traffic': None, 'algorithmic_bytes': r['algorithmic_bytes'], 'frac_of_hbm_peak': r['frac_of_hbm_peak'],
+                        'peak_is': 'nominal fp32 FMA rate (SMs x lanes x 2 x max SM clock)'}
             rows.append({'workload': 'FlowNet2 %s, 1024x436 synthetic pairs, batch %d (BASELINE.json configs[4])' % (r['op'], batch),
-                         'metric': 'pairs/sec', 'value': r['pairs_per_s'], 'unit': 'pairs/s', 'us_per_launch': r['us'],
-                         'roofline': {'bound': 'hbm', 'achieved': r['achieved_gbs'], 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                                      'frac': r['frac_of_hbm_peak'], 'traffic': None, 'algorithmic_bytes': r['algorithmic_bytes'],
-                                      'tflops_fp32': r.get('tflops_fp32')}})
+                         'metric': 'pairs/sec', 'value': r['pairs_per_s'], 'unit': 'pairs/s', 'us_per_launch': r['us'], 'roofline': roof})
+    f = bench_flow.run_flownet2(1, 5)
+    rows.append({'workload': 'FlowNet2 full stack (5 networks, 162.5 M parameters), one 512x384 pair (calc_optical_flow.py:49-57)', 'metric': 'pairs/sec',
+                 'value': f['pairs_per_s'], 'unit': 'pairs/s', 'ms_per_pair': f['ms'],
+                 'roofline': {'bound': 'fp32', 'achieved': f['tflops_fp32'], 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': f['tflops_fp32'] / fp32_peak,
+                              'traffic': None, 'algorithmic_gflop': f['algorithmic_gflop'],
+                              'peak_is': 'nominal fp32 FMA rate (SMs x lanes x 2 x max SM clock)'}})
     return rows
 
 

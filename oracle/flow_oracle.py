@@ -1,12 +1,14 @@
 """CPU oracle for the FlowNet2 native ops (TEST INFRASTRUCTURE ONLY -- imported by tests/, smoke() and bench.py's
 cpu_baseline leg, never by the product package).
 
-PARITY UNPINNED: the reference ships these ops only as CUDA sources built against ``torch.utils.ffi`` + legacy THC
-(removed from PyTorch >= 1.0) and sm_30 binaries for CPython 3.6; its CPU sources are empty stubs
-(correlation/src/correlation.c:3-33).  Nothing in the reference can execute them here, and the reference holds no test
-vectors for them.  This file therefore restates the kernels line by line in numpy (float32 arithmetic where the kernels
-use float, float64 where they promote to double) and is cross-checked in tests/test_flow_oracle.py against independent
-formulations (torch.nn.functional.unfold / grid_sample / autograd) instead of against reference outputs.
+Pinned (round 2): the reference ships these ops only as CUDA sources built against ``torch.utils.ffi`` + legacy THC and as sm_30 /
+CPython-3.6 binaries, so nothing of it could be executed in round 1.  The kernel SOURCES, however, compile as they are for sm_100a
+(``oracle/ref_build/build.sh`` -> ``oracle/_ref/libref_ops.so``, a two-line ``THC.h`` shim for two of the three files);
+``tests/golden/make_flow_golden.py`` ran them on a B200 over the cases of ``tests/_flow_cases.py`` and wrote
+``tests/golden/flow_ops.npz``, which ``tests/test_flow_reference_golden.py`` holds this file to (CPU) and
+``tests/test_flow_ops_gpu.py`` holds the CUDA path to.  ``tests/test_flow_oracle.py`` additionally cross-checks against independent
+formulations (torch.nn.functional.unfold / grid_sample / autograd).  This file restates the kernels line by line in numpy (float32
+arithmetic where the kernels use float, float64 where they promote to double).
 
 Restated (paths under FlowNet2_src/models/components/ops/):
   correlation_forward ........ correlation/src/correlation_cuda_kernel.cu:10-32 (zero-pad + NHWC repack), :34-106

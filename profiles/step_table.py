@@ -1,5 +1,6 @@
 """Turn an ncu per-launch metrics CSV of one train step (scratch/one_step.py) into a table: one row per launch.
-    python profiles/step_table.py gpurun_out/X.csv [out.txt]"""
+    python profiles/step_table.py gpurun_out/X.csv [out.txt]
+When the capture holds several steps only the last one is tabulated."""
 import collections
 import csv
 import re
@@ -27,8 +28,16 @@ def load(path):
     return by
 
 
+def last_step(by):
+    """scratch/one_step.py runs the step twice (warm-up + the one to read): keep the launches from the last weight re-layout on."""
+    ids = [k for k, d in by.items() if d['name'].startswith('k_prep_conv_w')]
+    if len(ids) < 2:
+        return by
+    return collections.OrderedDict((k, d) for k, d in by.items() if k >= ids[-1])
+
+
 def main():
-    by = load(sys.argv[1])
+    by = last_step(load(sys.argv[1]))
     out = open(sys.argv[2], 'w') if len(sys.argv) > 2 else sys.stdout
     out.write('# source: %s (ncu, one train step of batch 128 5raw1of; serialised, cold caches: compare shares)\n' % sys.argv[1])
     out.write('%4s %-34s %-12s %9s %9s %9s %9s %7s\n' % ('id', 'kernel', 'grid', 'us', 'dramRdMB', 'dramWrMB', 'xbarMB', 'tensor%'))

@@ -352,39 +352,25 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
     // 1. weights into GEMM layouts (they change every optimiser step): one launch for all conv units when they tile by 32
     bool batched = true;
     for (int u = 0; u < NU; u++) batched = batched && n->uN[u] % 32 == 0 && n->uCp[u] % 32 == 0;
-    // With the side stream only the first two units' weights (the 32x32 layers the forward starts with) are re-laid out on the
-    // critical path; the other twelve follow on the side stream while those layers run (the forward waits for them before unit 2).
     cudaStream_t sP = n->use_side ? n->wg_stream : st;
-    cudaEvent_t w_ready = nullptr;
     if (n->use_side) {
         VV_CK(cudaEventRecord(n->ev[VV_NEV - 1], st));
         VV_CK(cudaStreamWaitEvent(sP, n->ev[VV_NEV - 1], 0));
     }
     if (batched) {
-        static int prep_side = -1;          // VECVAD_PREP_SIDE=1: units 2..13 re-laid out on the side stream (measured slower: default off)
-        if (prep_side < 0) { const char *e = getenv("VECVAD_PREP_SIDE"); prep_side = (e && e[0] == '1') ? 1 : 0; }
-        const int n_early = (n->use_side && prep_side) ? 2 : NU;
-        for (int part = 0; part < 2; part++) {
-            const int u0 = part ? n_early : 0, u1 = part ? NU : n_early;
-            if (u0 >= u1) continue;
-            VvPrepAll all;
-            memset(&all, 0, sizeof(all));
-            all.n = u1 - u0;
-            for (int u = u0; u < u1; u++) {
-                VvPrepUnit &pu = all.u[u - u0];
-                pu.w_off = c.conv_w[u]; pu.b_off = c.conv_b[u]; pu.g_off = c.bn_w[u]; pu.beta_off = c.bn_b[u];
-                pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
-                pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
-                pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
-            }
-            all.w_f16 = n->f16;
-            int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, part ? sP : st);
-            if (r) return r;
-            if (part && n->use_side) {
-                w_ready = n->ev[VV_NEV - 3];
-                VV_CK(cudaEventRecord(w_ready, sP));
-            }
+        VvPrepAll all;
+        memset(&all, 0, sizeof(all));
+        all.n = NU;
+        for (int u = 0; u < NU; u++) {
+            VvPrepUnit &pu = all.u[u];
+            pu.w_off = c.conv_w[u]; pu.b_off = c.conv_b[u]; pu.g_off = c.bn_w[u]; pu.beta_off = c.bn_b[u];
+            pu.N = n->uN[u]; pu.C = n->uC[u]; pu.Cp = n->uCp[u];
+            pu.Wf = n->Wf[u]; pu.Wd = (training && u > 0) ? n->Wd[u] : nullptr; pu.vec = n->vec[u];
+            pu.wf_gs = 9LL * n->uN[u] * n->uCp[u]; pu.wd_gs = pu.wf_gs; pu.vec_gs = 3LL * n->uN[u];
         }
+        all.w_f16 = n->f16;
+        int r = vv_prep_conv_w_all(n->params, n->slot, c.slot_param_stride, all, G, st);
+        if (r) return r;
     } else {
         for (int u = 0; u < NU; u++) {
             int r = vv_prep_conv_w(n->params, n->slot, c.slot_param_stride, c.conv_w[u], c.conv_b[u], c.bn_w[u], c.bn_b[u], n->uN[u], n->uC[u],
@@ -456,10 +442,7 @@ extern "C" int vecvad_net_forward(vecvad_net *n, const float *x, const float *x_
         return run_igemm(n->cfg.use_tensor_cores != 0, p, st, 0, igemm_flops(B, n->tH[k], n->tH[k], n->tCo[k], n->tCi[k], 9, G));
     };
     int r;
-    for (int u = 0; u < 8; u++) {
-        if (u == 2 && w_ready) VV_CK(cudaStreamWaitEvent(st, w_ready, 0));
-        if ((r = conv_unit(u))) return r;
-    }
+    for (int u = 0; u < 8; u++) if ((r = conv_unit(u))) return r;
     for (int k = 0; k < 3; k++) {
         if (k == 0 && ct_ready) VV_CK(cudaStreamWaitEvent(st, ct_ready, 0));
         if ((r = convT(k))) return r;
