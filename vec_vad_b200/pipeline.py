@@ -321,7 +321,19 @@ def _epoch_batches(store, cfg, rank, world):
     return store.rank_batches(cfg.batch_size, rank, world, seed=ddp.shared_seed(), shuffle=True)
 
 
-def train(cfg_path='config.cfg', use_tensor_cores=True):
+def default_precision():
+    """Operand mode of the conv tiles for the entry points: ``VECVAD_PRECISION`` = f16 (default: fp16 operands, fp32 accumulation -- the mode
+    bench.py measures; losses within 1e-5 relative of the reference arithmetic, AUROC parity in tests/test_auroc_parity_gpu.py), tf32, or
+    fp32 (exact SIMT tiles)."""
+    v = os.environ.get('VECVAD_PRECISION', 'f16').lower()
+    if v not in ('f16', 'fp16', 'tf32', 'fp32', 'simt'):
+        raise ValueError('VECVAD_PRECISION must be f16, tf32 or fp32, got %r' % v)
+    return v
+
+
+def train(cfg_path='config.cfg', use_tensor_cores=None):
+    if use_tensor_cores is None:
+        use_tensor_cores = default_precision()
     cfg = Config(cfg_path, 'train')
     rank, local, world = ddp.init_from_env()
     device = torch.device('cuda', local)
@@ -489,7 +501,9 @@ def score_frames(cfg, net_for, stats_for, foreground_set, foreground_set2, foreg
     return masks
 
 
-def test(cfg_path='config.cfg', results_dir='results', use_tensor_cores=True):
+def test(cfg_path='config.cfg', results_dir='results', use_tensor_cores=None):
+    if use_tensor_cores is None:
+        use_tensor_cores = default_precision()
     cfg = Config(cfg_path, 'test')
     device = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
     torch.cuda.set_device(device)
