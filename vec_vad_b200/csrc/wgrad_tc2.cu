@@ -295,7 +295,11 @@ int vv_launch_wgrad_tc2(const VvWGrad &p, cudaStream_t st) {
         VV_REQUIRE(r == CUDA_SUCCESS, "wgrad_tc2: cuTensorMapEncodeTiled(Gd) failed with %d", (int)r);
     }
     const int out_tiles = wp.kchunks * wp.n_tiles * p.G;
-    int splits = (148 + out_tiles - 1) / out_tiles;
+    // CTAs per launch aimed at: two waves of shorter CTAs give SMs back to the main stream's tile kernels sooner than one wave of
+    // long ones (measured, batch 128: 148 -> 2.460 ms/step, 222 -> 2.449, 296 -> 2.443, 444 -> 2.495: more splits, more dW atomics)
+    static int target = -1;
+    if (target < 0) { const char *e = getenv("VECVAD_WG_TARGET"); target = e ? atoi(e) : 296; if (target < 1) target = 296; }
+    int splits = (target + out_tiles - 1) / out_tiles;
     if (splits > wp.m_tiles) splits = wp.m_tiles;
     if (splits < 1) splits = 1;
     wp.tiles_per_split = (wp.m_tiles + splits - 1) / splits;
