@@ -36,6 +36,34 @@ __device__ __forceinline__ void st4(void *base, long long idx, const float4 &v) 
     else *reinterpret_cast<float4 *>(reinterpret_cast<float *>(base) + idx) = v;
 }
 
+// eight consecutive elements: one 16-byte access for fp16, two for fp32
+template <bool H>
+__device__ __forceinline__ void ld8(const void *base, long long idx, float *v) {
+    if (H) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(reinterpret_cast<const __half *>(base) + idx);
+        const unsigned w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w[i]));
+            v[2 * i] = f.x; v[2 * i + 1] = f.y;
+        }
+    } else {
+        const float4 a = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + idx);
+        const float4 b = *reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(base) + idx + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+}
+template <bool H>
+__device__ __forceinline__ void st8(void *base, long long idx, const float *v) {
+    if (H) {
+        const uint2 lo = pack_h4(make_float4(v[0], v[1], v[2], v[3])), hi = pack_h4(make_float4(v[4], v[5], v[6], v[7]));
+        *reinterpret_cast<uint4 *>(reinterpret_cast<__half *>(base) + idx) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(base) + idx) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(reinterpret_cast<float *>(base) + idx + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
 __device__ __forceinline__ void st1(void *base, long long idx, float v, int h) {
     if (h) reinterpret_cast<__half *>(base)[idx] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
     else reinterpret_cast<float *>(base)[idx] = v;
@@ -62,10 +90,10 @@ __global__ void k_prep_input(const float *__restrict__ x, void *__restrict__ X0,
     const float *xb = x + (long long)b * 3 * T * S * S + pix;
     const long long dst = ((long long)g * M + m) * cinp;
     const int creal = padding ? 3 * T : 3 * (T - 1);
-    for (int c4 = 0; c4 < cinp; c4 += 4) {
-        float v[4];
+    for (int c4 = 0; c4 < cinp; c4 += 8) {              // cinp is a multiple of 32: 16-byte stores of eight channels
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
+        for (int j = 0; j < 8; j++) {
             int c = c4 + j;
             float val = 0.f;
             if (c < creal) {
@@ -75,7 +103,7 @@ __global__ void k_prep_input(const float *__restrict__ x, void *__restrict__ X0,
             }
             v[j] = val;
         }
-        st4<H>(X0, dst + c4, make_float4(v[0], v[1], v[2], v[3]));
+        st8<H>(X0, dst + c4, v);
     }
 }
 
@@ -163,14 +191,21 @@ __global__ void __launch_bounds__(256) k_prep_conv_w_all(const float *__restrict
         tile[n][r] = (r < cw * 9) ? P[U.w_off + ((long long)(n0 + n) * C + c0) * 9 + r] : 0.f;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
-        const int c = i & 31, n = (i >> 5) & 31, t = i >> 10;
-        st1(U.Wf, g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + c, tile[n][c * 9 + t], all.w_f16);
+    // four consecutive elements per store (8 bytes fp16 / 16 bytes fp32): [tap][n][c0 + 4q ..] and, transposed, [tap][c][n0 + 4q ..]
+    for (int i = threadIdx.x; i < 9 * 32 * 8; i += 256) {
+        const int q = i & 7, n = (i >> 3) & 31, t = i >> 8;
+        const float4 v = make_float4(tile[n][(4 * q) * 9 + t], tile[n][(4 * q + 1) * 9 + t], tile[n][(4 * q + 2) * 9 + t], tile[n][(4 * q + 3) * 9 + t]);
+        const long long o = g * U.wf_gs + ((long long)t * N + n0 + n) * Cp + c0 + 4 * q;
+        if (all.w_f16) st4<true>(U.Wf, o, v); else st4<false>(U.Wf, o, v);
     }
     if (U.Wd) {
-        for (int i = threadIdx.x; i < 9 * 32 * 32; i += 256) {
-            const int n = i & 31, c = (i >> 5) & 31, t = i >> 10;
-            if (c < cw) st1(U.Wd, g * U.wd_gs + ((long long)t * C + c0 + c) * N + n0 + n, tile[n][c * 9 + t], all.w_f16);
+        for (int i = threadIdx.x; i < 9 * 32 * 8; i += 256) {
+            const int q = i & 7, c = (i >> 3) & 31, t = i >> 8;
+            if (c < cw) {
+                const float4 v = make_float4(tile[4 * q][c * 9 + t], tile[4 * q + 1][c * 9 + t], tile[4 * q + 2][c * 9 + t], tile[4 * q + 3][c * 9 + t]);
+                const long long o = g * U.wd_gs + ((long long)t * C + c0 + c) * N + n0 + 4 * q;
+                if (all.w_f16) st4<true>(U.Wd, o, v); else st4<false>(U.Wd, o, v);
+            }
         }
     }
     if (lb == 0) {
@@ -657,22 +692,22 @@ __global__ void k_colsum(const void *__restrict__ D, long long d_gs, int ld, int
 }
 
 // ---- 1x1 output conv (model/unet.py:63-70) with fused squared error and MSE gradient (train.py:385-392, 414-427).
-//      One CTA = 256 threads = one cube (S*S pixels, S*S/256 pixels per thread) of one UNet: the per-cube SSE is a
-//      deterministic in-CTA reduction.  U [G][B*S*S][F];  out NCHW;  dout [G][B*S*S][4].
+//      One CTA = 256 threads = one cube (S*S pixels, one pixel row of F channels per thread and pass) of one UNet: the per-cube SSE
+//      is a deterministic in-CTA reduction.  U [G][B*S*S][F];  out NCHW;  dout [G][B*S*S][4].
 template <bool H>
 __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
     vv_pdl_wait();
-    extern __shared__ float sm[];   // tile [256][F+1], w [4][F], b[4]
+    extern __shared__ float sm[];   // w [4][F], b[4]
     const int g = blockIdx.y, b = blockIdx.x;
     const int F = p.F, SS = p.S * p.S;
-    float *tile = sm;
-    float *w = sm + 256 * (F + 1);
+    float *w = sm;
     float *bs = w + 4 * F;
     __shared__ float red[8];
     const int oc = p.out_channels.v[g];
     const float *P = p.params + p.slot.v[g] * p.slot_param_stride;
     for (int i = threadIdx.x; i < 4 * F; i += 256) w[i] = (i < oc * F) ? P[p.w_off + i] : 0.f;
     if (threadIdx.x < 4) bs[threadIdx.x] = threadIdx.x < oc ? P[p.b_off + threadIdx.x] : 0.f;
+    __syncthreads();
     const long long u0 = g * p.u_gs + (long long)b * SS * F;
     const bool flow = p.target_is_flow.v[g] != 0;
     float *out = flow ? p.of_out : p.raw_out;
@@ -685,22 +720,18 @@ __global__ void __launch_bounds__(256) k_outconv_fwd(const VvOutFwd p) {
     }
     const float coef = flow ? p.coef_of : p.coef_raw;
     float sse = 0.f;
-    for (int base = 0; base < SS; base += 256) {
-        __syncthreads();
-        // coalesced load of 256 pixels x F channels
-        for (int i = threadIdx.x; i < 256 * F / 4; i += 256) {
-            int r = (i * 4) / F, c = (i * 4) % F;
-            float4 v = ld4<H>(p.U, u0 + (long long)(base + r) * F + c);
-            float *d = tile + r * (F + 1) + c;
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-        __syncthreads();
-        const int pix = base + threadIdx.x;
+    // one thread per pixel: its F channels are one contiguous NHWC row read with 8- / 16-byte loads (a warp reads 32 consecutive
+    // rows), the three dot products run against the weights broadcast from shared memory in channel order (as before: same sums)
+    for (int pix = threadIdx.x; pix < SS; pix += 256) {
         float o[4] = {bs[0], bs[1], bs[2], bs[3]};
-        const float *row = tile + threadIdx.x * (F + 1);
-        for (int c = 0; c < F; c++) {
-            float u = row[c];
-            o[0] = fmaf(u, w[c], o[0]); o[1] = fmaf(u, w[F + c], o[1]); o[2] = fmaf(u, w[2 * F + c], o[2]);
+        const long long r0 = u0 + (long long)pix * F;
+        for (int c = 0; c < F; c += 8) {
+            float uu[8];
+            ld8<H>(p.U, r0 + c, uu);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                o[0] = fmaf(uu[k], w[c + k], o[0]); o[1] = fmaf(uu[k], w[F + c + k], o[1]); o[2] = fmaf(uu[k], w[2 * F + c + k], o[2]);
+            }
         }
         float dv[4] = {0.f, 0.f, 0.f, 0.f};
         for (int j = 0; j < oc; j++) {
@@ -1075,13 +1106,8 @@ int vv_colsum(const void *D, int d_f16, long long d_gs, int ld, int coff, int M,
 
 int vv_outconv_fwd(const VvOutFwd &p, int G, cudaStream_t st) {
     VV_REQUIRE((p.S * p.S) % 256 == 0, "outconv: S*S must be a multiple of 256 (S=%d)", p.S);
-    size_t smem = (256 * (p.F + 1) + 4 * p.F + 4) * sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
-        VV_CK(cudaFuncSetAttribute(k_outconv_fwd<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        VV_CK(cudaFuncSetAttribute(k_outconv_fwd<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-        attr_set = true;
-    }
+    VV_REQUIRE(p.F % 8 == 0, "outconv: feature count %d must be a multiple of 8", p.F);
+    const size_t smem = (4 * p.F + 4) * sizeof(float);
     if (p.u_f16) vv_launch(k_outconv_fwd<true>, dim3(p.B, G), dim3(256), smem, st, p);
     else vv_launch(k_outconv_fwd<false>, dim3(p.B, G), dim3(256), smem, st, p);
     VV_CKL();
