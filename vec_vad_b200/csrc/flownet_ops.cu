@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
             *reinterpret_cast<float4 *>(a) = *reinterpret_cast<const float4 *>(&As[buf][k][4 * tm]);
             *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[buf][k][64 + 4 * tm]);
             if constexpr (CN == 4) *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tn]);
+            else if constexpr (CN == 2) *reinterpret_cast<float2 *>(b) = *reinterpret_cast<const float2 *>(&Bs[buf][k][2 * tn]);
             else b[0] = Bs[buf][k][tn];
 #pragma unroll
             for (int i = 0; i < 8; i++)
@@ -183,7 +184,7 @@ __global__ void k_fn_conv_finish(const FnConv p) {
 // blockIdx.z so that ~4 CTAs per SM are in flight; the partial sums go through the caller's scratch buffer.
 int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t st) {
     const long long M = (long long)p.B * p.GH * p.GW;
-    const int tn = p.Co <= 16 ? 16 : 64;
+    const int tn = p.Co <= 16 ? 16 : (p.Co <= 32 ? 32 : 64);   // channel tile: no wasted columns for the 2- / 16- / 32-channel layers
     const long long base = (long long)vv_cdiv(M, FN_TM) * vv_cdiv(p.Co, tn);
     const int K = p.Cin * p.ntaps;
     int ksplit = 1;
@@ -198,7 +199,9 @@ int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t
     if (ksplit > 1) p.ksplit = ksplit = vv_cdiv(K, p.kper);          // rounding kper up may leave the last split empty: drop it
     p.partial = scratch;
     const dim3 grid(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, tn), ksplit);
-    cudaError_t e = tn == 16 ? vv_launch(k_fn_conv<16>, grid, dim3(256), 0, st, p) : vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p);
+    cudaError_t e = tn == 16   ? vv_launch(k_fn_conv<16>, grid, dim3(256), 0, st, p)
+                    : tn == 32 ? vv_launch(k_fn_conv<32>, grid, dim3(256), 0, st, p)
+                               : vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p);
     VV_CK(e);
     VV_CKL();
     if (ksplit > 1) {
