@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 6
+#define VECVAD_ABI_VERSION 7
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -178,6 +178,10 @@ int vecvad_net_backward(vecvad_net *net, const float *grad_raw_out, const float 
  * vecvad_net_grad_phase_wait:   makes `stream` wait (cudaStreamWaitEvent) until phase p of the LAST vecvad_net_backward call is
  *                               complete; call it after vecvad_net_backward returned (the backward itself is asynchronous). */
 int vecvad_net_grad_phase_ranges(const vecvad_net *net, int64_t *begin, int64_t *end);
+/* defer != 0: vecvad_net_backward returns WITHOUT making its stream wait for the side stream's last weight gradients; the caller must
+ * call vecvad_net_grad_phase_wait(net, 2, stream) before it reads phase-2 gradients or runs the next forward.  In between it can work on
+ * phases 0 and 1 (vecvad_net_grad_phase_wait for each, then e.g. vecvad_adam_step_ranges) while those last weight gradients finish. */
+int vecvad_net_defer_join(vecvad_net *net, int defer);
 int vecvad_net_grad_phase_wait(vecvad_net *net, int phase, vecvad_stream stream);
 
 /* fp16-operand mode only: the power-of-two loss scale the backward applies to the dZ operands it stores as fp16 (and removes again
@@ -194,6 +198,12 @@ int vecvad_net_losses(vecvad_net *net, const float *sse, int batch, float *losse
  * summing all-reduce). */
 int vecvad_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
                      float beta2, float eps, float weight_decay, int step, float grad_scale, vecvad_stream stream);
+/* The same update restricted to [begin, end) (floats) of each of n_slots slots of the flat buffers, slot_stride floats apart: with the
+ * ranges of vecvad_net_grad_phase_ranges the optimiser can start on the phases that are final while the last weight gradients still
+ * run (see vecvad_net_defer_join). */
+int vecvad_adam_step_ranges(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int n_slots, int64_t slot_stride,
+                            int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                            float grad_scale, vecvad_stream stream);
 
 /* debug / test facility: copy an internal workspace buffer (device to device) into dst as fp32.  kind: 0 X0, 1 Z[u], 2 A[u] (even u),
  * 3 CAT[k], 4 PL[k], 5 X4, 6 UU[k], 7 dCAT[k], 8 GA, 9 GB, 10 DOUT, 11 Wf[u], 12 dWf[u], 13 tWf[k], 14 tdW[k], 15 dUP[k] and

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -23,7 +23,7 @@ SYMBOLS = [
     'vecvad_channelnorm_forward', 'vecvad_channelnorm_backward', 'vecvad_warp_diff_norm',
     'vecvad_net_create', 'vecvad_net_destroy', 'vecvad_net_workspace_bytes', 'vecvad_net_bind',
     'vecvad_net_forward', 'vecvad_net_backward', 'vecvad_net_losses', 'vecvad_net_set_loss_scale', 'vecvad_adam_step',
-    'vecvad_net_grad_phase_ranges', 'vecvad_net_grad_phase_wait',
+    'vecvad_net_grad_phase_ranges', 'vecvad_net_grad_phase_wait', 'vecvad_net_defer_join', 'vecvad_adam_step_ranges',
     'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
     'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
     'vecvad_crop_resize',
@@ -85,6 +85,8 @@ def lib():
     L.vecvad_net_grad_phase_ranges.argtypes = [p, C.POINTER(i64), C.POINTER(i64)]
     L.vecvad_net_grad_phase_wait.argtypes = [p, i, p]
     L.vecvad_adam_step.argtypes = [p, p, p, p, i64, f, f, f, f, f, i, f, p]
+    L.vecvad_adam_step_ranges.argtypes = [p, p, p, p, i, i64, i64, i64, f, f, f, f, f, i, f, p]
+    L.vecvad_net_defer_join.argtypes = [p, i]
     L.vecvad_net_debug_read.argtypes = [p, i, i, p, i64, C.POINTER(i64), p]
     L.vecvad_conv3x3_forward.argtypes = [p, i, p, p, p, p, p, i, i, i, i, i, i, p]
     L.vecvad_conv3x3_wgrad.argtypes = [p, i, p, p, p, i, i, i, i, i, i, p]

@@ -84,6 +84,7 @@ struct vecvad_net {
     // training forward, off the critical path; ev_zero: recorded behind them
     cudaEvent_t ev_zero;
     int have_zero_ev, bwd_zeroed;
+    int defer_join;                          // vecvad_net_defer_join: the backward leaves the side stream unjoined (caller waits for phase 2)
 };
 
 namespace {
@@ -298,6 +299,7 @@ extern "C" int vecvad_net_create(const vecvad_net_config *cfg, vecvad_net **out)
     n->phases_recorded = 0;
     n->have_zero_ev = cudaEventCreateWithFlags(&n->ev_zero, cudaEventDisableTiming) == cudaSuccess;
     n->bwd_zeroed = 0;
+    n->defer_join = 0;
     *out = n;
     return 0;
 }
@@ -760,7 +762,7 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
         }
     }
     if ((r = phase_done(2, 0, 6))) return r;                   // the rest; its scatter runs on the side stream like the others
-    if (n->use_side) {                                         // join: every weight gradient and scatter is complete
+    if (n->use_side && !(n->defer_join && n->have_phase_ev)) { // join: every weight gradient and scatter is complete
         if (n->have_phase_ev) VV_CK(cudaStreamWaitEvent(st, n->ev_phase[2], 0));
         else {
             cudaEvent_t e = next_ev();
@@ -768,6 +770,12 @@ extern "C" int vecvad_net_backward(vecvad_net *n, const float *grad_raw_out, con
             VV_CK(cudaStreamWaitEvent(st, e, 0));
         }
     }
+    return 0;
+}
+
+extern "C" int vecvad_net_defer_join(vecvad_net *n, int defer) {
+    VV_REQUIRE(n, "defer_join: null net");
+    n->defer_join = defer ? 1 : 0;
     return 0;
 }
 

@@ -909,9 +909,11 @@ __global__ void k_losses(const float *__restrict__ sse, int G, int B, VvIntG is_
 }
 
 // ---- Adam (torch.optim.Adam, amsgrad=False, maximize=False): train.py:376
+// blockIdx.y = slot: the same [0, n) range of every slot, slot_stride floats apart (0: one flat range)
 __global__ void k_adam(float *__restrict__ p, const float *__restrict__ g, float *__restrict__ m, float *__restrict__ v, long long n,
-                       float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                       long long slot_stride, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
     vv_pdl_wait();
+    { const long long o = blockIdx.y * slot_stride; p += o; g += o; m += o; v += o; }
     long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * 4;
     if (i + 3 < n) {
         float4 pp = *reinterpret_cast<float4 *>(p + i);
@@ -1203,8 +1205,25 @@ extern "C" int vecvad_adam_step(float *params, const float *grads, float *exp_av
     double bc1 = 1.0 - pow((double)beta1, (double)step);
     double bc2 = 1.0 - pow((double)beta2, (double)step);
     long long nthr = (n + 3) / 4;
-    vv_launch(k_adam, dim3(vv_cdiv(nthr, 256)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay,
-                                                               (float)bc1, (float)sqrt(bc2), grad_scale);
+    vv_launch(k_adam, dim3(vv_cdiv(nthr, 256)), dim3(256), 0, (cudaStream_t)stream, params, grads, exp_avg, exp_avg_sq, n, 0LL, lr, beta1, beta2, eps,
+              weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
+    VV_CKL();
+    return 0;
+}
+
+// the same update on [begin, end) of every one of n_slots slots (the gradient phases of vecvad_net_grad_phase_ranges)
+extern "C" int vecvad_adam_step_ranges(float *params, const float *grads, float *exp_avg, float *exp_avg_sq, int n_slots, int64_t slot_stride,
+                                       int64_t begin, int64_t end, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                                       float grad_scale, vecvad_stream stream) {
+    VV_REQUIRE(params && grads && exp_avg && exp_avg_sq && n_slots >= 1 && step >= 1, "adam_ranges: bad arguments");
+    VV_REQUIRE(0 <= begin && begin < end && end <= slot_stride && begin % 4 == 0 && slot_stride % 4 == 0, "adam_ranges: bad range [%lld, %lld) of %lld",
+               (long long)begin, (long long)end, (long long)slot_stride);
+    VV_REQUIRE(((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16 == 0, "adam_ranges: buffers must be 16-byte aligned");
+    VV_REQUIRE(n_slots <= 65535, "adam_ranges: too many slots");
+    const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+    const long long n = end - begin, nthr = (n + 3) / 4;
+    vv_launch(k_adam, dim3(vv_cdiv(nthr, 256), n_slots), dim3(256), 0, (cudaStream_t)stream, params + begin, grads + begin, exp_avg + begin,
+              exp_avg_sq + begin, (long long)n, (long long)slot_stride, lr, beta1, beta2, eps, weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale);
     VV_CKL();
     return 0;
 }

@@ -13,6 +13,7 @@ Two ways to train:
     on the device, no host synchronisation (the fast path ``bench.py`` measures).
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -189,6 +190,8 @@ class CompletionNet(nn.Module):
         self._pflat = torch.zeros(nslots * self._pstride)
         self._gflat = None
         self._phase_views = None
+        self._phase_ranges = None
+        self._tail_adam = os.environ.get('VECVAD_TAIL_ADAM', '1') != '0'
         self._sflat = torch.zeros(nslots * self._sstride)
         self._nbt = torch.zeros(nslots * _lib.N_UNITS, dtype=torch.long)
         self._init_reference_order()          # seeded-init parity with the reference constructors
@@ -381,6 +384,7 @@ class CompletionNet(nn.Module):
         self._nbt = nbt.long() if nbt.dtype != torch.long else nbt
         self._gflat = None
         self._phase_views = None
+        self._phase_ranges = None
         self._release_engine()
         self._rebind()
         return self
@@ -631,8 +635,21 @@ class CompletionNet(nn.Module):
                 _lib.check(L.vecvad_net_losses(part['net'], C.c_void_p(sse.data_ptr() + 4 * part['g0'] * B), B,
                                                C.c_void_p(part_losses.data_ptr() + 8 * i), _lib.cur_stream()), 'net_losses')
             torch.sum(part_losses, dim=0, out=losses)
-        self._run_backward(None, None)
+        # the backward leaves the side stream unjoined: phases 0 / 1 of the update run behind it while the last weight gradients and their
+        # scatter (phase 2, ~50 us of side-stream work after the last main-stream kernel) finish
+        tail = len(self._parts) == 1 and self._tail_adam
+        net0 = self._parts[0]['net']
+        if tail:
+            _lib.check(L.vecvad_net_defer_join(net0, 1), 'defer_join')
+        try:
+            self._run_backward(None, None)
+        finally:
+            if tail:
+                _lib.check(L.vecvad_net_defer_join(net0, 0), 'defer_join')
         scale = 1.0
+        if tail and reduce_grads is not None:
+            _lib.check(L.vecvad_net_grad_phase_wait(net0, 2, _lib.cur_stream()), 'grad_phase_wait')      # the exchange needs every gradient
+            tail = False
         if reduce_grads is not None:
             # a reducer with ``reduce_phased`` exchanges each gradient phase as soon as the backward has produced it (the rest of
             # the backward is still running); anything else gets the whole flat buffer once the backward is complete
@@ -642,9 +659,20 @@ class CompletionNet(nn.Module):
                 scale = float(reduce_grads(self._gflat))
         a = self._adam
         a['step'] += 1
-        _lib.check(L.vecvad_adam_step(_lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(a['m']), _lib.ptr(a['v']),
-                                      self._pflat.numel(), a['lr'], a['b1'], a['b2'], a['eps'], a['wd'], a['step'], scale,
-                                      _lib.cur_stream()), 'adam_step')
+        if tail:
+            if self._phase_ranges is None:
+                b, e = (C.c_int64 * 3)(), (C.c_int64 * 3)()
+                _lib.check(L.vecvad_net_grad_phase_ranges(net0, b, e), 'grad_phase_ranges')
+                self._phase_ranges = [(int(b[i]), int(e[i])) for i in range(3)]
+            for ph, (b0, e0) in enumerate(self._phase_ranges):                 # same stream: phase by phase, the join before the last
+                _lib.check(L.vecvad_net_grad_phase_wait(net0, ph, _lib.cur_stream()), 'grad_phase_wait')
+                _lib.check(L.vecvad_adam_step_ranges(_lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(a['m']), _lib.ptr(a['v']),
+                                                     len(self._slots), self._pstride, b0, e0, a['lr'], a['b1'], a['b2'], a['eps'], a['wd'],
+                                                     a['step'], scale, _lib.cur_stream()), 'adam_step_ranges')
+        else:
+            _lib.check(L.vecvad_adam_step(_lib.ptr(self._pflat), _lib.ptr(self._gflat), _lib.ptr(a['m']), _lib.ptr(a['v']),
+                                          self._pflat.numel(), a['lr'], a['b1'], a['b2'], a['eps'], a['wd'], a['step'], scale,
+                                          _lib.cur_stream()), 'adam_step')
         return losses
 
     def train_step_empty(self, reduce_grads):
