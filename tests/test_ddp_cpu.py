@@ -226,3 +226,61 @@ def test_phased_reduction_equals_whole_buffer_reduction():
         assert same, tag
         assert scale == scale_ref
         assert waited == [0, 1, 2]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# sharded optimiser step: reduce-scatter + Adam on 1/world + all-gather == all-reduce + Adam everywhere
+class _ShardStandIn:
+    """What GradReducer.sharded_step needs from CompletionNet, on CPU buffers, with a plain-torch Adam update of a flat range."""
+    def __init__(self, params, grads):
+        self.flat_params, self.flat_grads = params, grads
+        self.m, self.v, self.step = torch.zeros_like(params), torch.zeros_like(params), 1
+
+    def _adam_flat(self, off, n, scale, lr=1e-3, b1=0.9, b2=0.999, eps=1e-7):
+        sl = slice(off, off + n)
+        g = self.flat_grads[sl] * scale
+        self.m[sl] = b1 * self.m[sl] + (1 - b1) * g
+        self.v[sl] = b2 * self.v[sl] + (1 - b2) * g * g
+        self.flat_params[sl] -= (lr / (1 - b1 ** self.step)) * self.m[sl] / (self.v[sl].sqrt() / (1 - b2 ** self.step) ** 0.5 + eps)
+
+
+def _worker_sharded(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    ddp.init_from_env('gloo')
+    g = torch.Generator().manual_seed(3)
+    params = torch.randn(128, generator=g)                              # identical on every rank (broadcast_state in real runs)
+    grads = torch.randn(128, generator=torch.Generator().manual_seed(50 + rank))
+    out = {}
+    for tag, local_n, global_n in (('even', 4, 8), ('ragged', 3 if rank == 0 else 2, 5)):
+        a = _ShardStandIn(params.clone(), grads.clone())
+        red = ddp.GradReducer(shard_optimizer=True)
+        red.set_batch(local_n, global_n)
+        red.sharded_step(a)
+        b = _ShardStandIn(params.clone(), grads.clone())
+        ref = ddp.GradReducer()
+        ref.set_batch(local_n, global_n)
+        b._adam_flat(0, 128, ref(b.flat_grads))
+        gathered = [torch.empty(128) for _ in range(world)]
+        dist.all_gather(gathered, a.flat_params)
+        out[tag] = (float((a.flat_params - b.flat_params).abs().max()), all(torch.equal(gathered[0], t) for t in gathered))
+    if rank == 0:
+        ret.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_optimizer_step_equals_replicated_step():
+    ctx = mp.get_context('spawn')
+    ret = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_sharded, args=(r, 2, port, ret)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for tag in ('even', 'ragged'):
+        diff, identical = out[tag]
+        assert diff < 1e-6, (tag, diff)          # same update as all-reduce + Adam on every rank ...
+        assert identical, tag                    # ... and bit-identical parameters on all ranks afterwards

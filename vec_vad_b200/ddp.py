@@ -94,12 +94,16 @@ class GradReducer:
     collective's SM time is paid either way (2.61 ms overlapped vs 2.60 ms after the backward, 2.46 ms on one GPU) -- and wins
     only when the collective is throttled to few CTAs (NCCL_MAX_CTAS <= 16); hence off by default."""
 
-    def __init__(self, group=None, bucket_bytes=0, overlap=False):
+    def __init__(self, group=None, bucket_bytes=0, overlap=False, shard_optimizer=False):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.bucket_elems = bucket_bytes // 4
         self.pre_weight = None
         self.overlap = overlap
+        # sharded optimiser step (``sharded_step``): same bytes on the wire as the all-reduce (reduce-scatter + all-gather), but every
+        # rank runs Adam on 1/world of the parameters instead of all of them
+        self.shard_optimizer = bool(shard_optimizer) and self.world > 1
         self._comm = None                 # side stream the phase exchanges are queued behind (created on first use)
 
     def set_batch(self, local_n, global_n):
@@ -116,6 +120,25 @@ class GradReducer:
             flat.mul_(pre)
         scale = 1.0 / self.world if pre is None else 1.0
         return self._sum(flat, scale)
+
+    def sharded_step(self, model):
+        """The optimiser step of a data-parallel rank without replicating Adam: sum-reduce-scatter of the flat gradient buffer (each
+        rank ends up with the summed gradients of ITS contiguous 1/world of the buffer, in place), Adam on that shard with
+        grad_scale 1/world, all-gather of the updated parameters (in place).  ``model``: CompletionNet (flat_params / flat_grads /
+        _adam_flat); its ``_adam['step']`` is already incremented.  The flat buffers are a multiple of 64 floats per slot, so they
+        split evenly over 2 / 4 / 8 ranks.  Every rank's parameters are bit-identical afterwards (they all receive the same shards)."""
+        flat_g, flat_p = model.flat_grads, model.flat_params
+        n = flat_g.numel()
+        if n % self.world:
+            raise RuntimeError('sharded_step: %d parameters do not split over %d ranks' % (n, self.world))
+        shard = n // self.world
+        lo = self.rank * shard
+        pre = self.pre_weight
+        if pre is not None:
+            flat_g.mul_(pre)
+        dist.reduce_scatter_tensor(flat_g[lo:lo + shard], flat_g, group=self.group)
+        model._adam_flat(lo, shard, 1.0 / self.world if pre is None else 1.0)
+        dist.all_gather_into_tensor(flat_p, flat_p[lo:lo + shard], group=self.group)
 
     def reduce_phased(self, model):
         """Called by ``CompletionNet.train_step`` right after the (asynchronous) backward was queued: exchange every gradient

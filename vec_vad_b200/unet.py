@@ -650,6 +650,11 @@ class CompletionNet(nn.Module):
         if tail and reduce_grads is not None:
             _lib.check(L.vecvad_net_grad_phase_wait(net0, 2, _lib.cur_stream()), 'grad_phase_wait')      # the exchange needs every gradient
             tail = False
+        if reduce_grads is not None and getattr(reduce_grads, 'shard_optimizer', False):
+            # reduce-scatter of the gradients, Adam on this rank's 1/world of the parameters, all-gather of the parameters
+            self._adam['step'] += 1
+            reduce_grads.sharded_step(self)
+            return losses
         if reduce_grads is not None:
             # a reducer with ``reduce_phased`` exchanges each gradient phase as soon as the backward has produced it (the rest of
             # the backward is still running); anything else gets the whole flat buffer once the backward is complete
@@ -675,6 +680,13 @@ class CompletionNet(nn.Module):
                                           _lib.cur_stream()), 'adam_step')
         return losses
 
+    def _adam_flat(self, off, n, scale):
+        """torch.optim.Adam's update (train.py:376) on floats [off, off + n) of the flat buffers, current stream."""
+        a = self._adam
+        _lib.check(_lib.lib().vecvad_adam_step(C.c_void_p(self._pflat.data_ptr() + 4 * off), C.c_void_p(self._gflat.data_ptr() + 4 * off),
+                                               C.c_void_p(a['m'].data_ptr() + 4 * off), C.c_void_p(a['v'].data_ptr() + 4 * off), n, a['lr'],
+                                               a['b1'], a['b2'], a['eps'], a['wd'], a['step'], scale, _lib.cur_stream()), 'adam_step')
+
     def train_step_empty(self, reduce_grads):
         """A data-parallel step for a rank whose share of a ragged last batch is EMPTY: no forward / backward, a zero gradient
         into the collective, then the same Adam update as every other rank (the replicas must stay identical).  BatchNorm
@@ -685,6 +697,10 @@ class CompletionNet(nn.Module):
         if self._gflat is None:
             self._gflat = torch.zeros_like(self._pflat)
         self._gflat.zero_()
+        if reduce_grads is not None and getattr(reduce_grads, 'shard_optimizer', False):
+            self._adam['step'] += 1
+            reduce_grads.sharded_step(self)
+            return torch.zeros(2, dtype=torch.float32, device=self._pflat.device)
         scale = float(reduce_grads(self._gflat)) if reduce_grads is not None else 1.0
         a = self._adam
         a['step'] += 1
