@@ -77,9 +77,10 @@ def test_phased_exchange_sums_every_gradient_once(prec):
         for step, (g2, g1) in enumerate(zip(grads, single)):
             g1 = g1.cpu()
             # both ranks computed the same gradient up to the order of their fp32 atomics, whose noise these ill-conditioned
-            # gradients amplify to ~1e-3 (tests/test_parity_b128_gpu.py): the sum is 2 g within 1e-2 ...
+            # gradients amplify to 1e-3 (fp32 tiles) .. 2e-2 (fp16 operands: measured 0.019) between two runs of the same step
+            # (tests/test_parity_b128_gpu.py): the sum is 2 g within 5e-2 ...
             err = (g2 - 2 * g1).norm() / (2 * g1).norm()
-            assert err < 1e-2, (overlap, step, float(err))
+            assert err < 5e-2, (overlap, step, float(err))
             # ... and no range was left un-summed or summed twice (relative error 0.5 / 1.0 in that range): range by range
             for lo in range(0, g1.numel(), 65536):
                 a, b = g2[lo:lo + 65536], 2 * g1[lo:lo + 65536]
