@@ -27,8 +27,8 @@ if REPO not in sys.path:
 # DRAM traffic of the contraction kernel classes over ONE train step (batch 128, 5raw1of): dram__bytes_read.sum + dram__bytes_write.sum
 # summed over the class's launches (k_igemm_flat + k_igemm_tc3, k_wgrad_flat + k_wgrad_tc2) in the per-launch ncu pass committed under
 # profiles/ (NCU_SOURCE; tabulated by profiles/step_table.py): {class: {operand type: (bytes per step, launches per step)}}
-NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': {'tf32': (1.876e9 + 0.604e9, 33), 'f16': (0.939e9 + 0.131e9, 33)},
-                           'wgrad_tcgen05': {'tf32': (1.924e9 + 0.002e9, 17), 'f16': (0.992e9 + 0.001e9, 17)}}
+NCU_DRAM_BYTES_PER_STEP = {'conv_dgrad_tcgen05': {'tf32': (1.876e9 + 0.604e9, 33), 'f16': (0.939e9 + 0.122e9, 33)},
+                           'wgrad_tcgen05': {'tf32': (1.924e9 + 0.002e9, 17), 'f16': (0.992e9 + 0.002e9, 17)}}
 NCU_SOURCE = 'profiles/r01_v5_step_metrics.csv (tf32), profiles/r02_f16_step_metrics.csv (f16)'
 
 METRIC = 'STCs/sec (train step, device-timed)'       # BASELINE.json's metric; both arms print the same string
