@@ -190,6 +190,8 @@ def broadcast_state(model, src=0, group=None):
     module from GPU 0 every step; here it is done once, the all-reduced gradients keep the replicas identical)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return
+    if hasattr(model, '_flush_nbt'):
+        model._flush_nbt()                  # step counters still pending on the host go into the buffer that is broadcast
     for t in (model._pflat, model._sflat, model._nbt):
         dist.broadcast(t, src=src, group=group)
 

@@ -194,6 +194,7 @@ class CompletionNet(nn.Module):
         self._tail_adam = os.environ.get('VECVAD_TAIL_ADAM', '1') != '0'
         self._sflat = torch.zeros(nslots * self._sstride)
         self._nbt = torch.zeros(nslots * _lib.N_UNITS, dtype=torch.long)
+        self._nbt_pending = 0
         self._init_reference_order()          # seeded-init parity with the reference constructors
         self._register_tree()
         # ---- engine state
@@ -373,6 +374,19 @@ class CompletionNet(nn.Module):
             else:
                 node._buffers[attr] = self._nbt[off]
 
+    def _flush_nbt(self):
+        if self._nbt_pending:
+            self._nbt += self._nbt_pending
+            self._nbt_pending = 0
+
+    def state_dict(self, *args, **kwargs):
+        self._flush_nbt()
+        return super().state_dict(*args, **kwargs)
+
+    def load_state_dict(self, state_dict, *args, **kwargs):
+        self._nbt_pending = 0                               # the loaded counters replace whatever was pending
+        return super().load_state_dict(state_dict, *args, **kwargs)
+
     def _apply(self, fn, recurse=True):
         # Move the flat buffers, then re-create the views: the default per-tensor _apply would break the aliasing.
         new_p = fn(self._pflat)
@@ -380,6 +394,7 @@ class CompletionNet(nn.Module):
             raise RuntimeError('vec_vad_b200: parameters are float32 (the engine computes conv tiles in TF32/FP32)')
         self._pflat = new_p.contiguous()
         self._sflat = fn(self._sflat).contiguous()
+        self._flush_nbt()
         nbt = fn(self._nbt)
         self._nbt = nbt.long() if nbt.dtype != torch.long else nbt
         self._gflat = None
@@ -458,6 +473,7 @@ class CompletionNet(nn.Module):
         with torch.no_grad():
             new._pflat.copy_(self._pflat)
             new._sflat.copy_(self._sflat)
+            self._flush_nbt()
             new._nbt.copy_(self._nbt)
         new.train(self.training)
         return new
@@ -555,7 +571,8 @@ class CompletionNet(nn.Module):
                                             float(lambda_raw), float(lambda_of), stream), 'net_forward')
         self._on_parts(fwd)
         if training:
-            self._nbt += 1                                  # BatchNorm2d.num_batches_tracked
+            self._nbt_pending += 1                          # BatchNorm2d.num_batches_tracked: counted on the host, written to the
+                                                            # buffers when somebody looks (state_dict / copy / move): no kernel per step
         self._keep = (x, xo)                                # inputs must outlive the asynchronous kernels
         return raw_out, of_out
 
