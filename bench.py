@@ -161,7 +161,7 @@ def measure_net(args, net, steps, warmup, with_e2e, sample_clocks):
         # NCCL sum over NVLink/NVSwitch, 1/world folded into Adam: one all-reduce of the flat buffer after the backward; --overlap:
         # each gradient phase (decoder / deepest encoder block / rest) is exchanged on a side stream as soon as it is final
         from vec_vad_b200 import ddp
-        reduce = ddp.GradReducer(overlap=args.overlap, shard_optimizer=args.shard_optimizer)
+        reduce = ddp.GradReducer(overlap=args.overlap, shard_optimizer=not (args.no_shard_optimizer or args.overlap))
 
     def step_dev(i):
         x, x_of = vd.cubes_to_device_tensors(dev_raw[i % P], dev_flow[i % P])
@@ -303,8 +303,8 @@ def run_ours(args):
                 'config': config_of(args.net, B, world, P),
                 'details': {'parallelism': 'dp%d' % world,
                             'grad_exchange': ('none' if world == 1 else 'three gradient phases exchanged while the backward runs' if args.overlap
-                                              else 'reduce-scatter, Adam on 1/N of the parameters, all-gather' if args.shard_optimizer
-                                              else 'one all-reduce after backward'),
+                                              else 'one all-reduce after backward, Adam on every rank' if args.no_shard_optimizer
+                                              else 'reduce-scatter after backward, Adam on 1/N of the parameters, all-gather of the parameters'),
                             'operands': ('fp32 SIMT' if args.simt else 'tcgen05 kind::%s operands, fp32 accumulation; BatchNorm, losses, 1x1 output '
                                          'conv and Adam in fp32' % args.precision),
                             'final_losses': m['final_loss']},
@@ -351,8 +351,8 @@ def main():
     ap.add_argument('--precision', default='f16', choices=['tf32', 'f16'], help='operand type of the tcgen05 tiles (fp32 accumulation either way)')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg')
     ap.add_argument('--no-secondary', action='store_true', help='skip the secondary workloads (5raw5of set, FlowNet2 ops)')
-    ap.add_argument('--shard-optimizer', action='store_true', help='N>1: reduce-scatter + Adam on 1/N of the parameters + all-gather instead of '
-                    'all-reduce + full Adam on every rank')
+    ap.add_argument('--no-shard-optimizer', action='store_true', help='N>1: all-reduce + full Adam on every rank instead of reduce-scatter + '
+                    'Adam on 1/N of the parameters + all-gather of the parameters')
     ap.add_argument('--overlap', action='store_true', help='N>1: exchange the three gradient phases while the backward runs instead of one '
                     'all-reduce after it (measured: no gain while the step saturates the SMs, profiles/r02_ddp_overlap_n2.txt)')
     args = ap.parse_args()

@@ -361,7 +361,7 @@ def train(cfg_path='config.cfg', use_tensor_cores=None):
             torch.distributed.barrier(group=slow_group)
     net = build_network(cfg, use_tensor_cores=use_tensor_cores).to(device)     # ONE instance shared by every block, like the reference
     ddp.broadcast_state(net)
-    reducer = ddp.GradReducer() if world > 1 else None
+    reducer = ddp.GradReducer(shard_optimizer=True) if world > 1 else None     # reduce-scatter, Adam on 1/world of the parameters, all-gather
     meters = (AverageMeter(), AverageMeter())
     if sh:
         n_frames = len(probe)
