@@ -2,7 +2,6 @@
 torch.nn.functional.conv2d in float64 on the CPU (the same op the reference calls: model/unet.py:10,13).
 use_tc: 0 = fp32 SIMT tiles, 1 = the tcgen05 tile the engine picks, 3 = flattened-sequence tiles, 4 = pair tiles, +16 = fp16 operands
 (kind::f16) instead of tf32.  Tolerances: fp32 tiles 1e-5 of the output range; tf32 / fp16 tiles 2e-3 (10-bit mantissa operands)."""
-import ctypes as C
 
 import numpy as np
 import pytest

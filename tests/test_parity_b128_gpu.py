@@ -28,7 +28,6 @@ import functools
 import json
 import os
 
-import numpy as np
 import pytest
 import torch
 

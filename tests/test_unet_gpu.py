@@ -3,7 +3,6 @@
 fresh seeded inputs.  Tolerances are stated per check; the north-star bar is fp32 MSE within 1e-4
 relative.  Both contraction paths are covered: fp32 SIMT tiles (tc=False) and tcgen05 tiles (tc=True).
 """
-import copy
 import os
 
 import numpy as np

@@ -17,7 +17,6 @@ stage boundary is one kernel, and there is no BatchNorm branch (with_bn=False is
 instantiates: flownet2.py:13, calc_optical_flow.py:15).  Inference only; no CPU path.
 """
 import ctypes as C
-import math
 
 import torch
 import torch.nn as nn

@@ -17,7 +17,6 @@ New, device side (the feed for >100k STC/s):
   * ``DeviceCubeStore`` -- all cubes of a block resident in HBM as uint8 (15 KB/STC) + fp32 flow,
     shuffled mini-batches gathered and converted on the device.
 """
-import ctypes as C
 import glob
 import os
 from collections import OrderedDict
