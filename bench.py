@@ -167,10 +167,12 @@ def measure_net(args, net, steps, warmup, with_e2e, sample_clocks):
         x, x_of = vd.cubes_to_device_tensors(dev_raw[i % P], dev_flow[i % P])
         model.train_step(x, x_of, 1.0, 1.0, losses=losses, reduce_grads=reduce)
 
+    feeder = vd.HostCubeFeeder(list(zip(host_raw, host_flow)), device=dev) if with_e2e else None
+
     def step_e2e(i):
-        raw = host_raw[i % P].to(dev, non_blocking=True)
-        fl = host_flow[i % P].to(dev, non_blocking=True)
-        x, x_of = vd.cubes_to_device_tensors(raw, fl)
+        # every step: one H2D copy of a batch of pinned host cubes (queued one batch ahead on the feeder's copy stream, so it
+        # overlaps the previous step) and one D2H read of the two losses (a host sync)
+        x, x_of = feeder.next()
         return model.train_step(x, x_of, 1.0, 1.0, reduce_grads=reduce).cpu()
 
     def barrier():

@@ -268,3 +268,17 @@ def test_full_batch_properties(tc):
     assert torch.equal(rp, r1[perm]) and torch.equal(op_, o1[perm])
     rr, _ = m.score(x[:1].expand(128, -1, -1, -1).contiguous(), x_of[:1].expand(128, -1, -1, -1).contiguous())
     assert torch.equal(rr, rr[:1].expand(128)) and torch.equal(rr[0], r1[0])
+
+
+def test_host_cube_feeder_hands_out_the_batches_in_order():
+    """HostCubeFeeder: batch i of a cycled list of pinned host batches, converted exactly like cubes_to_device_tensors, one copy ahead."""
+    from vec_vad_b200 import vad_datasets as vd
+    g = torch.Generator().manual_seed(9)
+    host = [(torch.randint(0, 256, (3, 5, 32, 32, 3), generator=g, dtype=torch.uint8).pin_memory(),
+             torch.randn((3, 1, 32, 32, 2), generator=g).pin_memory()) for _ in range(3)]
+    feeder = vd.HostCubeFeeder(host)
+    for i in range(7):                                       # more than one cycle
+        x, x_of = feeder.next()
+        raw, flow = host[i % 3]
+        wx, wo = vd.cubes_to_device_tensors(raw.cuda(), flow.cuda())
+        assert torch.equal(x, wx) and torch.equal(x_of, wo)

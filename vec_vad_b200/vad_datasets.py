@@ -461,3 +461,44 @@ class DeviceCubeStore:
             idx = idx.to(self.raw.device)
             x, x_of = cubes_to_device_tensors(self.raw.index_select(0, idx), self.flow.index_select(0, idx))
             yield x, x_of, int(idx.numel()), global_n
+
+
+class HostCubeFeeder:
+    """Mini-batches that live in HOST memory (pinned uint8 cubes + fp32 flow) -> float device tensors, one batch ahead.
+
+    For cube sets that are not kept resident in HBM (``DeviceCubeStore``), e.g. a block streamed from disk segment by segment
+    (train.py:293-299): ``next()`` hands out batch i -- whose host-to-device copy was queued on a copy stream while batch i-1 was
+    being trained on -- and immediately queues the copy of batch i+1, so the copy overlaps the step instead of preceding it.  The
+    uint8 -> float conversion (``cube_to_train_dataset`` + ``ToTensor``) runs on the consumer's stream as in ``cubes_to_device_tensors``.
+
+    batches: a sequence of ``(raw_u8 [B,T,S,S,3] uint8, flow [B,T_of,S,S,2] float32)`` host tensors, pinned for asynchronous copies;
+    it is cycled (``next()`` never ends; the caller decides how many steps an epoch has)."""
+
+    def __init__(self, batches, device='cuda'):
+        self.batches = list(batches)
+        if not self.batches:
+            raise ValueError('HostCubeFeeder needs at least one batch')
+        self.device = torch.device(device)
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self._i = 0
+        self._pending = None
+        self._queue()
+
+    def _queue(self):
+        raw, flow = self.batches[self._i % len(self.batches)]
+        self._i += 1
+        with torch.cuda.stream(self.copy_stream):
+            d_raw = raw.to(self.device, non_blocking=True)
+            d_flow = flow.to(self.device, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.copy_stream)
+        self._pending = (d_raw, d_flow, done)
+
+    def next(self):
+        d_raw, d_flow, done = self._pending
+        cur = torch.cuda.current_stream(self.device)
+        cur.wait_event(done)
+        d_raw.record_stream(cur)                 # allocated on the copy stream, consumed on the caller's
+        d_flow.record_stream(cur)
+        self._queue()                            # the next batch's copy overlaps the step the caller is about to run
+        return cubes_to_device_tensors(d_raw, d_flow)
