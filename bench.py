@@ -125,8 +125,9 @@ def run_reference(args):
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': 'STC/s', 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': config_of(args.net, batch, 1, args.pool),
-            'details': {'timing': 'host wall clock on rank 0 only (the CPU arm has no device): each step is one batch of the same workload'},
+            'config': config_of(args.net, batch, max(1, args.gpus), args.pool),      # the workload of the arm it stands beside (N x batch)
+            'details': {'timing': 'host wall clock on rank 0 only (the CPU arm has no device): each step is one batch of %d cubes of the same '
+                                  'workload, a bounded sample of the N-GPU global batch' % batch},
             'cpu_baseline': {'value': v, 'unit': 'STC/s', 'cores': threads, 'kind': 'port',
                              'sample': '%d train steps of batch %d (oracle port of model/unet.py + train.py:383-402, torch CPU fp32)' % (args.steps, batch)},
             'e2e': {'value': v, 'unit': 'STC/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
