@@ -284,6 +284,44 @@ def flow_secondary(pk):
     return rows
 
 
+def epoch_secondary(args):
+    """SURVEY.md section 8d's epoch-shaped run: the real UCSDped2 training-box count (31 089 STCs) resident in HBM as uint8 cubes,
+    one epoch of shuffled batches of 128 through DeviceCubeStore + train_step (243 steps, the last one ragged: 113 cubes)."""
+    import torch
+    from vec_vad_b200 import unet as vu, vad_datasets as vd
+    n = 31089
+    g = torch.Generator().manual_seed(7)
+    raw = torch.randint(0, 256, (n, 5, 32, 32, 3), generator=g, dtype=torch.uint8)
+    flow = torch.randn((n, 1, 32, 32, 2), generator=g)
+    store = vd.DeviceCubeStore(raw, flow)
+    kind, kw, _ = NET_KW['net4']
+    torch.manual_seed(0)
+    prec = 0 if args.simt else {'tf32': 1, 'f16': 2}[args.precision]
+    model = vu.SelfCompleteNet4(use_tensor_cores=prec, **kw).cuda().train()
+    model.init_adam(lr=1e-3, eps=1e-7)
+    losses = torch.zeros(2, device='cuda')
+
+    def epoch(seed):
+        steps = 0
+        for x, x_of in store.batches(args.batch, shuffle=True, generator=torch.Generator().manual_seed(seed)):
+            model.train_step(x, x_of, 1.0, 1.0, losses=losses)
+            steps += 1
+        return steps
+    epoch(0)                                             # warm-up epoch (workspace, allocator, both batch shapes)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    steps = epoch(1)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    del model, store
+    torch.cuda.empty_cache()
+    return {'workload': 'UCSDped2-shaped epoch: %d synthetic STCs resident in HBM, shuffled batches of %d through DeviceCubeStore + train_step '
+                        '(%d steps, ragged last batch)' % (n, args.batch, steps), 'metric': 'STCs/sec (one training epoch, device-timed)',
+            'value': n / (ms * 1e-3), 'unit': 'STC/s', 'ms_per_epoch': ms, 'steps': steps}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -325,6 +363,10 @@ def run_ours(args):
                         'value': B / (m2['ms_dev'] * 1e-3), 'unit': 'STC/s', 'ms_per_step': m2['ms_dev'], 'gpu_launches': m2['launches'],
                         'roofline': roofline_of(args, 'full', m2, pk, src),
                         'kernel_classes_ms_per_step': {k: round(v[0], 4) for k, v in m2['prof'].items() if v[2] > 0}})
+        try:
+            sec.append(epoch_secondary(args))
+        except Exception as e:
+            sec.append({'workload': 'UCSDped2-shaped epoch', 'error': repr(e)})
         try:
             sec += flow_secondary(pk)
         except Exception as e:                                  # the headline line must still print
