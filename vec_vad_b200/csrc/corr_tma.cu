@@ -112,14 +112,37 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_corr_fwd_tma(const __grid_cons
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
         }
+        // Epilogue through shared memory (the ring is idle now: every stage was consumed): a thread's 84 results belong to 21
+        // displacement planes x 4 scattered columns, so written directly they are 84 four-byte stores per thread; staged as
+        // [441 planes][64 columns] they leave as 16-byte stores covering whole 256-byte output rows.
+        asm volatile("bar.sync 1, 352;" ::: "memory");          // the eleven compute warps: nobody still reads the last stage
+        constexpr int OUT_LD = CTX + 4;                         // 68 floats: 16-byte aligned rows, the two tj of a warp on different banks
+        float *so = sm;
         if (active) {
             const float inv = 1.f / (float)p.C;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const int x = x0 + pp + 2 * (4 * q + k);
-                if (x < p.OW) {
+                const int xl = pp + 2 * (4 * q + k);
 #pragma unroll
-                    for (int i = 0; i < CD; i++) out[(((long long)n * p.OC + tj * CD + i) * p.OH + y) * p.OW + x] = acc[k][i] * inv;
+                for (int i = 0; i < CD; i++) so[(tj * CD + i) * OUT_LD + xl] = acc[k][i] * inv;
+            }
+        }
+        asm volatile("bar.sync 1, 352;" ::: "memory");
+        {
+            const long long plane = (long long)p.OH * p.OW;
+            float *o = out + (long long)n * p.OC * plane + (long long)y * p.OW + x0;
+            const bool vec = (p.OW % 4 == 0) && x0 + CTX <= p.OW;      // whole tile inside the row and 16-byte aligned
+            for (int e = t; e < CD * CD * (CTX / 4); e += 352) {
+                const int d = e / (CTX / 4), c4 = (e - d * (CTX / 4)) * 4;
+                const float4 v = *reinterpret_cast<const float4 *>(so + d * OUT_LD + c4);
+                float *dst = o + d * plane + c4;
+                if (vec) {
+                    *reinterpret_cast<float4 *>(dst) = v;
+                } else {
+                    if (x0 + c4 < p.OW) dst[0] = v.x;
+                    if (x0 + c4 + 1 < p.OW) dst[1] = v.y;
+                    if (x0 + c4 + 2 < p.OW) dst[2] = v.z;
+                    if (x0 + c4 + 3 < p.OW) dst[3] = v.w;
                 }
             }
         }
