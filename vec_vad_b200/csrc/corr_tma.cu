@@ -8,7 +8,7 @@
 // chunk of 8 channels, four TMA boxes into shared memory -- for each parity one 32-wide row of in1 and 21 rows (every
 // second image row, a TMA element stride) x 56 columns of in2, halo zero-filled by TMA -- through a 3-stage mbarrier ring
 // fed by a dedicated producer warp.  Compute threads are (tj, parity, quad): 4 output pixels x 21 ti = 84 accumulators,
-// operands fetched with 64/128-bit shared-memory loads (12 + 1 per channel for 84 FMAs).  Requires pad == max_displacement
+// operands fetched with 128-bit shared-memory loads (7 + 1 per channel for 84 FMAs).  Requires pad == max_displacement
 // (FlowNetC) so that box starts fall on 16-byte boundaries; other parameters use the kernels in flow_ops.cu.
 #include "tc_common.cuh"
 
@@ -45,7 +45,9 @@ __global__ void k_parity_split(const float *__restrict__ in, float *__restrict__
 __global__ void __launch_bounds__(C_THREADS, 1) k_corr_fwd_tma(const __grid_constant__ CUtensorMap tm1, const __grid_constant__ CUtensorMap tm2,
                                                                float *__restrict__ out, const CorrTmaParams p) {
     extern __shared__ uint8_t smem_raw[];
-    float *sm = (float *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    // aligned by an offset, not by an integer round trip: the pointer keeps its shared address space and the inner loop's operand
+    // fetches compile to LDS rather than generic LD
+    float *sm = (float *)(smem_raw + ((128u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 127u)) & 127u));
     uint64_t *full = (uint64_t *)(sm + C_STAGES * C_STAGE);
     uint64_t *empty = full + C_STAGES;
     const int x0 = blockIdx.x * CTX, y = blockIdx.y, n = blockIdx.z;
@@ -90,23 +92,26 @@ __global__ void __launch_bounds__(C_THREADS, 1) k_corr_fwd_tma(const __grid_cons
             const int s = ch % C_STAGES;
             mbar_wait(&full[s], (ch / C_STAGES) & 1);
             const float *st = sm + s * C_STAGE;
-            const float *f1 = st + pp * C_F1 + 4 * q, *f2 = st + 2 * C_F1 + pp * C_F2 + tj * C2H + 4 * q + 2;   // +2: box starts at h0 - 12
+            // the window a thread needs starts 2 floats into a 16-byte group (the box starts at h0 - 12, the window at h0 - 10): it reads
+            // the 28 floats from the aligned group on with seven 16-byte loads -- the eight q-lanes of a row then cover 128 contiguous
+            // bytes per load (one wavefront per row) where twelve 8-byte loads at a 16-byte stride used half of every wavefront
+            const float *f1 = st + pp * C_F1 + 4 * q, *f2 = st + 2 * C_F1 + pp * C_F2 + tj * C2H + 4 * q;
             if (active) {
 #pragma unroll
                 for (int c = 0; c < CCC; c++) {
                     const float4 av = *reinterpret_cast<const float4 *>(f1 + c * 32);
                     const float *row = f2 + c * CD * C2H;
-                    float bv[24];
+                    float bv[28];
 #pragma unroll
-                    for (int m = 0; m < 12; m++) {             // 8-byte aligned window
-                        float2 v = *reinterpret_cast<const float2 *>(row + 2 * m);
-                        bv[2 * m] = v.x; bv[2 * m + 1] = v.y;
+                    for (int m = 0; m < 7; m++) {
+                        const float4 v = *reinterpret_cast<const float4 *>(row + 4 * m);
+                        bv[4 * m] = v.x; bv[4 * m + 1] = v.y; bv[4 * m + 2] = v.z; bv[4 * m + 3] = v.w;
                     }
                     const float aa[4] = {av.x, av.y, av.z, av.w};
 #pragma unroll
                     for (int k = 0; k < 4; k++)
 #pragma unroll
-                        for (int i = 0; i < CD; i++) acc[k][i] = fmaf(aa[k], bv[k + i], acc[k][i]);
+                        for (int i = 0; i < CD; i++) acc[k][i] = fmaf(aa[k], bv[2 + k + i], acc[k][i]);
                 }
             }
             __syncwarp();

@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(FL_THREADS, 1) k_igemm_flat(const __grid_const
     constexpr int KSTEPS = F16 ? KS / 16 : KS / 8;           // MMAs per (tap, slab)
     constexpr int B_TAP = BN * ROWB;                         // one (tap, slab) weight tile
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *stage0 = (uint8_t *)(((uintptr_t)smem_raw + FL_GUARD + 1023) & ~(uintptr_t)1023);   // >= FL_GUARD bytes of ours in front
+    uint8_t *stage0 = smem_raw + FL_GUARD + vv_smem_pad(smem_raw + FL_GUARD, 1024);   // >= FL_GUARD bytes of ours in front
                                                              // stage (ring r, slot j) at stage0 + (r * spr + j) * stage_bytes
     uint8_t *b_stat = stage0 + 2 * p.spr * p.stage_bytes;
     uint8_t *stg_base = b_stat + 9 * p.kchunks * B_TAP;

@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) k_igemm_tc3(const __grid_consta
     constexpr int NBUF = (4 * BN <= 512) ? 2 : 1;              // accumulator double-buffering across pairs (BN = 128: all 512 TMEM columns)
     constexpr int TMEM_COLS = 2 * NBUF * BN < 32 ? 32 : 2 * NBUF * BN;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + vv_smem_pad(smem_raw, 1024);
     const int w_stage = p.stationary ? 0 : p.ndy * B_TAP;    // streamed weights lead each stage
     uint8_t *b_stat = smem + p.stages * p.stage_bytes;
     uint8_t *stg_base = b_stat + (p.stationary ? p.ntaps * p.kchunks * B_TAP : 0);

@@ -12,6 +12,9 @@ constexpr int BM = 128;            // pixels per MMA tile (TMEM lanes)
 constexpr int KS = 32;             // channels per smem row (128 bytes of fp32 / tf32)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// bytes to add to a shared-memory pointer to reach the next multiple of `align` (a power of two). Aligning by an offset rather than by
+// an integer round trip keeps the pointer in the shared address space, so the staged epilogues compile to LDS / STS, not generic LD / ST.
+__device__ __forceinline__ uint32_t vv_smem_pad(const void *p, uint32_t align) { return (align - (smem_u32(p) & (align - 1))) & (align - 1); }
 
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

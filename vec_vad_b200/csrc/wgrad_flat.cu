@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_flat(const __grid_constant__ C
     extern __shared__ uint8_t smem_raw[];
     // stage s: [activation box | slack][gradient box | slack]; the slack behind a box (>= WGF_GUARD bytes) is zeroed once and never
     // written by TMA: the slack of the activation box is the leading guard of the gradient box behind it
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + vv_smem_pad(smem_raw, 1024);
     const int a_span = p.stage_bytes - ((p.g_bytes + WGF_GUARD + 1023) / 1024 * 1024);      // activation box + slack
     uint8_t *tail = smem + p.stages * p.stage_bytes;
     uint64_t *full = (uint64_t *)tail, *empty = full + 8, *accum = empty + 8;

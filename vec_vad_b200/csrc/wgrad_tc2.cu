@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128, 1) k_wgrad_tc2(const __grid_constant__ CU
     constexpr int G_STAGE = NS * G_SLAB;
     constexpr int TMEM_COLS = (3 * NT <= 128) ? 128 : (3 * NT <= 256 ? 256 : 512);
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *smem = smem_raw + vv_smem_pad(smem_raw, 1024);
     uint8_t *g_ring = smem;                                       // [g_stages][NS][128 px][32 ch]
     uint8_t *a_ring = smem + p.g_stages * G_STAGE;                // [a_stages][rows][image][x][32 ch]  (+ one row_shift of slack)
     uint8_t *tail = a_ring + p.a_stages * p.a_bytes + 2 * p.row_shift;   // slack: M blocks 2/3 of the last stage read past its box
