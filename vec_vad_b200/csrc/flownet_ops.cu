@@ -21,7 +21,7 @@
 
 namespace {
 
-constexpr int FN_TM = 128, FN_KC = 16, FN_MAXTAPS = 49;
+constexpr int FN_TM = 128, FN_KC = 16;
 
 struct FnConv {
     const float *in;   long long in_bs;  int Cin, IH, IW;
@@ -31,28 +31,36 @@ struct FnConv {
     int GH, GW;                                          // pixel grid of this launch
     int o_mul, o_off_y, o_off_x;                         // output pixel = g * o_mul + o_off
     int i_mul;                                           // input pixel  = g * i_mul + tap offset
-    int ntaps;
-    signed char ty[FN_MAXTAPS], tx[FN_MAXTAPS];
+    // taps: t = ti * kw + tj, ti < kh, tj < kw, at input offset (ty0 + dty * ti, tx0 + dtx * tj).  A k x k convolution is
+    // (kh, kw, ty0, dty, tx0, dtx) = (k, k, -pad, 1, -pad, 1); an output-parity phase of the transposed conv is (2, 2, 0 or 1, -1, 0 or 1, -1)
+    int ntaps, kh, kw, ty0, dty, tx0, dtx;
+    unsigned m_taps, m_kw;                               // ceil(2^32 / ntaps), ceil(2^32 / kw): n / d = umulhi(n, m) for n < 2^16
     int B, act;                                          // act: LeakyReLU(0.1)
     int ksplit, kper;                                    // split-K: blockIdx.z handles k in [z * kper, (z + 1) * kper); kper % 16 == 0
     float *partial;                                      // ksplit > 1: raw partial sums [ksplit][Co][M], finished by k_fn_conv_finish
+    int w_vec, out_vec, part_vec;                        // 16-byte weight loads / output stores / partial-sum stores are legal
+    // phases == 4: the four output-parity phases of ConvTranspose2d(4, 2, 1) in ONE launch.  blockIdx.z = phase * ksplit + split;
+    // phase (py, px) = (ph >> 1, ph & 1) reads the weights w + ph * Co * K, starts its taps at (ty0, tx0) = (py, px) and writes the
+    // output pixels (2 gy + py, 2 gx + px)
+    int phases;
 };
 
+// TN = 128 keeps 64 accumulators a thread (8 pixels x 8 channels): 128 registers, two CTAs per SM
 template <int TN>
-__global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
+__global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_conv(const FnConv p) {
     constexpr int CN = TN / 16;                          // output channels per thread
     __shared__ __align__(16) float As[2][FN_KC][FN_TM + 4];
     __shared__ __align__(16) float Bs[2][FN_KC][TN + 4];
-    __shared__ signed char s_ty[FN_MAXTAPS], s_tx[FN_MAXTAPS];
     vv_pdl_wait();
     const int tid = threadIdx.x;
-    if (tid < p.ntaps) { s_ty[tid] = p.ty[tid]; s_tx[tid] = p.tx[tid]; }
     const int Kall = p.Cin * p.ntaps;
-    const int kbeg = blockIdx.z * p.kper, K = min(Kall, kbeg + p.kper);     // this CTA's share of the contraction
+    const int ph = p.phases > 1 ? blockIdx.z / p.ksplit : 0, zsplit = blockIdx.z - ph * p.ksplit;
+    const int py = p.phases > 1 ? ph >> 1 : 0, px = p.phases > 1 ? ph & 1 : 0;
+    const int kbeg = zsplit * p.kper, K = min(Kall, kbeg + p.kper);        // this CTA's share of the contraction
     const long long M = (long long)p.B * p.GH * p.GW;
     const long long m0 = (long long)blockIdx.x * FN_TM;
     const int n0 = blockIdx.y * TN;
-    // ---- loader roles.  A: thread owns pixel (tid % 128) and 8 consecutive k of the chunk; B: channel (tid / 4 ... ) and 4 k.
+    // ---- loader roles.  A: thread owns pixel (tid % 128) and 8 consecutive k of the chunk; B: a channel and TN / 16 consecutive k
     const int a_m = tid & 127, a_k0 = (tid >> 7) * 8;
     const long long am = m0 + a_m;
     const bool a_ok = am < M;
@@ -63,27 +71,45 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
         agy = r / p.GW; agx = r - agy * p.GW;
     }
     const float *a_base = p.in + (long long)ab * p.in_bs;
-    const int iy0 = agy * p.i_mul, ix0 = agx * p.i_mul;
-    const long long IHW = (long long)p.IH * p.IW;
-    constexpr int BPT = TN * FN_KC / 256;                // B elements per thread: 4 (TN = 64) or 1 (TN = 16)
+    const int iy0 = agy * p.i_mul + p.ty0 + py, ix0 = agx * p.i_mul + p.tx0 + px;
+    const int IHW = p.IH * p.IW;
+    const int row_adv = p.dty * p.IW - p.kw * p.dtx, ci_adv = IHW - p.kh * p.dty * p.IW;   // offset steps when tj / ti wrap
+    constexpr int BPT = TN * FN_KC / 256;                // B elements per thread: 8 (TN = 128) ... 1 (TN = 16)
     const int b_n = (tid * BPT) / FN_KC, b_k0 = (tid * BPT) % FN_KC;
     const bool b_ok = n0 + b_n < p.Co;
-    const float *b_base = p.w + (long long)(n0 + b_n) * Kall;
-    __syncthreads();                                     // tap tables visible
+    const float *b_base = p.w + ((long long)ph * p.Co + n0 + b_n) * Kall;
 
     float ra[8], rb[BPT];
     auto load = [&](int k0) {
+        // (ci, ti, tj) of the first k by two reciprocal multiplies, then the 8 consecutive k walk taps / rows / channels with running
+        // coordinates and a running offset: no table, no division
         int kg = k0 + a_k0;
-        int ci = kg / p.ntaps, t = kg - ci * p.ntaps;    // one division per chunk; the 8 consecutive k walk (ci, t) incrementally
+        const int ci = p.ntaps == 1 ? kg : (int)__umulhi((unsigned)kg, p.m_taps);
+        const int t = kg - ci * p.ntaps;
+        int ti = p.kw == 1 ? t : (int)__umulhi((unsigned)t, p.m_kw);
+        int tj = t - ti * p.kw;
+        int iy = iy0 + p.dty * ti, ix = ix0 + p.dtx * tj;
+        int off = ci * IHW + iy * p.IW + ix;
 #pragma unroll
         for (int j = 0; j < 8; j++, kg++) {
-            float v = 0.f;
-            if (a_ok && kg < K) {
-                const int iy = iy0 + s_ty[t], ix = ix0 + s_tx[t];
-                if (iy >= 0 && iy < p.IH && ix >= 0 && ix < p.IW) v = __ldg(a_base + ci * IHW + (long long)iy * p.IW + ix);
+            const bool ok = a_ok && kg < K && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
+            ra[j] = ok ? __ldg(a_base + off) : 0.f;
+            tj++; ix += p.dtx; off += p.dtx;
+            if (tj == p.kw) {
+                tj = 0; ix -= p.kw * p.dtx; iy += p.dty; off += row_adv; ti++;
+                if (ti == p.kh) { ti = 0; iy -= p.kh * p.dty; off += ci_adv; }
             }
-            ra[j] = v;
-            if (++t == p.ntaps) { t = 0; ci++; }
+        }
+        if constexpr (BPT >= 4) {
+            if (p.w_vec) {                                // K and every split boundary are multiples of 4: a group is all in or all out
+#pragma unroll
+                for (int j = 0; j < BPT; j += 4) {
+                    const int kb = k0 + b_k0 + j;
+                    const float4 v = (b_ok && kb < K) ? __ldg(reinterpret_cast<const float4 *>(b_base + kb)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    rb[j] = v.x; rb[j + 1] = v.y; rb[j + 2] = v.z; rb[j + 3] = v.w;
+                }
+                return;
+            }
         }
 #pragma unroll
         for (int j = 0; j < BPT; j++) {
@@ -118,7 +144,10 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
             float a[8], b[CN];
             *reinterpret_cast<float4 *>(a) = *reinterpret_cast<const float4 *>(&As[buf][k][4 * tm]);
             *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[buf][k][64 + 4 * tm]);
-            if constexpr (CN == 4) *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tn]);
+            if constexpr (CN == 8) {
+                *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][8 * tn]);
+                *reinterpret_cast<float4 *>(b + 4) = *reinterpret_cast<const float4 *>(&Bs[buf][k][8 * tn + 4]);
+            } else if constexpr (CN == 4) *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][4 * tn]);
             else if constexpr (CN == 2) *reinterpret_cast<float2 *>(b) = *reinterpret_cast<const float2 *>(&Bs[buf][k][2 * tn]);
             else b[0] = Bs[buf][k][tn];
 #pragma unroll
@@ -132,13 +161,45 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
             buf ^= 1;
         }
     }
-    // ---- epilogue: bias, LeakyReLU, NCHW store (a half-warp covers 64 consecutive pixels of a channel); split-K: raw partials
+    // ---- epilogue: bias, LeakyReLU, NCHW store; split-K: raw partials.  Whole groups of 4 pixels leave as one 16-byte store when
+    // the launch allows it (the 4 pixels then share an output row); otherwise a half-warp covers 64 consecutive pixels of a channel.
     const long long OHW = (long long)p.OH * p.OW;
+    const bool split = p.ksplit > 1;
+    if (split ? p.part_vec : p.out_vec) {
+#pragma unroll
+        for (int g = 0; g < 2; g++) {
+            const long long m = m0 + 64 * g + 4 * tm;
+            if (m >= M) continue;                         // M % 4 == 0: the group is whole
+            float *o;
+            if (split) o = p.partial + (long long)blockIdx.z * p.Co * M + m;
+            else {
+                const int b = (int)(m / ((long long)p.GH * p.GW));
+                const int r = (int)(m - (long long)b * p.GH * p.GW);
+                o = p.out + (long long)b * p.out_bs + r;  // o_mul == 1, no offset: the output plane is the pixel grid
+            }
+#pragma unroll
+            for (int j = 0; j < CN; j++) {
+                const int co = n0 + tn * CN + j;
+                if (co >= p.Co) continue;
+                float4 v = make_float4(acc[4 * g][j], acc[4 * g + 1][j], acc[4 * g + 2][j], acc[4 * g + 3][j]);
+                if (!split) {
+                    const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+                    v.x += bv; v.y += bv; v.z += bv; v.w += bv;
+                    if (p.act) {
+                        v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+                        v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+                    }
+                }
+                *reinterpret_cast<float4 *>(o + (long long)co * (split ? M : OHW)) = v;
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const long long m = m0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + i - 4);
         if (m >= M) continue;
-        if (p.ksplit > 1) {
+        if (split) {
 #pragma unroll
             for (int j = 0; j < CN; j++) {
                 const int co = n0 + tn * CN + j;
@@ -149,7 +210,7 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
         const int b = (int)(m / ((long long)p.GH * p.GW));
         const int r = (int)(m - (long long)b * p.GH * p.GW);
         const int gy = r / p.GW, gx = r - gy * p.GW;
-        float *o = p.out + (long long)b * p.out_bs + (long long)(gy * p.o_mul + p.o_off_y) * p.OW + (gx * p.o_mul + p.o_off_x);
+        float *o = p.out + (long long)b * p.out_bs + (long long)(gy * p.o_mul + p.o_off_y + py) * p.OW + (gx * p.o_mul + p.o_off_x + px);
 #pragma unroll
         for (int j = 0; j < CN; j++) {
             const int co = n0 + tn * CN + j;
@@ -165,47 +226,88 @@ __global__ void __launch_bounds__(256) k_fn_conv(const FnConv p) {
 // out = act(bias + sum over the splits of the partial sums)
 __global__ void k_fn_conv_finish(const FnConv p) {
     vv_pdl_wait();
-    const long long M = (long long)p.B * p.GH * p.GW, total = M * p.Co;
+    const long long M = (long long)p.B * p.GH * p.GW, per_phase = M * p.Co, total = per_phase * p.phases;
     const long long OHW = (long long)p.OH * p.OW;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int co = (int)(i / M);
-        const long long m = i - (long long)co * M;
+        const int ph = (int)(i / per_phase);
+        const long long r0 = i - ph * per_phase;
+        const int co = (int)(r0 / M);
+        const long long m = r0 - (long long)co * M;
         float v = p.bias ? __ldg(p.bias + co) : 0.f;
-        for (int z = 0; z < p.ksplit; z++) v += p.partial[((long long)z * p.Co + co) * M + m];
+        for (int z = 0; z < p.ksplit; z++) v += p.partial[((long long)(ph * p.ksplit + z) * p.Co + co) * M + m];
         if (p.act) v = v > 0.f ? v : 0.1f * v;
         const int b = (int)(m / ((long long)p.GH * p.GW));
         const int r = (int)(m - (long long)b * p.GH * p.GW);
         const int gy = r / p.GW, gx = r - gy * p.GW;
-        p.out[(long long)b * p.out_bs + co * OHW + (long long)(gy * p.o_mul + p.o_off_y) * p.OW + (gx * p.o_mul + p.o_off_x)] = v;
+        const int py = p.phases > 1 ? ph >> 1 : 0, px = p.phases > 1 ? ph & 1 : 0;
+        p.out[(long long)b * p.out_bs + co * OHW + (long long)(gy * p.o_mul + p.o_off_y + py) * p.OW + (gx * p.o_mul + p.o_off_x + px)] = v;
     }
 }
 
-// Launches with few CTAs (small images, deep layers: the contraction is long and the pixel grid tiny) split the contraction over
-// blockIdx.z so that ~4 CTAs per SM are in flight; the partial sums go through the caller's scratch buffer.
+// Tile width and split of the contraction, chosen by a small cost model (cycles on one SM slot, all shapes static per layer, so the
+// choice -- and with it the summation order -- is a function of the layer's shape alone):
+//   waves(ctas / (148 * CTAs per SM)) * k-chunks per CTA * cycles per chunk at the tile's measured FMA-pipe efficiency
+//   + for a split: the partial sums' trip through the scratch buffer and the finishing launch.
+// Wide tiles amortise the gather (one input element feeds TN channels) and the shared-memory reads (64 FMAs per four 16-byte reads
+// at TN = 128); narrow ones waste no columns on the 2- / 16- / 32-channel layers and quantise better on small pixel grids.
+struct FnPlan { int tn, ksplit; };
+FnPlan plan_conv(const FnConv &p, bool have_scratch, long long scratch_floats) {
+    static const int tns[4] = {16, 32, 64, 128}, occ[4] = {4, 3, 3, 2};
+    static const double eff[4] = {0.27, 0.36, 0.46, 0.62};
+    const long long M = (long long)p.B * p.GH * p.GW;
+    const int K = p.Cin * p.ntaps;
+    static int force = -1;                                // VECVAD_FN_TN=16|32|64|128 pins the tile width (measurement knob)
+    if (force < 0) { const char *e = getenv("VECVAD_FN_TN"); force = e ? atoi(e) : 0; }
+    FnPlan best = {64, 1};
+    double best_c = 1e300;
+    for (int v = 0; v < 4; v++) {
+        const int tn = tns[v];
+        if (force ? tn != force : (tn > 16 && p.Co <= tn / 2)) continue;       // a tile at most half full never wins
+        const long long base = (long long)vv_cdiv(M, FN_TM) * vv_cdiv(p.Co, tn) * p.phases;
+        const long long slots = 148LL * occ[v];
+        const double chunk = (double)FN_TM * tn * FN_KC * occ[v] / (128.0 * eff[v]);   // cycles per k-chunk with occ CTAs sharing the SM
+        const int max_split = have_scratch ? (K / 64 < 32 ? K / 64 : 32) : 1;
+        for (int ks = 1; ks <= (max_split < 1 ? 1 : max_split); ks++) {
+            if (ks > 1 && (long long)ks * p.phases * p.Co * M > scratch_floats) break;
+            const int kper = vv_cdiv(vv_cdiv(K, ks), FN_KC) * FN_KC;
+            const int eff_ks = vv_cdiv(K, kper);
+            if (eff_ks != ks) continue;
+            const long long waves = (base * ks + slots - 1) / slots;
+            double c = (double)waves * (kper / FN_KC) * chunk + 4000.0;        // + prologue / epilogue of a CTA
+            if (ks > 1) c += 8000.0 + 2.0 * ks * p.phases * p.Co * M * 4.0 / 1500.0;      // finishing launch + partials out and back (~3 TB/s)
+            if (c < best_c) { best_c = c; best.tn = tn; best.ksplit = ks; }
+        }
+    }
+    return best;
+}
+
 int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t st) {
     const long long M = (long long)p.B * p.GH * p.GW;
-    const int tn = p.Co <= 16 ? 16 : (p.Co <= 32 ? 32 : 64);   // channel tile: no wasted columns for the 2- / 16- / 32-channel layers
-    const long long base = (long long)vv_cdiv(M, FN_TM) * vv_cdiv(p.Co, tn);
     const int K = p.Cin * p.ntaps;
-    int ksplit = 1;
-    if (scratch && base < 296) {
-        ksplit = (int)(592 / base);
-        if (ksplit > K / 64) ksplit = K / 64;
-        while (ksplit > 1 && (long long)ksplit * p.Co * M > scratch_floats) ksplit--;
-        if (ksplit < 1) ksplit = 1;
-    }
+    VV_REQUIRE(K < 65536, "fn_conv: contraction of %d terms too long", K);
+    VV_REQUIRE((long long)p.Cin * p.IH * p.IW < (1LL << 31), "fn_conv: input image of %lld elements too large", (long long)p.Cin * p.IH * p.IW);
+    p.kh = p.ntaps / p.kw;
+    if (p.phases < 1) p.phases = 1;
+    p.m_taps = p.ntaps > 1 ? 0xFFFFFFFFu / (unsigned)p.ntaps + 1u : 0u;
+    p.m_kw = p.kw > 1 ? 0xFFFFFFFFu / (unsigned)p.kw + 1u : 0u;
+    const FnPlan plan = plan_conv(p, scratch != nullptr, scratch_floats);
+    const int tn = plan.tn, ksplit = plan.ksplit;
     p.ksplit = ksplit;
-    p.kper = ksplit > 1 ? vv_cdiv(vv_cdiv(K, ksplit), FN_KC) * FN_KC : ((K + FN_KC - 1) / FN_KC) * FN_KC;
-    if (ksplit > 1) p.ksplit = ksplit = vv_cdiv(K, p.kper);          // rounding kper up may leave the last split empty: drop it
+    p.kper = vv_cdiv(vv_cdiv(K, ksplit), FN_KC) * FN_KC;
     p.partial = scratch;
-    const dim3 grid(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, tn), ksplit);
+    p.w_vec = K % 4 == 0 && ((uintptr_t)p.w) % 16 == 0;
+    p.out_vec = p.o_mul == 1 && p.o_off_y == 0 && p.o_off_x == 0 && p.GW % 4 == 0 && p.OW == p.GW && p.OH == p.GH && ((uintptr_t)p.out) % 16 == 0 &&
+                p.out_bs % 4 == 0;
+    p.part_vec = M % 4 == 0 && ((uintptr_t)scratch) % 16 == 0;
+    const dim3 grid(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, tn), ksplit * p.phases);
     cudaError_t e = tn == 16   ? vv_launch(k_fn_conv<16>, grid, dim3(256), 0, st, p)
                     : tn == 32 ? vv_launch(k_fn_conv<32>, grid, dim3(256), 0, st, p)
-                               : vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p);
+                    : tn == 64 ? vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p)
+                               : vv_launch(k_fn_conv<128>, grid, dim3(256), 0, st, p);
     VV_CK(e);
     VV_CKL();
     if (ksplit > 1) {
-        const long long total = M * p.Co;
+        const long long total = M * p.Co * p.phases;
         VV_CK(vv_launch(k_fn_conv_finish, dim3((unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256)), dim3(256), 0, st, p));
         VV_CKL();
     }
@@ -299,9 +401,7 @@ extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_
     p.OH = (in_h + 2 * pad - ksize) / stride + 1; p.OW = (in_w + 2 * pad - ksize) / stride + 1;
     p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
     p.GH = p.OH; p.GW = p.OW; p.o_mul = 1; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = stride;
-    p.ntaps = ksize * ksize;
-    for (int ky = 0; ky < ksize; ky++)
-        for (int kx = 0; kx < ksize; kx++) { p.ty[ky * ksize + kx] = (signed char)(ky - pad); p.tx[ky * ksize + kx] = (signed char)(kx - pad); }
+    p.ntaps = ksize * ksize; p.kw = ksize; p.ty0 = -pad; p.dty = 1; p.tx0 = -pad; p.dtx = 1;
     p.B = batch; p.act = leaky;
     return launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
 }
@@ -313,26 +413,19 @@ extern "C" int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, i
                                      float *scratch, int64_t scratch_floats, vecvad_stream stream) {
     VV_REQUIRE(in && w_phases && out, "fn_deconv4x4s2: null pointer");
     VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_deconv4x4s2: bad shape");
-    for (int ph = 0; ph < 4; ph++) {
-        const int py = ph >> 1, px = ph & 1;
-        FnConv p;
-        memset(&p, 0, sizeof(p));
-        p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
-        p.w = w_phases + (long long)ph * c_out * c_in * 4; p.bias = bias;
-        p.OH = 2 * in_h; p.OW = 2 * in_w;
-        p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
-        p.GH = in_h; p.GW = in_w; p.o_mul = 2; p.o_off_y = py; p.o_off_x = px; p.i_mul = 1;
-        p.ntaps = 4;
-        // output row 2y + py receives input row y + dy through kernel row ky (oy = 2 iy - 1 + ky):
-        //   py = 0: (ky, dy) = (1, 0), (3, -1);   py = 1: (ky, dy) = (0, +1), (2, 0)
-        const int dys[2][2] = {{0, -1}, {1, 0}};
-        for (int a = 0; a < 2; a++)
-            for (int b = 0; b < 2; b++) { p.ty[a * 2 + b] = (signed char)dys[py][a]; p.tx[a * 2 + b] = (signed char)dys[px][b]; }
-        p.B = batch; p.act = leaky;
-        int r = launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
-        if (r) return r;
-    }
-    return 0;
+    FnConv p;
+    memset(&p, 0, sizeof(p));
+    p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
+    p.w = w_phases; p.bias = bias;
+    p.OH = 2 * in_h; p.OW = 2 * in_w;
+    p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
+    p.GH = in_h; p.GW = in_w; p.o_mul = 2; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = 1;
+    // output row 2y + py receives input row y + dy through kernel row ky (oy = 2 iy - 1 + ky):
+    //   py = 0: (ky, dy) = (1, 0), (3, -1);   py = 1: (ky, dy) = (0, +1), (2, 0)      -- dy = py - tap, likewise in x.
+    // All four phases run in one launch (FnConv::phases): the kernel adds (py, px) to the tap origin and to the output pixel.
+    p.ntaps = 4; p.kw = 2; p.ty0 = 0; p.dty = -1; p.tx0 = 0; p.dtx = -1; p.phases = 4;
+    p.B = batch; p.act = leaky;
+    return launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
 }
 
 // the kernel rows / columns that feed output parity 0 and 1, in tap order (see above): parity 0 -> k = 1, 3; parity 1 -> k = 0, 2
