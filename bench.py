@@ -309,17 +309,20 @@ def epoch_secondary(args):
         return steps
     epoch(0)                                             # warm-up epoch (workspace, allocator, both batch shapes)
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    steps = epoch(1)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    times = []
+    for seed in (1, 2):                                  # two timed epochs; the faster one is the value (the host issues ~100 launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)   # per step and a busy box shows there first)
+        e0.record()
+        steps = epoch(seed)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = min(times)
     del model, store
     torch.cuda.empty_cache()
     return {'workload': 'UCSDped2-shaped epoch: %d synthetic STCs resident in HBM, shuffled batches of %d through DeviceCubeStore + train_step '
                         '(%d steps, ragged last batch)' % (n, args.batch, steps), 'metric': 'STCs/sec (one training epoch, device-timed)',
-            'value': n / (ms * 1e-3), 'unit': 'STC/s', 'ms_per_epoch': ms, 'steps': steps}
+            'value': n / (ms * 1e-3), 'unit': 'STC/s', 'ms_per_epoch': ms, 'ms_per_epoch_all': times, 'steps': steps}
 
 
 def run_ours(args):

@@ -7,10 +7,11 @@
 // never executed: the producers write their channels straight into the concat buffer.
 //
 //   k_fn_conv<TN>   Conv2d (k in {1,3,5,7}, stride 1/2, pad (k-1)/2) and ConvTranspose2d(4, 2, 1) as ONE gather-GEMM:
-//                   out[b, co, gy*o_mul + o_off, ..] = bias[co] + sum_{ci, t} in[b, ci, gy*i_mul + ty[t], gx*i_mul + tx[t]] * w[co][ci*ntaps + t]
+//                   out[b, co, gy*o_mul + o_off, ..] = bias[co] + sum_{ci, t} in[b, ci, gy*i_mul + ty(t), gx*i_mul + tx(t)] * w[co][ci*ntaps + t]
 //                   (+ LeakyReLU(0.1), misc.py:25-26).  The transposed conv runs as its four output-parity phases, each a 2x2-tap
-//                   gather with the phase's weights re-laid out once at load time.  fp32 FMA tiles: 128 pixels x TN channels per
-//                   CTA, K staged through shared memory in chunks of 16 with a register prefetch of the next chunk.
+//                   gather with the phase's weights re-laid out once at load time, all four in one launch.  fp32 FMA tiles:
+//                   128 pixels x TN channels per CTA (TN = 16 ... 128, picked per layer shape by plan_conv), K staged through shared
+//                   memory in chunks of 16 with a register prefetch of the next chunk.
 //                   Arithmetic is exact fp32 (the reference runs these layers in fp32 cuDNN); summation order differs.
 //   k_fn_mean / k_fn_normalize   per-(image, colour) mean over both frames, (x - mean) / rgb_max, frames concatenated on channels
 //                   (flownet2.py:66-72).
