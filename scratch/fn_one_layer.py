@@ -8,6 +8,10 @@ SHAPES = [  # cin, cout, k, s, H, W
     (64, 128, 5, 2, 192, 256),
     (512, 512, 3, 1, 24, 32),
     (82, 16, 3, 1, 384, 512),
+    (12, 64, 7, 2, 384, 512),
+    (64, 64, 3, 2, 384, 512),
+    (194, 64, 3, 1, 96, 128),
+    (162, 32, 3, 1, 192, 256),
 ]
 once = len(sys.argv) > 1 and sys.argv[1] == 'once'
 dev = torch.device('cuda:0')

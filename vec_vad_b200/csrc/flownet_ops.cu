@@ -22,7 +22,7 @@
 
 namespace {
 
-constexpr int FN_TM = 128, FN_KC = 16;
+constexpr int FN_KC = 16;                             // granularity of a split of the contraction (every tile's chunk divides it)
 
 struct FnConv {
     const float *in;   long long in_bs;  int Cin, IH, IW;
@@ -46,12 +46,24 @@ struct FnConv {
     int phases;
 };
 
-// TN = 128 keeps 64 accumulators a thread (8 pixels x 8 channels): 128 registers, two CTAs per SM
-template <int TN>
-__global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_conv(const FnConv p) {
-    constexpr int CN = TN / 16;                          // output channels per thread
-    __shared__ __align__(16) float As[2][FN_KC][FN_TM + 4];
-    __shared__ __align__(16) float Bs[2][FN_KC][TN + 4];
+// One CTA of 256 threads computes TM pixels x TN channels; a thread owns 8 pixels (two groups of 4: 16-byte shared-memory reads and
+// 16-byte stores) x CN = TM * TN / 2048 channels.  The shapes in use (plan_conv picks one per layer):
+//   128 x 128, 256 x 64   8 x 8 accumulators: 64 FMAs per four 16-byte operand reads; two CTAs per SM
+//   128 x 64, 256 x 32    8 x 4
+//   512 x 16 (KC = 8)     8 x 4 for the 16-channel layers, where a 128-pixel tile would leave 8 FMAs per three operand reads
+//   128 x 32, 128 x 16    8 x 2, 8 x 1: small pixel grids of the narrow layers
+template <int TM, int TN, int KC>
+__global__ void __launch_bounds__(256, (TM * TN >= 16384 || TM >= 512) ? 2 : (TM * TN >= 8192 ? 3 : 4)) k_fn_conv(const FnConv p) {
+    constexpr int CN = TM * TN / 2048;                   // output channels per thread
+    constexpr int TMT = TM / 8;                          // threads along the pixels
+    constexpr int NPIX = TM > 256 ? TM / 256 : 1;        // loader: pixels per thread
+    constexpr int PIXT = TM / NPIX;                      // loader: pixels covered by one slice of threads
+    constexpr int KPT = KC / (256 / PIXT);               // loader: consecutive k per thread and pixel
+    constexpr int BPT = TN * KC >= 256 ? TN * KC / 256 : 1;   // weight elements per (loading) thread
+    static_assert(CN == 1 || CN == 2 || CN == 4 || CN == 8, "tile shape");
+    static_assert(KPT >= 1 && KPT * (256 / PIXT) == KC && FN_KC % KC == 0, "chunk shape");
+    __shared__ __align__(16) float As[2][KC][TM + 4];
+    __shared__ __align__(16) float Bs[2][KC][TN + 4];
     vv_pdl_wait();
     const int tid = threadIdx.x;
     const int Kall = p.Cin * p.ntaps;
@@ -59,46 +71,53 @@ __global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_
     const int py = p.phases > 1 ? ph >> 1 : 0, px = p.phases > 1 ? ph & 1 : 0;
     const int kbeg = zsplit * p.kper, K = min(Kall, kbeg + p.kper);        // this CTA's share of the contraction
     const long long M = (long long)p.B * p.GH * p.GW;
-    const long long m0 = (long long)blockIdx.x * FN_TM;
+    const long long m0 = (long long)blockIdx.x * TM;
     const int n0 = blockIdx.y * TN;
-    // ---- loader roles.  A: thread owns pixel (tid % 128) and 8 consecutive k of the chunk; B: a channel and TN / 16 consecutive k
-    const int a_m = tid & 127, a_k0 = (tid >> 7) * 8;
-    const long long am = m0 + a_m;
-    const bool a_ok = am < M;
-    int ab = 0, agy = 0, agx = 0;
-    if (a_ok) {
-        ab = (int)(am / ((long long)p.GH * p.GW));
-        const int r = (int)(am - (long long)ab * p.GH * p.GW);
-        agy = r / p.GW; agx = r - agy * p.GW;
+    // ---- loader roles.  A: thread owns NPIX pixels and KPT consecutive k of the chunk; B: a channel and BPT consecutive k
+    const int a_k0 = (tid / PIXT) * KPT;
+    const float *a_base[NPIX];                           // the pixel's own input position (tap offset (0, 0), channel 0)
+    int iy0[NPIX], ix0[NPIX];                            // a pixel beyond M fails every bounds check
+#pragma unroll
+    for (int q = 0; q < NPIX; q++) {
+        const long long am = m0 + (tid % PIXT) + q * PIXT;
+        a_base[q] = p.in; iy0[q] = 1 << 21; ix0[q] = 0;
+        if (am < M) {
+            const int ab = (int)(am / ((long long)p.GH * p.GW));
+            const int r = (int)(am - (long long)ab * p.GH * p.GW);
+            const int agy = r / p.GW, agx = r - agy * p.GW;
+            iy0[q] = agy * p.i_mul; ix0[q] = agx * p.i_mul;
+            a_base[q] = p.in + (long long)ab * p.in_bs + iy0[q] * p.IW + ix0[q];
+        }
     }
-    const float *a_base = p.in + (long long)ab * p.in_bs;
-    const int iy0 = agy * p.i_mul + p.ty0 + py, ix0 = agx * p.i_mul + p.tx0 + px;
     const int IHW = p.IH * p.IW;
     const int row_adv = p.dty * p.IW - p.kw * p.dtx, ci_adv = IHW - p.kh * p.dty * p.IW;   // offset steps when tj / ti wrap
-    constexpr int BPT = TN * FN_KC / 256;                // B elements per thread: 8 (TN = 128) ... 1 (TN = 16)
-    const int b_n = (tid * BPT) / FN_KC, b_k0 = (tid * BPT) % FN_KC;
-    const bool b_ok = n0 + b_n < p.Co;
+    const bool b_act = TN * KC >= 256 || tid < TN * KC;
+    const int b_n = (tid * BPT) / KC, b_k0 = (tid * BPT) % KC;
+    const bool b_ok = b_act && n0 + b_n < p.Co;
     const float *b_base = p.w + ((long long)ph * p.Co + n0 + b_n) * Kall;
 
-    float ra[8], rb[BPT];
+    float ra[NPIX][KPT], rb[BPT];
     auto load = [&](int k0) {
-        // (ci, ti, tj) of the first k by two reciprocal multiplies, then the 8 consecutive k walk taps / rows / channels with running
-        // coordinates and a running offset: no table, no division
+        // (ci, ti, tj) of the first k by two reciprocal multiplies, then the consecutive k walk taps / rows / channels with a running
+        // tap offset (dy, dx) and a running element offset: no table, no division; the walk is shared by the thread's pixels
         int kg = k0 + a_k0;
         const int ci = p.ntaps == 1 ? kg : (int)__umulhi((unsigned)kg, p.m_taps);
         const int t = kg - ci * p.ntaps;
         int ti = p.kw == 1 ? t : (int)__umulhi((unsigned)t, p.m_kw);
         int tj = t - ti * p.kw;
-        int iy = iy0 + p.dty * ti, ix = ix0 + p.dtx * tj;
-        int off = ci * IHW + iy * p.IW + ix;
+        int dy = p.ty0 + py + p.dty * ti, dx = p.tx0 + px + p.dtx * tj;
+        int off = ci * IHW + dy * p.IW + dx;
 #pragma unroll
-        for (int j = 0; j < 8; j++, kg++) {
-            const bool ok = a_ok && kg < K && (unsigned)iy < (unsigned)p.IH && (unsigned)ix < (unsigned)p.IW;
-            ra[j] = ok ? __ldg(a_base + off) : 0.f;
-            tj++; ix += p.dtx; off += p.dtx;
+        for (int j = 0; j < KPT; j++, kg++) {
+#pragma unroll
+            for (int q = 0; q < NPIX; q++) {
+                const bool ok = kg < K && (unsigned)(iy0[q] + dy) < (unsigned)p.IH && (unsigned)(ix0[q] + dx) < (unsigned)p.IW;
+                ra[q][j] = ok ? __ldg(a_base[q] + off) : 0.f;
+            }
+            tj++; dx += p.dtx; off += p.dtx;
             if (tj == p.kw) {
-                tj = 0; ix -= p.kw * p.dtx; iy += p.dty; off += row_adv; ti++;
-                if (ti == p.kh) { ti = 0; iy -= p.kh * p.dty; off += ci_adv; }
+                tj = 0; dx -= p.kw * p.dtx; dy += p.dty; off += row_adv; ti++;
+                if (ti == p.kh) { ti = 0; dy -= p.kh * p.dty; off += ci_adv; }
             }
         }
         if constexpr (BPT >= 4) {
@@ -120,13 +139,17 @@ __global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_
     };
     auto stage = [&](int buf) {
 #pragma unroll
-        for (int j = 0; j < 8; j++) As[buf][a_k0 + j][a_m] = ra[j];
+        for (int q = 0; q < NPIX; q++)
 #pragma unroll
-        for (int j = 0; j < BPT; j++) Bs[buf][b_k0 + j][b_n] = rb[j];
+            for (int j = 0; j < KPT; j++) As[buf][a_k0 + j][(tid % PIXT) + q * PIXT] = ra[q][j];
+        if (b_act) {
+#pragma unroll
+            for (int j = 0; j < BPT; j++) Bs[buf][b_k0 + j][b_n] = rb[j];
+        }
     };
-    // ---- compute roles: 16 x 16 threads, thread (tm, tn) owns pixels 4 tm .. 4 tm + 3 and 64 + 4 tm .. + 3 (two 16-byte shared-memory
-    // reads per k instead of eight scalar ones) and channels tn * CN + j
-    const int tm = tid & 15, tn = tid >> 4;
+    // ---- compute roles: TM / 8 x (256 / (TM / 8)) threads, thread (tm, tn) owns pixels 4 tm .. 4 tm + 3 and TM / 2 + 4 tm .. + 3 (two
+    // 16-byte shared-memory reads per k instead of eight scalar ones) and channels tn * CN + j
+    const int tm = tid % TMT, tn = tid / TMT;
     float acc[8][CN];
 #pragma unroll
     for (int i = 0; i < 8; i++)
@@ -137,14 +160,14 @@ __global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_
     stage(0);
     __syncthreads();
     int buf = 0;
-    for (int k0 = kbeg; k0 < K; k0 += FN_KC) {
-        const bool more = k0 + FN_KC < K;
-        if (more) load(k0 + FN_KC);                       // global loads of the next chunk in flight during the FMAs
+    for (int k0 = kbeg; k0 < K; k0 += KC) {
+        const bool more = k0 + KC < K;
+        if (more) load(k0 + KC);                          // global loads of the next chunk in flight during the FMAs
 #pragma unroll
-        for (int k = 0; k < FN_KC; k++) {
+        for (int k = 0; k < KC; k++) {
             float a[8], b[CN];
             *reinterpret_cast<float4 *>(a) = *reinterpret_cast<const float4 *>(&As[buf][k][4 * tm]);
-            *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[buf][k][64 + 4 * tm]);
+            *reinterpret_cast<float4 *>(a + 4) = *reinterpret_cast<const float4 *>(&As[buf][k][TM / 2 + 4 * tm]);
             if constexpr (CN == 8) {
                 *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&Bs[buf][k][8 * tn]);
                 *reinterpret_cast<float4 *>(b + 4) = *reinterpret_cast<const float4 *>(&Bs[buf][k][8 * tn + 4]);
@@ -163,13 +186,13 @@ __global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_
         }
     }
     // ---- epilogue: bias, LeakyReLU, NCHW store; split-K: raw partials.  Whole groups of 4 pixels leave as one 16-byte store when
-    // the launch allows it (the 4 pixels then share an output row); otherwise a half-warp covers 64 consecutive pixels of a channel.
+    // the launch allows it (the 4 pixels then share an output row); otherwise consecutive lanes cover consecutive pixel groups.
     const long long OHW = (long long)p.OH * p.OW;
     const bool split = p.ksplit > 1;
     if (split ? p.part_vec : p.out_vec) {
 #pragma unroll
         for (int g = 0; g < 2; g++) {
-            const long long m = m0 + 64 * g + 4 * tm;
+            const long long m = m0 + (TM / 2) * g + 4 * tm;
             if (m >= M) continue;                         // M % 4 == 0: the group is whole
             float *o;
             if (split) o = p.partial + (long long)blockIdx.z * p.Co * M + m;
@@ -198,7 +221,7 @@ __global__ void __launch_bounds__(256, TN == 128 ? 2 : (TN == 64 ? 3 : 4)) k_fn_
     }
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        const long long m = m0 + (i < 4 ? 4 * tm + i : 64 + 4 * tm + i - 4);
+        const long long m = m0 + (i < 4 ? 4 * tm + i : TM / 2 + 4 * tm + i - 4);
         if (m >= M) continue;
         if (split) {
 #pragma unroll
@@ -245,38 +268,40 @@ __global__ void k_fn_conv_finish(const FnConv p) {
     }
 }
 
-// Tile width and split of the contraction, chosen by a small cost model (cycles on one SM slot, all shapes static per layer, so the
-// choice -- and with it the summation order -- is a function of the layer's shape alone):
-//   waves(ctas / (148 * CTAs per SM)) * k-chunks per CTA * cycles per chunk at the tile's measured FMA-pipe efficiency
-//   + for a split: the partial sums' trip through the scratch buffer and the finishing launch.
-// Wide tiles amortise the gather (one input element feeds TN channels) and the shared-memory reads (64 FMAs per four 16-byte reads
-// at TN = 128); narrow ones waste no columns on the 2- / 16- / 32-channel layers and quantise better on small pixel grids.
-struct FnPlan { int tn, ksplit; };
+// Tile shape and split of the contraction, chosen by a small cost model (all shapes static per layer, so the choice -- and with it
+// the summation order -- is a function of the layer's shape alone):
+//   cycles = CTAs on the busiest SM x FMAs per CTA / (128 lanes x the tile's measured FMA-pipe efficiency)
+//            + for a split: the partial sums' trip through the scratch buffer and the finishing launch.
+// The efficiencies are fitted to isolated-layer timings of every tile on eight FlowNet2 layer shapes
+// (profiles/r02_fn_conv_tiles.txt).  Wide tiles amortise the gather (one input element feeds TN channels) and the shared-memory reads
+// (64 FMAs per four 16-byte reads with 8 x 8 accumulators); narrow ones waste no columns on the 2- / 16- / 32-channel layers; short
+// ones quantise better on small pixel grids.
+struct FnTileInfo { int tm, tn, occ; double eff; };
+const FnTileInfo FN_TILES[] = {{128, 16, 4, 0.18}, {128, 32, 4, 0.33}, {128, 64, 3, 0.48}, {128, 128, 2, 0.53},
+                               {256, 64, 2, 0.49}, {256, 32, 3, 0.48}, {512, 16, 2, 0.36}};
+constexpr int FN_NTILES = sizeof(FN_TILES) / sizeof(FN_TILES[0]);
+struct FnPlan { int tile, ksplit; };
 FnPlan plan_conv(const FnConv &p, bool have_scratch, long long scratch_floats) {
-    static const int tns[4] = {16, 32, 64, 128}, occ[4] = {4, 3, 3, 2};
-    static const double eff[4] = {0.27, 0.36, 0.46, 0.62};
     const long long M = (long long)p.B * p.GH * p.GW;
     const int K = p.Cin * p.ntaps;
-    static int force = -1;                                // VECVAD_FN_TN=16|32|64|128 pins the tile width (measurement knob)
-    if (force < 0) { const char *e = getenv("VECVAD_FN_TN"); force = e ? atoi(e) : 0; }
-    FnPlan best = {64, 1};
+    static int force = -2;                                // VECVAD_FN_TILE=0..6 pins the tile shape (measurement knob)
+    if (force < -1) { const char *e = getenv("VECVAD_FN_TILE"); force = e ? atoi(e) : -1; }
+    FnPlan best = {2, 1};
     double best_c = 1e300;
-    for (int v = 0; v < 4; v++) {
-        const int tn = tns[v];
-        if (force ? tn != force : (tn > 16 && p.Co <= tn / 2)) continue;       // a tile at most half full never wins
-        const long long base = (long long)vv_cdiv(M, FN_TM) * vv_cdiv(p.Co, tn) * p.phases;
-        const long long slots = 148LL * occ[v];
-        const double chunk = (double)FN_TM * tn * FN_KC * occ[v] / (128.0 * eff[v]);   // cycles per k-chunk with occ CTAs sharing the SM
+    for (int v = 0; v < FN_NTILES; v++) {
+        const FnTileInfo &t = FN_TILES[v];
+        if (force >= 0 ? v != force : (t.tn > 16 && p.Co <= t.tn / 2)) continue;   // a tile at most half full never wins
+        const long long base = (long long)vv_cdiv(M, t.tm) * vv_cdiv(p.Co, t.tn) * p.phases;
         const int max_split = have_scratch ? (K / 64 < 32 ? K / 64 : 32) : 1;
         for (int ks = 1; ks <= (max_split < 1 ? 1 : max_split); ks++) {
             if (ks > 1 && (long long)ks * p.phases * p.Co * M > scratch_floats) break;
             const int kper = vv_cdiv(vv_cdiv(K, ks), FN_KC) * FN_KC;
-            const int eff_ks = vv_cdiv(K, kper);
-            if (eff_ks != ks) continue;
-            const long long waves = (base * ks + slots - 1) / slots;
-            double c = (double)waves * (kper / FN_KC) * chunk + 4000.0;        // + prologue / epilogue of a CTA
-            if (ks > 1) c += 8000.0 + 2.0 * ks * p.phases * p.Co * M * 4.0 / 1500.0;      // finishing launch + partials out and back (~3 TB/s)
-            if (c < best_c) { best_c = c; best.tn = tn; best.ksplit = ks; }
+            if (vv_cdiv(K, kper) != ks) continue;          // rounding kper up left the last split empty: same as a smaller ks
+            const long long per_sm = (base * ks + 147) / 148;
+            const double fill = per_sm >= t.occ ? 1.0 : 0.6 + 0.4 * (double)per_sm / t.occ;   // fewer resident warps hide less latency
+            double c = (double)per_sm * t.tm * t.tn * kper / (128.0 * t.eff * fill) + 4000.0;  // + prologue / epilogue of a CTA
+            if (ks > 1) c += 8000.0 + 2.0 * ks * p.phases * p.Co * M * 4.0 / 1500.0;   // finishing launch + partials out and back (~3 TB/s)
+            if (c < best_c) { best_c = c; best.tile = v; best.ksplit = ks; }
         }
     }
     return best;
@@ -292,7 +317,8 @@ int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t
     p.m_taps = p.ntaps > 1 ? 0xFFFFFFFFu / (unsigned)p.ntaps + 1u : 0u;
     p.m_kw = p.kw > 1 ? 0xFFFFFFFFu / (unsigned)p.kw + 1u : 0u;
     const FnPlan plan = plan_conv(p, scratch != nullptr, scratch_floats);
-    const int tn = plan.tn, ksplit = plan.ksplit;
+    const FnTileInfo &t = FN_TILES[plan.tile];
+    const int ksplit = plan.ksplit;
     p.ksplit = ksplit;
     p.kper = vv_cdiv(vv_cdiv(K, ksplit), FN_KC) * FN_KC;
     p.partial = scratch;
@@ -300,11 +326,17 @@ int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t
     p.out_vec = p.o_mul == 1 && p.o_off_y == 0 && p.o_off_x == 0 && p.GW % 4 == 0 && p.OW == p.GW && p.OH == p.GH && ((uintptr_t)p.out) % 16 == 0 &&
                 p.out_bs % 4 == 0;
     p.part_vec = M % 4 == 0 && ((uintptr_t)scratch) % 16 == 0;
-    const dim3 grid(vv_cdiv(M, FN_TM), vv_cdiv(p.Co, tn), ksplit * p.phases);
-    cudaError_t e = tn == 16   ? vv_launch(k_fn_conv<16>, grid, dim3(256), 0, st, p)
-                    : tn == 32 ? vv_launch(k_fn_conv<32>, grid, dim3(256), 0, st, p)
-                    : tn == 64 ? vv_launch(k_fn_conv<64>, grid, dim3(256), 0, st, p)
-                               : vv_launch(k_fn_conv<128>, grid, dim3(256), 0, st, p);
+    const dim3 grid(vv_cdiv(M, t.tm), vv_cdiv(p.Co, t.tn), ksplit * p.phases);
+    cudaError_t e;
+    switch (plan.tile) {
+        case 0: e = vv_launch(k_fn_conv<128, 16, 16>, grid, dim3(256), 0, st, p); break;
+        case 1: e = vv_launch(k_fn_conv<128, 32, 16>, grid, dim3(256), 0, st, p); break;
+        case 2: e = vv_launch(k_fn_conv<128, 64, 16>, grid, dim3(256), 0, st, p); break;
+        case 3: e = vv_launch(k_fn_conv<128, 128, 16>, grid, dim3(256), 0, st, p); break;
+        case 4: e = vv_launch(k_fn_conv<256, 64, 16>, grid, dim3(256), 0, st, p); break;
+        case 5: e = vv_launch(k_fn_conv<256, 32, 16>, grid, dim3(256), 0, st, p); break;
+        default: e = vv_launch(k_fn_conv<512, 16, 8>, grid, dim3(256), 0, st, p); break;
+    }
     VV_CK(e);
     VV_CKL();
     if (ksplit > 1) {
