@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VECVAD_ABI_VERSION 7
+#define VECVAD_ABI_VERSION 8
 #define VECVAD_MAX_UNETS 10   /* 5 raw + 5 flow (SelfCompleteNetFull, model/unet.py:270-408) */
 #define VECVAD_N_UNITS 14     /* conv3x3+BN+ReLU units per UNet (model/unet.py:187-196) */
 #define VECVAD_N_UPS 3        /* ConvTranspose2d per UNet (model/unet.py:54) */
@@ -261,7 +261,10 @@ int vecvad_convt3x3s2_wgrad(const float *in, const float *grad_out, int ld, int 
  * fn_upsample4     nn.Upsample(scale_factor=4, mode = 0 'bilinear' (align_corners False) | 1 'nearest'), times mul.
  * fn_scale_copy    out slice = mul * in slice, then LeakyReLU(leaky_slope) if leaky_slope >= 0.
  * scratch (fn_conv2d / fn_deconv4x4s2): caller-owned device floats (may be NULL): launches whose pixel grid is too small to fill the
- *                  GPU split the contraction over more CTAs and pass their partial sums through it (used size <= scratch_floats). */
+ *                  GPU split the contraction over more CTAs and pass their partial sums through it (used size <= scratch_floats).
+ * fn_conv_plan     host only, no launch: the CTA tile (pixels x channels) and the split of the contraction that fn_conv2d
+ *                  (transposed = 0) or fn_deconv4x4s2 (transposed = 1; ksize / stride ignored) uses for this shape with a scratch
+ *                  buffer of scratch_floats floats (0: none).  A function of the arguments alone -- so is the summation order. */
 int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias, float *out,
                      int64_t out_batch_stride, int c_out, int ksize, int stride, int leaky, int batch, float *scratch,
                      int64_t scratch_floats, vecvad_stream stream);
@@ -269,6 +272,8 @@ int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, int c_in, in
                           float *out, int64_t out_batch_stride, int c_out, int leaky, int batch, float *scratch, int64_t scratch_floats,
                           vecvad_stream stream);
 int vecvad_fn_deconv_taps(int *k_of_parity_tap);
+int vecvad_fn_conv_plan(int c_in, int in_h, int in_w, int c_out, int ksize, int stride, int transposed, int batch, int64_t scratch_floats,
+                        int *tile_pixels, int *tile_channels, int *ksplit);
 int vecvad_fn_normalize_pair(const float *ims, float *x, double *scratch, int batch, int height, int width, float rgb_max, vecvad_stream stream);
 int vecvad_fn_upsample4(const float *in, int64_t in_batch_stride, int channels, int h, int w, float *out, int64_t out_batch_stride, int mode,
                         float mul, int batch, vecvad_stream stream);

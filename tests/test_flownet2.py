@@ -54,9 +54,48 @@ def _views():
     return fn
 
 
+# (cin, cout, k, stride, h, w, leaky) at batch 2.  Small grids, ragged sizes (scalar epilogue, part-filled tiles) and shapes large
+# enough that the planner (csrc/flownet_ops.cu plan_conv) leaves the 128-pixel tiles: together they use every tile shape, which
+# test_conv_plan_covers_every_tile_shape keeps true.
+CONV_CASES = [(3, 64, 7, 2, 64, 96, 1), (12, 64, 7, 2, 32, 64, 1), (64, 128, 5, 2, 24, 40, 1), (37, 50, 3, 1, 19, 23, 1),
+              (256, 32, 1, 1, 8, 12, 1), (130, 2, 3, 1, 16, 16, 0), (16, 16, 3, 2, 33, 31, 0), (82, 16, 3, 1, 40, 24, 0),
+              (20, 16, 3, 1, 160, 192, 1), (20, 13, 3, 1, 157, 191, 0), (24, 32, 3, 1, 128, 160, 1), (40, 70, 3, 1, 61, 67, 1),
+              (24, 130, 3, 1, 90, 131, 1), (32, 128, 3, 1, 64, 96, 0), (30, 60, 3, 1, 50, 77, 1)]
+ALL_TILES = {(128, 16), (128, 32), (128, 64), (128, 128), (256, 64), (256, 32), (512, 16)}
+
+
+def _plan(cin, h, w, cout, k, s, transposed, batch, scratch_floats):
+    import ctypes as C
+    from vec_vad_b200 import _lib
+    tm, tn, ks = C.c_int(), C.c_int(), C.c_int()
+    _lib.check(_lib.lib().vecvad_fn_conv_plan(cin, h, w, cout, k, s, transposed, batch, scratch_floats, C.byref(tm), C.byref(tn), C.byref(ks)),
+               'fn_conv_plan')
+    return tm.value, tn.value, ks.value
+
+
+def test_conv_plan_covers_every_tile_shape():
+    """Host-only: the plan is a function of the shape alone, respects the scratch bound, and the GPU cases above reach every tile."""
+    scratch = 16 << 20                                                          # flownet2._scratch's default: 64 MB
+    used = set()
+    for cin, cout, k, s, h, w, _ in CONV_CASES:
+        tm, tn, ks = _plan(cin, h, w, cout, k, s, 0, 2, scratch)
+        assert (tm, tn, ks) == _plan(cin, h, w, cout, k, s, 0, 2, scratch)
+        assert (tm, tn) in ALL_TILES and 1 <= ks <= 32
+        oh, ow = (h + 2 * ((k - 1) // 2) - k) // s + 1, (w + 2 * ((k - 1) // 2) - k) // s + 1
+        assert ks == 1 or ks * cout * 2 * oh * ow <= scratch
+        assert _plan(cin, h, w, cout, k, s, 0, 2, 0)[2] == 1                     # no scratch buffer, no split
+        used.add((tm, tn))
+    assert used == ALL_TILES, sorted(ALL_TILES - used)
+    tm, tn, ks = _plan(770, 24, 32, 128, 4, 2, 1, 1, scratch)                    # a transposed conv of FlowNetS: four phases, one plan
+    assert (tm, tn) in ALL_TILES and ks * 4 * 128 * 24 * 32 <= scratch
+    from vec_vad_b200 import _lib
+    import ctypes as C
+    z = C.c_int()
+    assert _lib.lib().vecvad_fn_conv_plan(8, 8, 8, 8, 4, 1, 0, 1, 0, C.byref(z), C.byref(z), C.byref(z)) != 0   # kernel size 4 is no Conv2d here
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize('cin,cout,k,s,h,w,leaky', [(3, 64, 7, 2, 64, 96, 1), (12, 64, 7, 2, 32, 64, 1), (64, 128, 5, 2, 24, 40, 1), (37, 50, 3, 1, 19, 23, 1),
-                                                    (256, 32, 1, 1, 8, 12, 1), (130, 2, 3, 1, 16, 16, 0), (16, 16, 3, 2, 33, 31, 0), (82, 16, 3, 1, 40, 24, 0)])
+@pytest.mark.parametrize('cin,cout,k,s,h,w,leaky', CONV_CASES)
 def test_conv2d_kernel_matches_torch(cin, cout, k, s, h, w, leaky):
     fn = _views()
     g = torch.Generator().manual_seed(cin * 131 + cout)

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(_HERE, 'libvecvad.so')
 MAX_UNETS = 10
 N_UNITS = 14
 N_UPS = 3
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # every symbol include/vecvad.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
@@ -27,7 +27,7 @@ SYMBOLS = [
     'vecvad_net_debug_read', 'vecvad_conv3x3_forward', 'vecvad_conv3x3_wgrad', 'vecvad_conv3x3_dgrad',
     'vecvad_convt3x3s2_forward', 'vecvad_convt3x3s2_dgrad', 'vecvad_convt3x3s2_wgrad', 'vecvad_cubes_to_tensors',
     'vecvad_crop_resize',
-    'vecvad_fn_conv2d', 'vecvad_fn_deconv4x4s2', 'vecvad_fn_deconv_taps', 'vecvad_fn_normalize_pair', 'vecvad_fn_upsample4', 'vecvad_fn_scale_copy',
+    'vecvad_fn_conv2d', 'vecvad_fn_deconv4x4s2', 'vecvad_fn_deconv_taps', 'vecvad_fn_conv_plan', 'vecvad_fn_normalize_pair', 'vecvad_fn_upsample4', 'vecvad_fn_scale_copy',
 ]
 
 
@@ -99,6 +99,7 @@ def lib():
     L.vecvad_fn_conv2d.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, i, i, p, i64, p]
     L.vecvad_fn_deconv4x4s2.argtypes = [p, i64, i, i, i, p, p, p, i64, i, i, i, p, i64, p]
     L.vecvad_fn_deconv_taps.argtypes = [ip]
+    L.vecvad_fn_conv_plan.argtypes = [i, i, i, i, i, i, i, i, i64, ip, ip, ip]
     L.vecvad_fn_normalize_pair.argtypes = [p, p, p, i, i, i, f, p]
     L.vecvad_fn_upsample4.argtypes = [p, i64, i, i, i, p, i64, i, f, i, p]
     L.vecvad_fn_scale_copy.argtypes = [p, i64, p, i64, i64, f, f, i, p]

@@ -417,6 +417,32 @@ __global__ void k_fn_scale_copy(const float *__restrict__ in, long long in_bs, f
     }
 }
 
+// the launch description of a Conv2d / of the four fused phases of a ConvTranspose2d(4, 2, 1), minus pointers
+FnConv describe_conv(int c_in, int in_h, int in_w, int c_out, int ksize, int stride, int batch) {
+    const int pad = (ksize - 1) / 2;
+    FnConv p;
+    memset(&p, 0, sizeof(p));
+    p.Cin = c_in; p.IH = in_h; p.IW = in_w; p.Co = c_out;
+    p.OH = (in_h + 2 * pad - ksize) / stride + 1; p.OW = (in_w + 2 * pad - ksize) / stride + 1;
+    p.GH = p.OH; p.GW = p.OW; p.o_mul = 1; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = stride;
+    p.ntaps = ksize * ksize; p.kw = ksize; p.ty0 = -pad; p.dty = 1; p.tx0 = -pad; p.dtx = 1;
+    p.B = batch; p.phases = 1;
+    return p;
+}
+FnConv describe_deconv(int c_in, int in_h, int in_w, int c_out, int batch) {
+    FnConv p;
+    memset(&p, 0, sizeof(p));
+    p.Cin = c_in; p.IH = in_h; p.IW = in_w; p.Co = c_out;
+    p.OH = 2 * in_h; p.OW = 2 * in_w;
+    p.GH = in_h; p.GW = in_w; p.o_mul = 2; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = 1;
+    // output row 2y + py receives input row y + dy through kernel row ky (oy = 2 iy - 1 + ky):
+    //   py = 0: (ky, dy) = (1, 0), (3, -1);   py = 1: (ky, dy) = (0, +1), (2, 0)      -- dy = py - tap, likewise in x.
+    // All four phases run in one launch (FnConv::phases): the kernel adds (py, px) to the tap origin and to the output pixel.
+    p.ntaps = 4; p.kw = 2; p.ty0 = 0; p.dty = -1; p.tx0 = 0; p.dtx = -1; p.phases = 4;
+    p.B = batch;
+    return p;
+}
+
 }  // namespace
 
 extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_in, int in_h, int in_w, const float *w, const float *bias,
@@ -426,16 +452,8 @@ extern "C" int vecvad_fn_conv2d(const float *in, int64_t in_batch_stride, int c_
     VV_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "fn_conv2d: kernel size %d not in {1,3,5,7}", ksize);
     VV_REQUIRE(stride == 1 || stride == 2, "fn_conv2d: stride %d not in {1,2}", stride);
     VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_conv2d: bad shape");
-    const int pad = (ksize - 1) / 2;
-    FnConv p;
-    memset(&p, 0, sizeof(p));
-    p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
-    p.w = w; p.bias = bias;
-    p.OH = (in_h + 2 * pad - ksize) / stride + 1; p.OW = (in_w + 2 * pad - ksize) / stride + 1;
-    p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
-    p.GH = p.OH; p.GW = p.OW; p.o_mul = 1; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = stride;
-    p.ntaps = ksize * ksize; p.kw = ksize; p.ty0 = -pad; p.dty = 1; p.tx0 = -pad; p.dtx = 1;
-    p.B = batch; p.act = leaky;
+    FnConv p = describe_conv(c_in, in_h, in_w, c_out, ksize, stride, batch);
+    p.in = in; p.in_bs = in_batch_stride; p.w = w; p.bias = bias; p.out = out; p.out_bs = out_batch_stride; p.act = leaky;
     return launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
 }
 
@@ -446,19 +464,23 @@ extern "C" int vecvad_fn_deconv4x4s2(const float *in, int64_t in_batch_stride, i
                                      float *scratch, int64_t scratch_floats, vecvad_stream stream) {
     VV_REQUIRE(in && w_phases && out, "fn_deconv4x4s2: null pointer");
     VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_deconv4x4s2: bad shape");
-    FnConv p;
-    memset(&p, 0, sizeof(p));
-    p.in = in; p.in_bs = in_batch_stride; p.Cin = c_in; p.IH = in_h; p.IW = in_w;
-    p.w = w_phases; p.bias = bias;
-    p.OH = 2 * in_h; p.OW = 2 * in_w;
-    p.out = out; p.out_bs = out_batch_stride; p.Co = c_out;
-    p.GH = in_h; p.GW = in_w; p.o_mul = 2; p.o_off_y = 0; p.o_off_x = 0; p.i_mul = 1;
-    // output row 2y + py receives input row y + dy through kernel row ky (oy = 2 iy - 1 + ky):
-    //   py = 0: (ky, dy) = (1, 0), (3, -1);   py = 1: (ky, dy) = (0, +1), (2, 0)      -- dy = py - tap, likewise in x.
-    // All four phases run in one launch (FnConv::phases): the kernel adds (py, px) to the tap origin and to the output pixel.
-    p.ntaps = 4; p.kw = 2; p.ty0 = 0; p.dty = -1; p.tx0 = 0; p.dtx = -1; p.phases = 4;
-    p.B = batch; p.act = leaky;
+    FnConv p = describe_deconv(c_in, in_h, in_w, c_out, batch);
+    p.in = in; p.in_bs = in_batch_stride; p.w = w_phases; p.bias = bias; p.out = out; p.out_bs = out_batch_stride; p.act = leaky;
     return launch_conv(p, scratch, scratch_floats, (cudaStream_t)stream);
+}
+
+extern "C" int vecvad_fn_conv_plan(int c_in, int in_h, int in_w, int c_out, int ksize, int stride, int transposed, int batch,
+                                   int64_t scratch_floats, int *tile_pixels, int *tile_channels, int *ksplit) {
+    VV_REQUIRE(tile_pixels && tile_channels && ksplit, "fn_conv_plan: null pointer");
+    VV_REQUIRE(batch >= 1 && c_in >= 1 && c_out >= 1 && in_h >= 1 && in_w >= 1, "fn_conv_plan: bad shape");
+    if (!transposed) {
+        VV_REQUIRE(ksize == 1 || ksize == 3 || ksize == 5 || ksize == 7, "fn_conv_plan: kernel size %d not in {1,3,5,7}", ksize);
+        VV_REQUIRE(stride == 1 || stride == 2, "fn_conv_plan: stride %d not in {1,2}", stride);
+    }
+    const FnConv p = transposed ? describe_deconv(c_in, in_h, in_w, c_out, batch) : describe_conv(c_in, in_h, in_w, c_out, ksize, stride, batch);
+    const FnPlan plan = plan_conv(p, scratch_floats > 0, scratch_floats);
+    *tile_pixels = FN_TILES[plan.tile].tm; *tile_channels = FN_TILES[plan.tile].tn; *ksplit = plan.ksplit;
+    return 0;
 }
 
 // the kernel rows / columns that feed output parity 0 and 1, in tap order (see above): parity 0 -> k = 1, 3; parity 1 -> k = 0, 2

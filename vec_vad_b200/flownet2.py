@@ -17,6 +17,7 @@ stage boundary is one kernel, and there is no BatchNorm branch (with_bn=False is
 instantiates: flownet2.py:13, calc_optical_flow.py:15).  Inference only; no CPU path.
 """
 import ctypes as C
+import os
 
 import torch
 import torch.nn as nn
@@ -150,11 +151,13 @@ _SCRATCH = {}
 
 
 def _scratch(device):
-    """Split-K partial sums of the layers whose pixel grid is too small to fill the GPU (csrc/flownet_ops.cu launch_conv): one
-    16 MB buffer per device, reused by every layer (all launches are ordered on the caller's stream)."""
+    """Partial sums of the layers whose contraction is split over CTAs (csrc/flownet_ops.cu plan_conv): one 64 MB buffer per
+    device (VECVAD_FN_SCRATCH_MB), reused by every layer (all launches are ordered on the caller's stream).  Its size bounds the
+    splits plan_conv may choose, so it is part of what fixes the summation order."""
     key = (device.type, device.index)
     if key not in _SCRATCH:
-        _SCRATCH[key] = torch.empty(4 << 20, dtype=torch.float32, device=device)
+        mb = int(os.environ.get('VECVAD_FN_SCRATCH_MB', '64'))
+        _SCRATCH[key] = torch.empty(mb << 18, dtype=torch.float32, device=device)
     return _SCRATCH[key]
 
 
