@@ -268,6 +268,48 @@ __global__ void k_fn_conv_finish(const FnConv p) {
     }
 }
 
+// The same, four consecutive pixels per thread (M % 4 == 0, partial sums 16-byte aligned): 16-byte reads of the partial sums, several
+// splits' loads in flight, one 16-byte store where the output plane is the pixel grid.  Same order of additions as the scalar form.
+__global__ void k_fn_conv_finish4(const FnConv p) {
+    vv_pdl_wait();
+    const long long M = (long long)p.B * p.GH * p.GW, M4 = M / 4, per_phase = M4 * p.Co, total = per_phase * p.phases;
+    const long long OHW = (long long)p.OH * p.OW, GHW = (long long)p.GH * p.GW;
+    const long long zs = (long long)p.Co * M4;          // float4 stride between two splits
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int ph = (int)(i / per_phase);
+        const long long r0 = i - ph * per_phase;
+        const int co = (int)(r0 / M4);
+        const long long m = (r0 - (long long)co * M4) * 4;
+        const float bv = p.bias ? __ldg(p.bias + co) : 0.f;
+        float4 v = make_float4(bv, bv, bv, bv);
+        const float4 *src = reinterpret_cast<const float4 *>(p.partial + ((long long)ph * p.ksplit * p.Co + co) * M + m);
+#pragma unroll 4
+        for (int z = 0; z < p.ksplit; z++) {
+            const float4 t = src[z * zs];
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+        }
+        if (p.act) {
+            v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y;
+            v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w;
+        }
+        if (p.out_vec) {                                  // o_mul == 1, no offsets, GW % 4 == 0: the four pixels are contiguous in the output
+            const int b = (int)(m / GHW);
+            *reinterpret_cast<float4 *>(p.out + (long long)b * p.out_bs + co * OHW + (m - (long long)b * GHW)) = v;
+        } else {
+            const int py = p.phases > 1 ? ph >> 1 : 0, px = p.phases > 1 ? ph & 1 : 0;
+            const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const long long mq = m + q;
+                const int b = (int)(mq / GHW);
+                const int r = (int)(mq - (long long)b * GHW);
+                const int gy = r / p.GW, gx = r - gy * p.GW;
+                p.out[(long long)b * p.out_bs + co * OHW + (long long)(gy * p.o_mul + p.o_off_y + py) * p.OW + (gx * p.o_mul + p.o_off_x + px)] = e[q];
+            }
+        }
+    }
+}
+
 // Tile shape and split of the contraction, chosen by a small cost model (all shapes static per layer, so the choice -- and with it
 // the summation order -- is a function of the layer's shape alone):
 //   cycles = CTAs on the busiest SM x FMAs per CTA / (128 lanes x the tile's measured FMA-pipe efficiency)
@@ -340,8 +382,9 @@ int launch_conv(FnConv p, float *scratch, long long scratch_floats, cudaStream_t
     VV_CK(e);
     VV_CKL();
     if (ksplit > 1) {
-        const long long total = M * p.Co * p.phases;
-        VV_CK(vv_launch(k_fn_conv_finish, dim3((unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256)), dim3(256), 0, st, p));
+        const long long total = M * p.Co * p.phases / (p.part_vec ? 4 : 1);
+        const dim3 fgrid((unsigned)((total + 255) / 256 > 1184 ? 1184 : (total + 255) / 256));
+        VV_CK(p.part_vec ? vv_launch(k_fn_conv_finish4, fgrid, dim3(256), 0, st, p) : vv_launch(k_fn_conv_finish, fgrid, dim3(256), 0, st, p));
         VV_CKL();
     }
     return 0;
