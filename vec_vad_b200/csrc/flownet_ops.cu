@@ -328,6 +328,8 @@ FnPlan plan_conv(const FnConv &p, bool have_scratch, long long scratch_floats) {
     const int K = p.Cin * p.ntaps;
     static int force = -2;                                // VECVAD_FN_TILE=0..6 pins the tile shape (measurement knob)
     if (force < -1) { const char *e = getenv("VECVAD_FN_TILE"); force = e ? atoi(e) : -1; }
+    static double split_scale = -1.0;                     // VECVAD_FN_SPLIT_COST scales the modelled cost of a split (measurement knob)
+    if (split_scale < 0.0) { const char *e = getenv("VECVAD_FN_SPLIT_COST"); split_scale = e ? atof(e) : 1.0; }
     FnPlan best = {2, 1};
     double best_c = 1e300;
     for (int v = 0; v < FN_NTILES; v++) {
@@ -342,7 +344,7 @@ FnPlan plan_conv(const FnConv &p, bool have_scratch, long long scratch_floats) {
             const long long per_sm = (base * ks + 147) / 148;
             const double fill = per_sm >= t.occ ? 1.0 : 0.6 + 0.4 * (double)per_sm / t.occ;   // fewer resident warps hide less latency
             double c = (double)per_sm * t.tm * t.tn * kper / (128.0 * t.eff * fill) + 4000.0;  // + prologue / epilogue of a CTA
-            if (ks > 1) c += 8000.0 + 2.0 * ks * p.phases * p.Co * M * 4.0 / 1500.0;   // finishing launch + partials out and back (~3 TB/s)
+            if (ks > 1) c += split_scale * (8000.0 + 2.0 * ks * p.phases * p.Co * M * 4.0 / 1500.0);   // finishing launch + partials out and back
             if (c < best_c) { best_c = c; best.tile = v; best.ksplit = ks; }
         }
     }
