@@ -217,3 +217,38 @@ def test_calc_optical_flow_stage_writes_the_flow_modality(tmp_path, monkeypatch)
         ims = np.array([[cv2.resize(frames[pair[0]], (512, 384)), cv2.resize(frames[pair[1]], (512, 384))]]).transpose((0, 4, 1, 2, 3))
         want = cv2.resize(net(torch.from_numpy(ims.astype(np.float32)).cuda())[0].cpu().numpy().transpose((1, 2, 0)), (360, 240))
         assert np.allclose(saved, want, rtol=1e-4, atol=1e-4 * float(np.abs(want).max()))
+
+
+def test_calc_optical_flow_batched_writes_the_same_files(tmp_path, monkeypatch):
+    """Host logic of the optical-flow stage (calc_optical_flow.py:12-88) with a stand-in network on the CPU: grouping ``batch_pairs`` frame
+    pairs per network call writes the same files, in the same layout, as one pair per call -- including a ragged last group."""
+    import cv2
+    from tests import _synthetic_dataset as syn
+    from vec_vad_b200 import optical_flow as of, vad_datasets as vd
+    root = syn.make(str(tmp_path / 'ws'), n_train=(3, 2), n_test=(2,))
+    monkeypatch.chdir(root)
+
+    class PerImageNet(torch.nn.Module):                        # [B,3,2,384,512] -> [B,2,384,512], every image on its own
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.tensor([0.5, -0.25]))
+            self.calls = []
+
+        def forward(self, ims):
+            self.calls.append(ims.shape[0])
+            assert tuple(ims.shape[1:]) == (3, 2, 384, 512) and ims.dtype == torch.float32
+            d = (ims[:, :, 1] - ims[:, :, 0]).mean(1, keepdim=True) + ims[:, :, 0].mean(1, keepdim=True) * 0.01
+            return (d * self.w.view(1, 2, 1, 1)).detach()
+
+    ds = vd.unified_dataset_interface(dataset_name='UCSDped2', dir=os.path.join('raw_datasets', 'UCSDped2'), context_frame_num=1, mode='train',
+                                      border_mode='hard')
+    one, four = PerImageNet(), PerImageNet()
+    of.calc_optical_flow(ds, net=one, of_root_dir='./of_one', verbose=False)
+    of.calc_optical_flow(ds, net=four, of_root_dir='./of_four', verbose=False, batch_pairs=4)
+    assert one.calls == [1] * 5 and four.calls == [4, 1]
+    files = sorted(os.path.relpath(os.path.join(d, f), 'of_one') for d, _, fs in os.walk('of_one') for f in fs)
+    assert len(files) == 5 and files == sorted(os.path.relpath(os.path.join(d, f), 'of_four') for d, _, fs in os.walk('of_four') for f in fs)
+    frame = cv2.imread(ds.all_frame_addr[0])
+    for f in files:
+        a, b = np.load(os.path.join('of_one', f)), np.load(os.path.join('of_four', f))
+        assert a.shape == frame.shape[:2] + (2,) and a.dtype == np.float32 and np.array_equal(a, b) and np.abs(a).max() > 0
